@@ -1,0 +1,54 @@
+"""Generate tests/golden/kissfft_golden.npz from the UNMODIFIED vendored reference (oracle/_ref).
+
+Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+The fixtures let the GPU box and any machine without /root/reference check both the restated oracle and
+the CUDA path against outputs of the reference itself.  Inputs are regenerated from the seeds stored in
+the file, outputs are what kiss_fft()/kiss_fastfir() of the reference build returned.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+import oracle  # noqa: E402
+
+FFT_SIZES = [2, 4, 8, 16, 32, 64, 128, 240, 256, 512, 1000, 1024, 2048, 4096, 8192]
+SEED = 20261017
+
+
+def fft_input(n: int, seed: int = SEED) -> np.ndarray:
+    rng = np.random.default_rng(seed + n)
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def fastfir_case(seed: int = SEED):
+    rng = np.random.default_rng(seed)
+    h = (rng.standard_normal(300) + 1j * rng.standard_normal(300)).astype(np.complex64) / 16
+    x = (rng.standard_normal(6000) + 1j * rng.standard_normal(6000)).astype(np.complex64)
+    return h, x
+
+
+def main() -> None:
+    assert oracle.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    out = {"seed": np.int64(SEED), "fft_sizes": np.array(FFT_SIZES)}
+    for n in FFT_SIZES:
+        x = fft_input(n)
+        out[f"fwd_{n}"] = oracle.ref_kissfft(x, False)
+        out[f"inv_{n}"] = oracle.ref_kissfft(x, True)
+    h, x = fastfir_case()
+    out["fastfir_noflush"] = oracle.ref_fastfir(h, x, 0, False)     # nfft auto = 1024
+    out["fastfir_flush"] = oracle.ref_fastfir(h, x, 0, True)
+    # the one hard-coded golden vector of the reference tree: test/fft.py:95-98 (tolerance 1e-5, :104)
+    out["fftpy_tvec"] = np.array([0.309655, 0.815653, 0.768570, 0.591841, 0.404767, 0.637617, 0.007803, 0.012665],
+                                 dtype=np.float32)
+    out["fftpy_Ftvec"] = (np.array([3.548571, -0.378761, -0.061950, 0.188537, -0.566981, 0.188537, -0.061950, -0.378761])
+                          + 1j * np.array([0.0, -1.296198, -0.848764, 0.225337, 0.0, -0.225337, 0.848764, 1.296198]))
+    path = os.path.join(os.path.dirname(__file__), "kissfft_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
