@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric : Msamples/s of cf32 through the FIR-decimate + FFT chain (64-tap low-pass /10 -> 1024-pt Hann FFT ->
+         |X|^2 averaged over K=64 frames), absolute and as a fraction of the HBM roofline.
+step   : one pass of the fused chain kernel over one batch of synthetic cf32 samples resident in HBM:
+         65536 frames = 2^26 decimated samples into the FFT (configs[1]) = 671 088 694 input samples (5.4 GB),
+         much larger than the 126 MB L2, so no L2 flush is needed between steps.
+N > 1  : one process per GPU (torchrun); each rank owns an independent stream of the same size (weak
+         scaling, channels sharded across GPUs); the only exchange is an NCCL all-gather of the 4 MB of
+         output rows per rank over NVLink, inside the timed region.
+e2e    : the same step through the host-buffer entry point lrc_chain_run_host (pinned host input, chunked
+         H2D overlapped with the kernel through the double-buffered device ring, rows copied back).
+--impl reference : the reference's own CPU path (oracle/: strict-f32 restatement of dsputils::convolve +
+         the vendored kissfft built with the reference's flags), all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NTAPS, DECIM, NFFT, K_AVG = 64, 10, 1024, 64
+FRAMES = 65536                      # 2^26 decimated samples / 1024
+BYTES_PER_SAMPLE = 8.0              # compulsory traffic = first read of cf32 (+ 4/(10*K) B of rows)
+METRIC = "Msamples/s cf32 through FIR-decimate+FFT chain"
+UNIT = "Msamples/s"
+
+
+def n_input(frames: int) -> int:
+    return frames * NFFT * DECIM + NTAPS - DECIM
+
+
+def workload_name(frames: int) -> str:
+    return (f"cf32 {n_input(frames)} samples -> FIR{NTAPS}/{DECIM} -> {frames} frames x {NFFT}-pt Hann FFT "
+            f"(2^{int(np.log2(frames * NFFT))} samples into the FFT) -> |X|^2 avg K={K_AVG}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline
+# ------------------------------------------------------------------------------------------------------
+def cpu_chain_rate(seconds_target: float, threads: int, frames_per_call: int = 64):
+    """Time the CPU chain (oracle FIR restatement + vendored kissfft at the reference's build flags) on a
+    bounded sample with `threads` host threads.  Returns (Msamples/s, description, kind, frames, secs)."""
+    import oracle
+    from libredio_b200 import synth
+    from concurrent.futures import ThreadPoolExecutor
+    taps = synth.lpf_taps(NTAPS, 0.04)
+    win = synth.hann_periodic(NFFT)
+    x = synth.cf32_noise_tones(n_input(frames_per_call), seed=2)
+    use_ref = oracle.have_ref()
+
+    def one(_):
+        psd, nfr = oracle.chain_psd_cpu(x, taps, DECIM, NFFT, win, use_ref=use_ref, opt=False)
+        return nfr
+
+    t0 = time.perf_counter()
+    one(0)
+    per_call = time.perf_counter() - t0
+    calls = max(threads, int(seconds_target / max(per_call, 1e-6)) * threads)
+    calls = (calls + threads - 1) // threads * threads
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        frames = sum(ex.map(one, range(calls)))
+    dt = time.perf_counter() - t0
+    msps = frames * NFFT * DECIM / dt / 1e6
+    kind = "port"
+    desc = (f"{frames} frames ({frames * NFFT * DECIM} input samples) of the same workload, {threads} threads: "
+            f"strict-f32 C restatement of dsputils::convolve (decimating: only kept outputs are computed) + "
+            + ("vendored kiss_fft.c built with the reference's flags (libkissfft/Makefile:4, no -O)" if use_ref
+               else "restated kissfft (oracle/_ref not present)") + " + Hann + |X|^2 accumulation")
+    return msps, desc, kind, frames, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup):
+        cpu_chain_rate(0.5, cores)
+    per_step = max(2.0, min(20.0, 90.0 / max(args.steps, 1)))
+    t_all = 0.0
+    frames_all = 0
+    desc = kind = ""
+    for _ in range(args.steps):
+        msps, desc, kind, frames, dt = cpu_chain_rate(per_step, cores)
+        vals.append(msps); t_all += dt; frames_all += frames
+    value = frames_all * NFFT * DECIM / t_all / 1e6
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(FRAMES), "sample_per_step": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from libredio_b200 import blocks, synth, capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = blocks.Context(local)
+    dev = ctx.tdev
+    frames = args.frames
+    n_in = n_input(frames)
+    taps = synth.lpf_taps(NTAPS, 0.04)
+    chain = blocks.Chain(ctx, taps, DECIM, NFFT, capi.WINDOW_HANN)
+
+    # synthetic input, generated on the device for the HBM-resident leg: noise + 3 tones, seeded per rank
+    g = torch.Generator(device=dev).manual_seed(2 + rank)
+    x = torch.view_as_complex(torch.randn(n_in, 2, device=dev, generator=g))
+    CH = 1 << 24
+    for f, a in ((0.011, 2.0), (-0.0273, 1.0), (0.0402, 0.5)):
+        for s in range(0, n_in, CH):
+            e = min(n_in, s + CH)
+            ph = (2 * np.pi * f) * torch.arange(s, e, device=dev, dtype=torch.float64)
+            x[s:e] += torch.polar(torch.full((e - s,), a, device=dev, dtype=torch.float32), (ph % (2 * np.pi)).float())
+    rows = frames // K_AVG
+    out = torch.empty((rows, NFFT), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        chain.run(x, K_AVG, out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)     # the only exchange: NVLink gather of the output rows
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev[0].record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        chain.run(x, K_AVG, out)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_in / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e through the host-buffer entry point (rank-local pinned input) ---------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_frames = min(frames, args.e2e_frames)
+    n_e = n_input(e2e_frames)
+    xh = torch.empty(n_e, dtype=torch.complex64, pin_memory=True)
+    xh.copy_(x[:n_e])
+    rows_h = torch.empty((e2e_frames // K_AVG, NFFT), dtype=torch.float32, pin_memory=True)
+    chain.run_host(xh, K_AVG, rows_h)                      # warm-up (allocates the ring)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        chain.run_host(xh, K_AVG, rows_h)                  # synchronous: returns when rows are on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e * e2e_steps / float(te.item()) / 1e6
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+        alg_bytes = n_in * BYTES_PER_SAMPLE + rows * NFFT * 4
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "chain_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            msps, desc, kind, _, _ = cpu_chain_rate(args.cpu_seconds, os.cpu_count() or 1)
+            cpu = {"value": msps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(frames), "ntaps": NTAPS, "decim": DECIM, "nfft": NFFT, "k_avg": K_AVG,
+                       "window": "hann", "l2": "input 5.4 GB per step >> 126 MB L2, no flush needed",
+                       "sharding": f"{world} independent streams, one per GPU; all-gather of output rows only",
+                       "e2e_workload": workload_name(e2e_frames) + f", {e2e_steps} steps through lrc_chain_run_host"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "chain_kernel<64,10,10,7> (+ psd_reduce)",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e * 8,
+                    "d2h_bytes_per_step": (e2e_frames // K_AVG) * NFFT * 4},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    chain.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per step (default: BASELINE config)")
+    ap.add_argument("--e2e-frames", type=int, default=16384, dest="e2e_frames",
+                    help="frames per e2e step through host buffers (1.3 GB pinned by default)")
+    ap.add_argument("--cpu-seconds", type=float, default=1.5, dest="cpu_seconds",
+                    help="per-thread seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

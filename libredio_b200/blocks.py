@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's block interfaces over the C ABI, for tests and bench.py.
+
+One class per reference function; names and argument meaning follow the reference:
+
+    unpack / data_to_samples   rtlsdr::data_to_samples          src/rtlsdr/src/rtlsdr.rs:160-162
+    Fir (convolve + decimate)  dsputils::convolve               src/dsputils/src/dsputils.rs:30-32
+    Fft (block_size, inv)      kissfft::fft                     src/kissfft/src/kissfft.rs:18-31
+    Resampler (ratio)          samplerate::resample             src/samplerate/src/samplerate.rs:59-87
+    Ook                        trigger/discretize/rle/dle/...   src/bitfount/src/bitfount.rs:36-96, src/ratpak.rs:60-111
+    FastFir                    kiss_fastfir                     libkissfft/tools/kiss_fastfir.c:65-245
+
+torch is used for device memory and streams only.  Errors follow the reference's convention: what would
+panic there (odd unpack length, frame length != block_size, closed port) raises here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import check
+
+
+def _p(t) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(None)
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    """torch's current stream as a cudaStream_t.  torch reports the legacy default stream as handle 0,
+    which the C ABI reads as "use the context's own stream"; pass cudaStreamLegacy (0x1) instead so the
+    launch is ordered with the torch ops around it."""
+    h = torch.cuda.current_stream().cuda_stream
+    return C.c_void_p(h if h else 1)
+
+
+class Context:
+    """One per GPU (one process per GPU under torch.distributed)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("libredio_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = device
+        torch.cuda.set_device(device)
+        self.h = C.c_void_p()
+        check(self.lib.lrc_ctx_create(device, C.byref(self.h)), "lrc_ctx_create")
+        n = C.c_int()
+        check(self.lib.lrc_ctx_sm_count(self.h, C.byref(n)), "lrc_ctx_sm_count")
+        self.sm_count = n.value
+        self.tdev = torch.device("cuda", device)
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def close(self):
+        if self.h:
+            self.lib.lrc_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def pinned(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+# ---- (1) -------------------------------------------------------------------------------------------
+def data_to_samples(ctx: Context, iq: torch.Tensor) -> torch.Tensor:
+    """u8 IQ (device, 1-D, even length) -> complex64."""
+    assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous()
+    n = iq.numel()
+    out = torch.empty(n // 2 + (n & 1), dtype=torch.complex64, device=iq.device)
+    check(ctx.lib.lrc_unpack_u8_cf32(ctx.h, _p(iq), n, _p(out), _stream()), "lrc_unpack_u8_cf32")
+    return out
+
+
+# ---- (2) -------------------------------------------------------------------------------------------
+class Fir:
+    def __init__(self, ctx: Context, taps, decim: int = 1):
+        self.ctx = ctx
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.decim = int(decim)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_fir_create(ctx.h, _p(self.taps), self.taps.size, self.decim, C.byref(self.h)), "lrc_fir_create")
+
+    def out_len(self, n_in: int) -> int:
+        return int(self.ctx.lib.lrc_fir_out_len(self.h, n_in))
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        """x: complex64 [n] or [n_ch, n] -> [.., n_out]"""
+        assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        n_ch, n = x2.shape
+        no = self.out_len(n)
+        out = torch.empty((n_ch, no), dtype=torch.complex64, device=x.device)
+        check(self.ctx.lib.lrc_fir_run_cf32(self.h, _p(x2), n_ch, n, n, _p(out), max(no, 1), _stream()), "lrc_fir_run_cf32")
+        return out.reshape(*x.shape[:-1], no)
+
+    def run_u8(self, iq: torch.Tensor) -> torch.Tensor:
+        """iq: uint8 [2n] or [n_ch, 2n] -> complex64 [.., n_out] (fused unpack + FIR)"""
+        assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous() and iq.shape[-1] % 2 == 0
+        q2 = iq.reshape(-1, iq.shape[-1])
+        n_ch, nb = q2.shape
+        n = nb // 2
+        no = self.out_len(n)
+        out = torch.empty((n_ch, no), dtype=torch.complex64, device=iq.device)
+        check(self.ctx.lib.lrc_fir_run_u8(self.h, _p(q2), n_ch, n, n, _p(out), max(no, 1), _stream()), "lrc_fir_run_u8")
+        return out.reshape(*iq.shape[:-1], no)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_fir_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class FirStream:
+    """Seam-exact streaming FIR+decimate over n_ch channels."""
+
+    def __init__(self, fir: Fir, n_ch: int, max_chunk: int, u8: bool = False):
+        self.fir, self.n_ch, self.max_chunk, self.u8 = fir, n_ch, max_chunk, u8
+        self.h = C.c_void_p()
+        check(fir.ctx.lib.lrc_fir_stream_create(fir.h, n_ch, max_chunk, int(u8), C.byref(self.h)), "lrc_fir_stream_create")
+
+    def push(self, chunk: torch.Tensor) -> torch.Tensor:
+        assert chunk.is_cuda and chunk.is_contiguous()
+        c2 = chunk.reshape(self.n_ch, -1)
+        n = c2.shape[1] // 2 if self.u8 else c2.shape[1]
+        cap = (self.fir.taps.size + n) // self.fir.decim + 2
+        out = torch.empty((self.n_ch, cap), dtype=torch.complex64, device=chunk.device)
+        no = C.c_size_t()
+        check(self.fir.ctx.lib.lrc_fir_stream_push(self.h, _p(c2), n, n, _p(out), cap, C.byref(no), _stream()),
+              "lrc_fir_stream_push")
+        return out[:, : no.value]
+
+    def close(self):
+        if self.h:
+            self.fir.ctx.lib.lrc_fir_stream_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+# ---- (3) -------------------------------------------------------------------------------------------
+class Fft:
+    """kissfft::fft(pin, cout, block_size, inv): frames of exactly block_size samples, unscaled."""
+
+    def __init__(self, ctx: Context, block_size: int, inv: int = 0):
+        self.ctx, self.block_size, self.inv = ctx, int(block_size), int(inv)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_fft_create(ctx.h, self.block_size, self.inv, C.byref(self.h)), "lrc_fft_create")
+
+    def run(self, x: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+        assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous()
+        if x.shape[-1] != self.block_size:
+            # assert!(din.len() == block_size)  kissfft.rs:24
+            raise capi.LrcError(capi.ERR_LENGTH, "Fft.run", f"frame length {x.shape[-1]} != block_size {self.block_size}")
+        out = x if inplace else torch.empty_like(x)
+        batch = x.numel() // self.block_size
+        check(self.ctx.lib.lrc_fft_run(self.h, _p(x), _p(out), batch, _stream()), "lrc_fft_run")
+        return out
+
+    def run_host(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.empty_like(x)
+        check(self.ctx.lib.lrc_fft_run_host(self.h, _p(x), _p(out), x.size), "lrc_fft_run_host")
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_fft_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Psd:
+    def __init__(self, ctx: Context, nfft: int, window: int = capi.WINDOW_HANN):
+        self.ctx, self.nfft = ctx, int(nfft)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_psd_create(ctx.h, self.nfft, window, C.byref(self.h)), "lrc_psd_create")
+
+    def set_window(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        assert w.size == self.nfft
+        check(self.ctx.lib.lrc_psd_set_window(self.h, _p(w)), "lrc_psd_set_window")
+
+    def run(self, x: torch.Tensor, k_avg: int) -> torch.Tensor:
+        assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous()
+        n_frames = x.numel() // self.nfft
+        rows = n_frames // k_avg
+        out = torch.empty((rows, self.nfft), dtype=torch.float32, device=x.device)
+        check(self.ctx.lib.lrc_psd_run(self.h, _p(x), n_frames, k_avg, _p(out), _stream()), "lrc_psd_run")
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_psd_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Chain:
+    """cf32 -> FIR/decimate -> window -> FFT -> |X|^2 average, one fused kernel."""
+
+    def __init__(self, ctx: Context, taps, decim: int, nfft: int, window: int = capi.WINDOW_HANN):
+        self.ctx, self.nfft, self.decim = ctx, int(nfft), int(decim)
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_chain_create(ctx.h, _p(self.taps), self.taps.size, self.decim, self.nfft, window,
+                                       C.byref(self.h)), "lrc_chain_create")
+
+    def frames(self, n_in: int) -> int:
+        return int(self.ctx.lib.lrc_chain_frames(self.h, n_in))
+
+    def run(self, x: torch.Tensor, k_avg: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous() and x.dim() == 1
+        rows = self.frames(x.numel()) // k_avg
+        if out is None:
+            out = torch.empty((rows, self.nfft), dtype=torch.float32, device=x.device)
+        nr = C.c_size_t()
+        check(self.ctx.lib.lrc_chain_run(self.h, _p(x), x.numel(), k_avg, _p(out), C.byref(nr), _stream()), "lrc_chain_run")
+        assert nr.value == rows
+        return out
+
+    def run_host(self, x, k_avg: int, out=None):
+        """x: pinned CPU complex64 tensor (or numpy array); returns rows as a CPU tensor/array of the same kind."""
+        n = x.numel() if isinstance(x, torch.Tensor) else x.size
+        rows = self.frames(n) // k_avg
+        if out is None:
+            out = (torch.empty((rows, self.nfft), dtype=torch.float32, pin_memory=True)
+                   if isinstance(x, torch.Tensor) else np.empty((rows, self.nfft), dtype=np.float32))
+        nr = C.c_size_t()
+        check(self.ctx.lib.lrc_chain_run_host(self.h, _p(x), n, k_avg, _p(out), C.byref(nr)), "lrc_chain_run_host")
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_chain_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+# ---- (4) -------------------------------------------------------------------------------------------
+def fm_demod(ctx: Context, x: torch.Tensor, state: torch.Tensor | None = None) -> torch.Tensor:
+    """d[n] = arg(x[n] conj(x[n-1])); x: complex64 [n] or [n_ch, n]; state: complex64 [n_ch] carried x[-1]
+    (updated in place), None = stateless (x[-1] = 0)."""
+    assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous()
+    x2 = x.reshape(-1, x.shape[-1])
+    n_ch, n = x2.shape
+    out = torch.empty((n_ch, n), dtype=torch.float32, device=x.device)
+    if state is not None:
+        assert state.dtype == torch.complex64 and state.numel() == n_ch and state.is_cuda
+    check(ctx.lib.lrc_fmdemod_run(ctx.h, _p(x2), n_ch, n, n, _p(state), _p(out), max(n, 1), _stream()), "lrc_fmdemod_run")
+    return out.reshape(x.shape)
+
+
+class Resampler:
+    """samplerate::resample(din, dout, ratio): streaming, state carried across chunks (samplerate.rs:59-87)."""
+
+    def __init__(self, ctx: Context, ratio: float, n_ch: int = 1, max_chunk: int = 1 << 20):
+        self.ctx, self.ratio, self.n_ch, self.max_chunk = ctx, float(ratio), n_ch, max_chunk
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_resampler_create(ctx.h, C.c_double(self.ratio), n_ch, max_chunk, C.byref(self.h)),
+              "lrc_resampler_create")
+        nt, L, M = C.c_size_t(), C.c_int(), C.c_int()
+        check(ctx.lib.lrc_resampler_get_taps(self.h, None, 0, C.byref(nt), C.byref(L), C.byref(M)), "lrc_resampler_get_taps")
+        self.L, self.M, self.ntaps = L.value, M.value, nt.value
+
+    def taps(self) -> np.ndarray:
+        h = np.empty(self.ntaps, dtype=np.float64)
+        check(self.ctx.lib.lrc_resampler_get_taps(self.h, _p(h), h.size, None, None, None), "lrc_resampler_get_taps")
+        return h
+
+    def reset(self):
+        check(self.ctx.lib.lrc_resampler_reset(self.h), "lrc_resampler_reset")
+
+    def process(self, x: torch.Tensor) -> torch.Tensor:
+        """x: float32 [n] or [n_ch, n] -> [.., n_out]; the reference sizes the output ratio*len + 1 (:64)."""
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
+        x2 = x.reshape(self.n_ch, -1)
+        n = x2.shape[1]
+        cap = int(self.ratio * n + 1) + 1
+        out = torch.empty((self.n_ch, cap), dtype=torch.float32, device=x.device)
+        no = C.c_size_t()
+        check(self.ctx.lib.lrc_resampler_process(self.h, _p(x2), n, n, _p(out), cap, C.byref(no), _stream()),
+              "lrc_resampler_process")
+        res = out[:, : no.value]
+        return res.reshape(-1) if x.dim() == 1 else res
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_resampler_destroy(self.h)
+            self.h = C.c_void_p()

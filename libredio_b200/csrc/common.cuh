@@ -1,0 +1,157 @@
+// common.cuh -- shared host/device helpers for libredio_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include "../../include/libredio_cuda.h"
+
+// ---------------------------------------------------------------------------------------------
+// context + error plumbing
+// ---------------------------------------------------------------------------------------------
+struct lrc_ctx {
+    int          device;
+    int          n_sm;
+    cudaStream_t stream;       // default compute stream of the context
+    cudaStream_t copy_stream;  // H2D ring copies
+    cudaStream_t out_stream;   // D2H of results
+};
+
+void lrc_set_error(const char *fmt, ...);
+
+#define LRC_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            lrc_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return LRC_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define LRC_REQUIRE(cond, code, msg)                                                         \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            lrc_set_error("%s:%d %s", __FILE__, __LINE__, msg);                              \
+            return (code);                                                                   \
+        }                                                                                    \
+    } while (0)
+
+static inline cudaStream_t lrc_stream(const lrc_ctx *ctx, void *s)
+{
+    return s ? reinterpret_cast<cudaStream_t>(s) : ctx->stream;
+}
+
+// every entry point binds the context's device first: several contexts (one per GPU) may live in
+// one process (kpn thread-per-block graphs), and torch may have changed the current device.
+#define LRC_BIND(ctx)                                                                        \
+    do {                                                                                     \
+        LRC_REQUIRE((ctx) != nullptr, LRC_ERR_INVALID, "null context");                      \
+        LRC_CUDA(cudaSetDevice((ctx)->device));                                              \
+    } while (0)
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conjb(float2 a, float2 b)   // a * conj(b)
+{
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// streaming 128-bit global load that does not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4 *p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + TMA (cp.async.bulk, 1-D) -----------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; bytes, src and dst must be 16-byte aligned.
+// Completion is signalled on `bar` as transaction bytes.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// same with an L2 evict-first policy: streaming input that is read exactly once
+__device__ __forceinline__ void tma_load_1d_evict_first(void *smem_dst, const void *gmem_src,
+                                                        uint32_t bytes, uint64_t *bar)
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// order generic-proxy smem accesses before subsequent async-proxy (TMA) writes to the same buffer
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// named barrier among `nthreads` threads (multiple of 32); id 1..15 (0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,172 @@
+// fft_core.cuh -- register/shared-memory Stockham FFT building blocks (power-of-two sizes).
+//
+// Replaces the arithmetic of kf_work / kf_bfly2 / kf_bfly4 (libkissfft/kiss_fft.c:21-90,238-302):
+// same unscaled DFT, forward exp(-j 2 pi k n / N), inverse exp(+j ...).  kissfft is a recursive
+// out-of-place radix-4/2 DIT; here each thread owns E = min(16, N) points in registers, a pass is a
+// radix-E butterfly done entirely in registers, and passes exchange data through padded shared
+// memory in Stockham (auto-sort) order, so input and output are both in natural order and both use
+// the coalesced layout "thread t holds x[t + e*T]", T = N/E threads per transform.
+#pragma once
+#include "common.cuh"
+
+namespace lrfft {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// forward: a * (-j);  inverse: a * (+j)
+template <bool INV>
+__device__ __forceinline__ float2 rot90(float2 a)
+{
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <bool INV>
+__device__ __forceinline__ void bfly2(float2 &a, float2 &b)
+{
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+// natural-order 4-point DFT in place
+template <bool INV>
+__device__ __forceinline__ void bfly4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+    float2 s13 = cadd(a1, a3), d13 = rot90<INV>(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = cadd(d02, d13);
+    a3 = csub(d02, d13);
+}
+
+// a * W16^k, W16 = exp(-+ 2 pi j / 16); k is a compile-time constant after unrolling
+template <bool INV>
+__device__ __forceinline__ float2 mul_w16(float2 a, int k)
+{
+    constexpr float C1 = 0.92387953251128673848f;   // cos(pi/8)
+    constexpr float S1 = 0.38268343236508978178f;   // sin(pi/8)
+    constexpr float H = 0.70710678118654752440f;    // cos(pi/4)
+    k &= 15;
+    if (k == 0) return a;
+    if (k == 4) return rot90<INV>(a);
+    if (k == 8) return make_float2(-a.x, -a.y);
+    if (k == 12) return rot90<!INV>(a);
+    float c, s;   // W = c - j s (forward)
+    switch (k) {
+        case 1:  c = C1;  s = S1;  break;
+        case 2:  c = H;   s = H;   break;
+        case 3:  c = S1;  s = C1;  break;
+        case 5:  c = -S1; s = C1;  break;
+        case 6:  c = -H;  s = H;   break;
+        case 7:  c = -C1; s = S1;  break;
+        case 9:  c = -C1; s = -S1; break;
+        case 10: c = -H;  s = -H;  break;
+        case 11: c = -S1; s = -C1; break;
+        case 13: c = S1;  s = -C1; break;
+        case 14: c = H;   s = -H;  break;
+        default: c = C1;  s = -S1; break;   // 15
+    }
+    if (INV) s = -s;
+    // (a.x + j a.y)(c - j s)
+    return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+
+// natural-order R-point DFT of v[0..R) held in registers, R in {1, 2, 4, 8, 16}
+template <int R, bool INV>
+struct RegFFT {
+    static_assert(R == 8 || R == 16, "radix");
+    __device__ __forceinline__ static void run(float2 *v)
+    {
+        constexpr int R2 = R / 4;    // R = 4 * R2 ; input index s = R2*a + b, output index r = c + 4*d
+#pragma unroll
+        for (int b = 0; b < R2; ++b) bfly4<INV>(v[b], v[R2 + b], v[2 * R2 + b], v[3 * R2 + b]);
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+#pragma unroll
+            for (int b = 1; b < R2; ++b) v[R2 * c + b] = mul_w16<INV>(v[R2 * c + b], b * c * (16 / R));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) RegFFT<R2, INV>::run(v + R2 * c);
+        float2 tmp[R];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int d = 0; d < R2; ++d) tmp[c + 4 * d] = v[R2 * c + d];
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = tmp[i];
+    }
+};
+template <bool INV> struct RegFFT<1, INV> { __device__ __forceinline__ static void run(float2 *) {} };
+template <bool INV> struct RegFFT<2, INV> {
+    __device__ __forceinline__ static void run(float2 *v) { bfly2<INV>(v[0], v[1]); }
+};
+template <bool INV> struct RegFFT<4, INV> {
+    __device__ __forceinline__ static void run(float2 *v) { bfly4<INV>(v[0], v[1], v[2], v[3]); }
+};
+
+// synchronisation among the T threads of one transform
+struct SyncCta   { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct SyncNamed { int id, n; __device__ __forceinline__ void operator()() const { named_bar_sync(id, n); } };
+struct SyncWarp  { unsigned mask; __device__ __forceinline__ void operator()() const { __syncwarp(mask); } };
+
+template <int LOG2N, bool INV>
+struct CtaFFT {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int E = N >= 16 ? 16 : N;      // points per thread
+    static constexpr int T = N / E;                  // threads per transform
+    static constexpr int SMEM_CPX = N + (N >> 4);    // padded exchange buffer (float2 units)
+    __device__ __forceinline__ static int pad(int i) { return i + (i >> 4); }
+
+    template <int NS, class Sync>
+    __device__ __forceinline__ static void stage(float2 *v, float2 *sm, const float2 *__restrict__ tw,
+                                                 int t, const Sync &sync)
+    {
+        constexpr int REM = N / NS;
+        constexpr int R = REM >= E ? E : REM;   // radix of this pass
+        constexpr int NB = E / R;               // butterflies per thread
+        constexpr bool LAST = (NS * R == N);
+        if (NS > 1) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int k = (t + q * T) & (NS - 1);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    float2 w = __ldg(&tw[r * k * (N / (NS * R))]);
+                    if (INV) w.y = -w.y;
+                    v[q + r * NB] = cmulf(v[q + r * NB], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            float2 u[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) u[r] = v[q + r * NB];
+            RegFFT<R, INV>::run(u);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q + r * NB] = u[r];
+        }
+        if constexpr (!LAST) {
+            // not the last pass => R == E, one butterfly per thread (j = t)
+            const int base = (t / NS) * (NS * R) + (t & (NS - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) sm[pad(base + r * NS)] = v[r];
+            sync();
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = sm[pad(t + e * T)];
+            sync();
+            stage<NS * R, Sync>(v, sm, tw, t, sync);
+        }
+    }
+
+    // in: v[e] = x[t + e*T];  out: v[e] = X[t + e*T].  tw[k] = exp(-2 pi j k / N) (f64 -> f32 table).
+    template <class Sync>
+    __device__ __forceinline__ static void run(float2 *v, float2 *sm, const float2 *__restrict__ tw, int t,
+                                               const Sync &sync)
+    {
+        stage<1, Sync>(v, sm, tw, t, sync);
+    }
+};
+
+}  // namespace lrfft

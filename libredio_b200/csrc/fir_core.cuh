@@ -1,0 +1,78 @@
+// fir_core.cuh -- register-blocked polyphase FIR + decimate on a shared-memory tile.
+//
+// Replaces the arithmetic of dsputils::convolve (src/dsputils/src/dsputils.rs:30-32) on the re and
+// im planes:  z[k] = sum_j x[k*DECIM + j] * taps[j]  (correlation, taps not reversed, j ascending).
+//
+// A thread owns R consecutive outputs.  Its input window is the contiguous run of
+// (R-1)*DECIM + NTAPS samples starting at R*DECIM*t; the window is streamed once through 128-bit
+// shared loads and every loaded sample feeds the <= ceil(NTAPS/DECIM) accumulators it belongs to, so
+// a sample costs one quarter of an LDS.128 for up to 2*ceil(NTAPS/DECIM) FFMAs.  With R odd the
+// per-thread stride R*DECIM*8 bytes is an odd multiple of 16 bytes, which makes the 8 threads of an
+// LDS.128 phase hit 8 distinct 16-byte bank groups (conflict-free) without padding the TMA-written
+// tile.  Taps are kernel parameters (constant bank, immediate offsets): FFMA reads them for free.
+#pragma once
+#include "common.cuh"
+
+template <int NTAPS>
+struct FirTaps { float h[NTAPS]; };
+
+template <int NTAPS, int DECIM, int R>
+struct FirTile {
+    static constexpr int WIN = (R - 1) * DECIM + NTAPS;        // samples a thread reads
+    static constexpr int STEP = R * DECIM;                      // samples between thread windows
+    static_assert(WIN % 2 == 0, "window must be a whole number of 16-byte loads");
+    static_assert((STEP * 8) % 16 == 0, "thread windows must start 16-byte aligned");
+
+    // sx: this thread's window in shared memory (cf32), 16-byte aligned
+    __device__ __forceinline__ static void run_cf32(const float2 *sx, const FirTaps<NTAPS> &taps, float2 *acc)
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < WIN; j += 2) {
+            const float4 x = *reinterpret_cast<const float4 *>(sx + j);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k0 = j - r * DECIM, k1 = k0 + 1;
+                if (k0 >= 0 && k0 < NTAPS) {
+                    acc[r].x = fmaf(x.x, taps.h[k0], acc[r].x);
+                    acc[r].y = fmaf(x.y, taps.h[k0], acc[r].y);
+                }
+                if (k1 >= 0 && k1 < NTAPS) {
+                    acc[r].x = fmaf(x.z, taps.h[k1], acc[r].x);
+                    acc[r].y = fmaf(x.w, taps.h[k1], acc[r].y);
+                }
+            }
+        }
+    }
+
+    // u8 IQ window (2 bytes per sample), 4-byte aligned.  The unpack i2f(b) = b/127 - 1 is folded:
+    // sum_j h_j (b_j/127 - 1) = sum_j (h_j/127) (b_j - 127), and b - 127 is exact in f32, so the
+    // caller passes taps already divided by 127 (in double, on the host).
+    __device__ __forceinline__ static void run_u8(const uint32_t *sw, const FirTaps<NTAPS> &taps127, float2 *acc)
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < WIN; j += 2) {
+            const uint32_t w = sw[j / 2];
+            // 0x4B0000bb is the float 2^23 + bb; subtracting 2^23 + 127 gives bb - 127 exactly
+            const float i0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - 8388735.0f;
+            const float q0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388735.0f;
+            const float i1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - 8388735.0f;
+            const float q1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - 8388735.0f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k0 = j - r * DECIM, k1 = k0 + 1;
+                if (k0 >= 0 && k0 < NTAPS) {
+                    acc[r].x = fmaf(i0, taps127.h[k0], acc[r].x);
+                    acc[r].y = fmaf(q0, taps127.h[k0], acc[r].y);
+                }
+                if (k1 >= 0 && k1 < NTAPS) {
+                    acc[r].x = fmaf(i1, taps127.h[k1], acc[r].x);
+                    acc[r].y = fmaf(q1, taps127.h[k1], acc[r].y);
+                }
+            }
+        }
+    }
+};

@@ -1,0 +1,356 @@
+// k_fft.cu -- batched FFT (kissfft seam) and the fused window + FFT + |X|^2-average kernel.
+//
+// Replaces: kissfft::fft block + kiss_fft_alloc/kiss_fft (src/kissfft/src/kissfft.rs:11-31,
+// libkissfft/kiss_fft.c:339-388); |X|^2 averaging after tools/psdpng.c:157-178.
+#include "fft_core.cuh"
+#include <cmath>
+#include <vector>
+
+using namespace lrfft;
+
+struct lrc_fft {
+    lrc_ctx *ctx;
+    int      nfft, log2n, inverse;
+    float2  *d_tw;     // exp(-2 pi j k / nfft), k < nfft (forward table; kernels conjugate for inverse)
+};
+
+struct lrc_psd {
+    lrc_ctx *ctx;
+    int      nfft, log2n;
+    float2  *d_tw;
+    float   *d_win;        // nfft window values (all ones for LRC_WINDOW_NONE)
+    float   *d_partial;    // [n_items][nfft] scratch
+    size_t   partial_cap;  // in floats
+};
+
+// twiddles exactly as kiss_fft_alloc builds them (kiss_fft.c:357-363): phase in double, cast to float
+int lrc_make_twiddles(int nfft, float2 **d_tw)
+{
+    std::vector<float2> tw(nfft);
+    const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+    for (int i = 0; i < nfft; ++i) {
+        double ph = -2.0 * pi * i / nfft;
+        tw[i] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    LRC_CUDA(cudaMalloc(d_tw, sizeof(float2) * nfft));
+    LRC_CUDA(cudaMemcpy(*d_tw, tw.data(), sizeof(float2) * nfft, cudaMemcpyHostToDevice));
+    return LRC_OK;
+}
+
+int lrc_log2_exact(int n)
+{
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return ((1 << l) == n) ? l : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched FFT: G = blockDim/T transforms per CTA, grid-stride over the batch
+// ---------------------------------------------------------------------------------------------
+template <int LOG2N, bool INV>
+__global__ void __launch_bounds__((1 << LOG2N) / 16 > 128 ? (1 << LOG2N) / 16 : 128)
+fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, size_t batch,
+                 const float2 *__restrict__ tw)
+{
+    using F = CtaFFT<LOG2N, INV>;
+    constexpr int N = F::N, E = F::E, T = F::T;
+    extern __shared__ float2 sm_all[];
+    const int G = blockDim.x / T;
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *sm = sm_all + (size_t)g * F::SMEM_CPX;
+    for (size_t base = (size_t)blockIdx.x * G; base < batch; base += (size_t)gridDim.x * G) {
+        const size_t f = base + g;
+        const bool active = f < batch;
+        float2 v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = active ? in[f * N + t + e * T] : make_float2(0.f, 0.f);
+        F::run(v, sm, tw, t, SyncCta{});
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) out[f * N + t + e * T] = v[e];
+        }
+    }
+}
+
+template <int LOG2N, bool INV>
+static int launch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t batch, cudaStream_t s)
+{
+    using F = CtaFFT<LOG2N, INV>;
+    constexpr int T = F::T;
+    const int threads = T > 128 ? T : 128;
+    const int G = threads / T;
+    const size_t smem = (size_t)G * F::SMEM_CPX * sizeof(float2);
+    auto kern = fft_batch_kernel<LOG2N, INV>;
+    if (smem > 48 * 1024) LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t blocks = ceil_div(batch, (size_t)G);
+    const size_t max_blocks = (size_t)p->ctx->n_sm * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(in, out, batch, p->d_tw);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
+}
+
+template <bool INV>
+static int dispatch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t batch, cudaStream_t s)
+{
+    switch (p->log2n) {
+        case 1:  return launch_fft<1, INV>(p, in, out, batch, s);
+        case 2:  return launch_fft<2, INV>(p, in, out, batch, s);
+        case 3:  return launch_fft<3, INV>(p, in, out, batch, s);
+        case 4:  return launch_fft<4, INV>(p, in, out, batch, s);
+        case 5:  return launch_fft<5, INV>(p, in, out, batch, s);
+        case 6:  return launch_fft<6, INV>(p, in, out, batch, s);
+        case 7:  return launch_fft<7, INV>(p, in, out, batch, s);
+        case 8:  return launch_fft<8, INV>(p, in, out, batch, s);
+        case 9:  return launch_fft<9, INV>(p, in, out, batch, s);
+        case 10: return launch_fft<10, INV>(p, in, out, batch, s);
+        case 11: return launch_fft<11, INV>(p, in, out, batch, s);
+        case 12: return launch_fft<12, INV>(p, in, out, batch, s);
+        case 13: return launch_fft<13, INV>(p, in, out, batch, s);
+    }
+    lrc_set_error("nfft=%d not supported", p->nfft);
+    return LRC_ERR_UNSUPPORTED;
+}
+
+extern "C" int lrc_fft_create(lrc_ctx *ctx, int nfft, int inverse, lrc_fft **out)
+{
+    LRC_BIND(ctx);
+    LRC_REQUIRE(out != nullptr && nfft >= 1, LRC_ERR_INVALID, "lrc_fft_create: bad arguments");
+    const int l2 = lrc_log2_exact(nfft);
+    if (l2 < 1 || l2 > 13) {
+        lrc_set_error("lrc_fft_create: nfft=%d: only powers of two in [2, 8192] are implemented "
+                      "(kissfft also accepts mixed radix 3/5/odd sizes)", nfft);
+        return LRC_ERR_UNSUPPORTED;
+    }
+    lrc_fft *p = new (std::nothrow) lrc_fft{ctx, nfft, l2, inverse ? 1 : 0, nullptr};
+    LRC_REQUIRE(p != nullptr, LRC_ERR_NOMEM, "out of host memory");
+    int rc = lrc_make_twiddles(nfft, &p->d_tw);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return LRC_OK;
+}
+
+extern "C" int lrc_fft_destroy(lrc_fft *p)
+{
+    if (!p) return LRC_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_tw);
+    delete p;
+    return LRC_OK;
+}
+
+extern "C" int lrc_fft_run(lrc_fft *p, const float *d_in, float *d_out, size_t batch, void *stream)
+{
+    LRC_REQUIRE(p != nullptr, LRC_ERR_INVALID, "null plan");
+    LRC_BIND(p->ctx);
+    if (batch == 0) return LRC_OK;
+    LRC_REQUIRE(d_in && d_out, LRC_ERR_INVALID, "lrc_fft_run: null buffer");
+    LRC_REQUIRE(((uintptr_t)d_in & 7) == 0 && ((uintptr_t)d_out & 7) == 0, LRC_ERR_INVALID,
+                "lrc_fft_run: buffers must be 8-byte aligned");
+    cudaStream_t s = lrc_stream(p->ctx, stream);
+    return p->inverse ? dispatch_fft<true>(p, (const float2 *)d_in, (float2 *)d_out, batch, s)
+                      : dispatch_fft<false>(p, (const float2 *)d_in, (float2 *)d_out, batch, s);
+}
+
+extern "C" int lrc_fft_run_host(lrc_fft *p, const float *h_in, float *h_out, size_t n_samples)
+{
+    LRC_REQUIRE(p != nullptr, LRC_ERR_INVALID, "null plan");
+    LRC_BIND(p->ctx);
+    if (n_samples % (size_t)p->nfft != 0) {
+        // assert!(din.len() == block_size)  src/kissfft/src/kissfft.rs:24
+        lrc_set_error("lrc_fft_run_host: %zu samples is not a multiple of block_size %d", n_samples, p->nfft);
+        return LRC_ERR_LENGTH;
+    }
+    if (n_samples == 0) return LRC_OK;
+    LRC_REQUIRE(h_in && h_out, LRC_ERR_INVALID, "null buffer");
+    float *d = nullptr;
+    const size_t bytes = n_samples * sizeof(float2);
+    LRC_CUDA(cudaMalloc(&d, bytes));
+    cudaStream_t s = p->ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(d, h_in, bytes, cudaMemcpyHostToDevice, s);
+    int rc = LRC_OK;
+    if (e == cudaSuccess) rc = lrc_fft_run(p, d, d, n_samples / p->nfft, s);
+    if (e == cudaSuccess && rc == LRC_OK) e = cudaMemcpyAsync(h_out, d, bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) { lrc_set_error("lrc_fft_run_host: %s", cudaGetErrorString(e)); return LRC_ERR_CUDA; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// window + FFT + |X|^2 accumulate.  Work item = `fpi` consecutive frames inside one row; each
+// transform group of a CTA walks its items, accumulating |X|^2 in registers, and writes one
+// partial spectrum per item; psd_reduce_kernel sums the partials of a row in fixed order.
+// ---------------------------------------------------------------------------------------------
+template <int LOG2N>
+__global__ void __launch_bounds__((1 << LOG2N) / 16 > 128 ? (1 << LOG2N) / 16 : 128)
+psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
+           float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
+{
+    using F = CtaFFT<LOG2N, false>;
+    constexpr int N = F::N, E = F::E, T = F::T;
+    extern __shared__ float2 sm_all[];
+    const int G = blockDim.x / T;
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *sm = sm_all + (size_t)g * F::SMEM_CPX;
+    float w[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) w[e] = win[t + e * T];
+
+    for (size_t item = (size_t)blockIdx.x * G + g; item < n_items; item += (size_t)gridDim.x * G) {
+        const size_t row = item / ipr, c = item % ipr;
+        const size_t f0 = row * k_avg + c * fpi;
+        size_t f1 = f0 + fpi;
+        if (f1 > (row + 1) * k_avg) f1 = (row + 1) * k_avg;
+        float acc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = 0.f;
+        for (size_t f = f0; f < f1; ++f) {
+            float2 v[E];
+            const float2 *src = in + f * N + t;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                float2 x = __ldcs(src + e * T);
+                v[e] = make_float2(x.x * w[e], x.y * w[e]);
+            }
+            if constexpr (T >= 32) {
+                F::run(v, sm, tw, t, SyncNamed{1 + g, T});
+            } else {
+                const unsigned lane = threadIdx.x & 31;
+                const unsigned mask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (lane / T * T));
+                F::run(v, sm, tw, t, SyncWarp{mask});
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));
+        }
+        float *dst = partial + item * N + t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) dst[e * T] = acc[e];
+    }
+}
+
+__global__ void psd_reduce_kernel(const float *__restrict__ partial, float *__restrict__ rows, int nfft,
+                                  size_t ipr, size_t n_rows, float scale, int accumulate)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * (size_t)nfft) return;
+    const size_t row = i / nfft, b = i % nfft;
+    const float *p = partial + row * ipr * nfft + b;
+    float s = 0.f;
+    for (size_t c = 0; c < ipr; ++c) s += p[c * nfft];
+    s *= scale;
+    rows[i] = accumulate ? rows[i] + s : s;
+}
+
+template <int LOG2N>
+static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, size_t ipr, size_t n_items,
+                      cudaStream_t s)
+{
+    using F = CtaFFT<LOG2N, false>;
+    constexpr int T = F::T;
+    const int threads = T > 128 ? T : 128;
+    const int G = threads / T;
+    const size_t smem = (size_t)G * F::SMEM_CPX * sizeof(float2);
+    auto kern = psd_kernel<LOG2N>;
+    if (smem > 48 * 1024) LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    size_t blocks = ceil_div(n_items, (size_t)G);
+    const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+    if (blocks > max_blocks) blocks = max_blocks;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
+}
+
+extern "C" int lrc_psd_create(lrc_ctx *ctx, int nfft, int window, lrc_psd **out)
+{
+    LRC_BIND(ctx);
+    LRC_REQUIRE(out != nullptr, LRC_ERR_INVALID, "lrc_psd_create: null out");
+    const int l2 = lrc_log2_exact(nfft);
+    if (l2 < 1 || l2 > 13) {
+        lrc_set_error("lrc_psd_create: nfft=%d: only powers of two in [2, 8192]", nfft);
+        return LRC_ERR_UNSUPPORTED;
+    }
+    LRC_REQUIRE(window == LRC_WINDOW_NONE || window == LRC_WINDOW_HANN, LRC_ERR_INVALID, "unknown window");
+    lrc_psd *p = new (std::nothrow) lrc_psd{ctx, nfft, l2, nullptr, nullptr, nullptr, 0};
+    LRC_REQUIRE(p != nullptr, LRC_ERR_NOMEM, "out of host memory");
+    int rc = lrc_make_twiddles(nfft, &p->d_tw);
+    if (rc) { delete p; return rc; }
+    std::vector<float> w(nfft);
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int i = 0; i < nfft; ++i)
+        w[i] = window == LRC_WINDOW_HANN ? (float)(0.5 - 0.5 * cos(2.0 * pi * i / nfft)) : 1.0f;
+    if (cudaMalloc(&p->d_win, sizeof(float) * nfft) != cudaSuccess) { lrc_psd_destroy(p); lrc_set_error("cudaMalloc window"); return LRC_ERR_CUDA; }
+    *out = p;
+    return lrc_psd_set_window(p, w.data());
+}
+
+extern "C" int lrc_psd_set_window(lrc_psd *p, const float *h_window)
+{
+    LRC_REQUIRE(p && h_window, LRC_ERR_INVALID, "lrc_psd_set_window: null");
+    LRC_BIND(p->ctx);
+    LRC_CUDA(cudaMemcpy(p->d_win, h_window, sizeof(float) * p->nfft, cudaMemcpyHostToDevice));
+    return LRC_OK;
+}
+
+extern "C" int lrc_psd_destroy(lrc_psd *p)
+{
+    if (!p) return LRC_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_tw); cudaFree(p->d_win); cudaFree(p->d_partial);
+    delete p;
+    return LRC_OK;
+}
+
+// frames per work item: small enough that items outnumber resident transform groups several times,
+// large enough that the 4*nfft-byte partial written per item is noise next to fpi*8*nfft bytes read
+size_t lrc_psd_frames_per_item(size_t k_avg) { return k_avg < 16 ? (k_avg ? k_avg : 1) : 16; }
+
+int lrc_psd_ensure_partial(float **d_partial, size_t *cap, size_t need_floats)
+{
+    if (*cap >= need_floats) return LRC_OK;
+    if (*d_partial) cudaFree(*d_partial);
+    *d_partial = nullptr; *cap = 0;
+    LRC_CUDA(cudaMalloc(d_partial, need_floats * sizeof(float)));
+    *cap = need_floats;
+    return LRC_OK;
+}
+
+int lrc_psd_reduce(const float *d_partial, float *d_rows, int nfft, size_t ipr, size_t n_rows, float scale,
+                   int accumulate, cudaStream_t s)
+{
+    const size_t n = n_rows * (size_t)nfft;
+    psd_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_partial, d_rows, nfft, ipr, n_rows, scale, accumulate);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
+}
+
+extern "C" int lrc_psd_run(lrc_psd *p, const float *d_in, size_t n_frames, size_t k_avg, float *d_rows,
+                           void *stream)
+{
+    LRC_REQUIRE(p != nullptr, LRC_ERR_INVALID, "null plan");
+    LRC_BIND(p->ctx);
+    LRC_REQUIRE(k_avg >= 1, LRC_ERR_INVALID, "lrc_psd_run: k_avg must be >= 1");
+    const size_t n_rows = n_frames / k_avg;
+    if (n_rows == 0) return LRC_OK;
+    LRC_REQUIRE(d_in && d_rows, LRC_ERR_INVALID, "lrc_psd_run: null buffer");
+    LRC_REQUIRE(((uintptr_t)d_in & 7) == 0, LRC_ERR_INVALID, "lrc_psd_run: input must be 8-byte aligned");
+    cudaStream_t s = lrc_stream(p->ctx, stream);
+    const size_t fpi = lrc_psd_frames_per_item(k_avg);
+    const size_t ipr = ceil_div(k_avg, fpi);
+    const size_t n_items = n_rows * ipr;
+    int rc = lrc_psd_ensure_partial(&p->d_partial, &p->partial_cap, n_items * (size_t)p->nfft);
+    if (rc) return rc;
+    const float2 *in = (const float2 *)d_in;
+    switch (p->log2n) {
+#define PSD_CASE(L) case L: rc = launch_psd<L>(p, in, k_avg, fpi, ipr, n_items, s); break;
+        PSD_CASE(1) PSD_CASE(2) PSD_CASE(3) PSD_CASE(4) PSD_CASE(5) PSD_CASE(6) PSD_CASE(7)
+        PSD_CASE(8) PSD_CASE(9) PSD_CASE(10) PSD_CASE(11) PSD_CASE(12) PSD_CASE(13)
+#undef PSD_CASE
+        default: rc = LRC_ERR_UNSUPPORTED;
+    }
+    if (rc) return rc;
+    return lrc_psd_reduce(p->d_partial, d_rows, p->nfft, ipr, n_rows, 1.0f / (float)k_avg, 0, s);
+}

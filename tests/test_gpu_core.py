@@ -1,0 +1,356 @@
+"""GPU parity, part 1: unpack, FIR+decimate, FFT, PSD, fused chain -- all through the C ABI, checked
+against oracle/ (the CPU restatement, itself pinned to the vendored kissfft and the golden fixtures).
+
+Tolerances are BASELINE.json's: bit-exact for the u8 unpack; max |err| <= 1e-4 x RMS(reference output)
+for the float FIR / FFT stages.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import defined_f64 as D
+from libredio_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # x RMS of the reference output (north_star)
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.abs(np.asarray(a, dtype=np.complex128)) ** 2)))
+
+
+def dev(a, ctx):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
+
+
+def assert_close_rms(got, ref, tol=TOL):
+    ref = np.asarray(ref)
+    got = np.asarray(got)
+    assert got.shape == ref.shape
+    err = float(np.max(np.abs(got.astype(np.complex128) - ref.astype(np.complex128)))) if ref.size else 0.0
+    assert err <= tol * rms(ref), f"max|err| {err:.3e} > {tol} x rms {rms(ref):.3e}"
+
+
+# ---- (1) unpack: bit-exact --------------------------------------------------------------------------
+def test_unpack_all_256_values_bit_exact(ctx):
+    from libredio_b200 import blocks
+    b = np.arange(256, dtype=np.uint8).repeat(2)          # every byte as I and as Q
+    got = blocks.data_to_samples(ctx, dev(b, ctx)).cpu().numpy()
+    ref = oracle.data_to_samples(b)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # hand-computed micro-cases
+    t = got.view(np.float32)[0::2]
+    assert t[0] == -1.0 and t[127] == 0.0 and t[254] == 1.0 and t[255] == np.float32(1.007874)
+
+
+@pytest.mark.parametrize("nbytes", [2, 14, 16, 30, 4096, 1024 * 1024 + 6, 2_400_000 * 2])
+def test_unpack_random_bit_exact(ctx, nbytes):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(nbytes)
+    b = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    got = blocks.data_to_samples(ctx, dev(b, ctx)).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.data_to_samples(b).view(np.uint32))
+
+
+def test_unpack_unaligned_and_empty(ctx):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(5)
+    b = rng.integers(0, 256, 1001 * 2 + 2, dtype=np.uint8)
+    d = dev(b, ctx)[2:]                                     # 2-byte offset: not 16-byte aligned
+    got = blocks.data_to_samples(ctx, d.contiguous() if not d.is_contiguous() else d).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.data_to_samples(b[2:]).view(np.uint32))
+    assert blocks.data_to_samples(ctx, dev(np.empty(0, np.uint8), ctx)).numel() == 0
+
+
+def test_unpack_odd_length_fails_like_reference(ctx):
+    from libredio_b200 import blocks
+    with pytest.raises(capi.LrcError) as e:
+        blocks.data_to_samples(ctx, dev(np.zeros(7, np.uint8), ctx))
+    assert e.value.status == capi.ERR_ODD_LENGTH
+    with pytest.raises(IndexError):
+        oracle.data_to_samples(np.zeros(7, np.uint8))
+
+
+# ---- (2) FIR + decimate ----------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [64, 73, 74, 640, 8960 + 54, 8960 + 55, 8960 + 64, 100_003, 2_400_000])
+def test_fir64_decim10_cf32_vs_oracle(ctx, n):
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    x = synth.cf32_noise_tones(n, seed=n)
+    fir = blocks.Fir(ctx, taps, 10)
+    got = fir.run(dev(x, ctx)).cpu().numpy()
+    ref = oracle.fir_decimate(x, taps, 10)
+    assert got.shape == ref.shape == ((n - 64) // 10 + 1,)
+    assert_close_rms(got, ref)
+    fir.close()
+
+
+def test_fir_shorter_than_taps_is_empty(ctx):
+    from libredio_b200 import blocks
+    fir = blocks.Fir(ctx, synth.lpf_taps(64, 0.04), 10)
+    assert fir.run(dev(synth.cf32_noise_tones(63), ctx)).numel() == 0
+    assert oracle.fir_decimate(synth.cf32_noise_tones(63), synth.lpf_taps(64, 0.04), 10).size == 0
+    fir.close()
+
+
+def test_fir_multichannel_and_unaligned(ctx):
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    n_ch, n = 5, 20_001                                   # odd stride: rows 2..4 are not 16-byte aligned
+    x = np.stack([synth.cf32_noise_tones(n, seed=100 + c) for c in range(n_ch)])
+    fir = blocks.Fir(ctx, taps, 10)
+    got = fir.run(dev(x, ctx)).cpu().numpy()
+    for c in range(n_ch):
+        assert_close_rms(got[c], oracle.fir_decimate(x[c], taps, 10))
+    fir.close()
+
+
+@pytest.mark.parametrize("ntaps,decim,n", [(1, 1, 100), (5, 3, 1000), (33, 1, 5000), (64, 5, 30_000), (129, 16, 40_000), (4, 10, 1003)])
+def test_fir_generic_shapes_vs_oracle(ctx, ntaps, decim, n):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(ntaps * 1000 + decim)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    x = synth.cf32_noise_tones(n, seed=7)
+    fir = blocks.Fir(ctx, taps, decim)
+    got = fir.run(dev(x, ctx)).cpu().numpy()
+    assert_close_rms(got, oracle.fir_decimate(x, taps, decim))
+    # 'full' (convolve everything, then stride) is the same function
+    assert np.array_equal(oracle.fir_decimate(x, taps, decim, full=True), oracle.fir_decimate(x, taps, decim))
+    fir.close()
+
+
+def test_fir_matches_reference_convolve_on_real_planes(ctx):
+    """dsputils::convolve is real-only: the cf32 kernel must equal convolve() on each plane."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    x = synth.cf32_noise_tones(5000, seed=9)
+    fir = blocks.Fir(ctx, taps, 1)
+    got = fir.run(dev(x, ctx)).cpu().numpy()
+    assert_close_rms(got.real, oracle.convolve(x.real.copy(), taps))
+    assert_close_rms(got.imag, oracle.convolve(x.imag.copy(), taps))
+    fir.close()
+
+
+@pytest.mark.parametrize("n", [64, 8960 + 54, 250_000])
+def test_fir_fused_u8_vs_oracle(ctx, n):
+    """config 1: u8 IQ -> i2f -> FIR64 /10, unpack fused into the FIR tile."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    iq = synth.iq_tone_noise_u8(n, seed=1)
+    fir = blocks.Fir(ctx, taps, 10)
+    got = fir.run_u8(dev(iq, ctx)).cpu().numpy()
+    ref = oracle.fir_decimate(oracle.data_to_samples(iq), taps, 10)
+    assert_close_rms(got, ref)
+    fir.close()
+
+
+def test_fir_nan_taps_rejected(ctx):
+    """dsputils::lpf yields NaN taps in the reference (window bug); the GPU plan refuses them loudly."""
+    from libredio_b200 import blocks
+    bad = oracle.lpf(64, 0.04, faithful=True)
+    assert not np.all(np.isfinite(bad))
+    with pytest.raises(capi.LrcError):
+        blocks.Fir(ctx, bad, 10)
+
+
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("chunks", [[5000], [63, 1, 1, 700, 4235], [9014, 9014, 13], [10] * 50 + [4500]])
+def test_fir_stream_is_seam_exact(ctx, chunks, u8):
+    """output must be independent of chunking: bit-identical to one call over the whole stream."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    n, n_ch = sum(chunks), 3
+    if u8:
+        x = np.stack([synth.iq_tone_noise_u8(n, seed=c) for c in range(n_ch)])
+    else:
+        x = np.stack([synth.cf32_noise_tones(n, seed=c) for c in range(n_ch)])
+    fir = blocks.Fir(ctx, taps, 10)
+    whole = (fir.run_u8(dev(x, ctx)) if u8 else fir.run(dev(x, ctx))).cpu().numpy()
+    st = blocks.FirStream(fir, n_ch, max(chunks), u8=u8)
+    outs, pos = [], 0
+    for c in chunks:
+        w = 2 * c if u8 else c
+        p = 2 * pos if u8 else pos
+        outs.append(st.push(dev(x[:, p:p + w], ctx)).cpu().numpy())
+        pos += c
+    got = np.concatenate(outs, axis=1)
+    assert got.shape == whole.shape
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    st.close(); fir.close()
+
+
+# ---- (3) FFT -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("inv", [0, 1])
+def test_fft_vs_golden_and_oracle(ctx, golden, n, inv):
+    from libredio_b200 import blocks
+    import tests.golden.make_golden as mg
+    x = mg.fft_input(n)
+    f = blocks.Fft(ctx, n, inv)
+    got = f.run(dev(x, ctx)).cpu().numpy()
+    assert_close_rms(got, golden[f"{'inv' if inv else 'fwd'}_{n}"])          # the reference's own output
+    assert_close_rms(got, oracle.fft(x, bool(inv)))                           # the restatement
+    # and the self-test of the reference: SNR vs an f64 DFT (test_vs_dft.c), >= 100 dB (mk_test.py:30)
+    exact = np.fft.ifft(x.astype(np.complex128)) * n if inv else np.fft.fft(x.astype(np.complex128))
+    assert D.snr_db(exact, got) >= 100.0
+    f.close()
+
+
+@pytest.mark.parametrize("n,batch", [(1024, 1), (1024, 7), (1024, 4097), (64, 1000), (8, 3), (8192, 5), (256, 33)])
+def test_fft_batched_inplace_and_ragged_batch(ctx, n, batch):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(n + batch)
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    f = blocks.Fft(ctx, n, 0)
+    ref = np.fft.fft(x.astype(np.complex128), axis=-1)
+    d = dev(x, ctx)
+    got = f.run(d).cpu().numpy()
+    assert_close_rms(got, ref)
+    f.run(d, inplace=True)                                 # fin == fout is allowed (kiss_fft.c:373-379)
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), got.view(np.uint32))
+    f.close()
+
+
+def test_fft_golden_vector_of_reference_tree(ctx, golden):
+    """test/fft.py:95-98, tolerance 1e-5 (:104): 8-point real sequence and its spectrum."""
+    from libredio_b200 import blocks
+    f = blocks.Fft(ctx, 8, 0)
+    got = f.run(dev(golden["fftpy_tvec"].astype(np.complex64), ctx)).cpu().numpy()
+    assert np.max(np.abs(got - golden["fftpy_Ftvec"])) < 1e-5
+    f.close()
+
+
+def test_fft_roundtrip_is_scaled_by_n(ctx):
+    """neither direction scales (libkissfft/README:105): ifft(fft(x)) == n*x"""
+    from libredio_b200 import blocks
+    n = 1024
+    x = synth.cf32_noise_tones(n * 9, seed=3).reshape(9, n)
+    fw, bw = blocks.Fft(ctx, n, 0), blocks.Fft(ctx, n, 1)
+    back = bw.run(fw.run(dev(x, ctx))).cpu().numpy()
+    assert_close_rms(back, n * x)
+    fw.close(); bw.close()
+
+
+def test_fft_block_size_mismatch_and_unsupported(ctx):
+    from libredio_b200 import blocks
+    f = blocks.Fft(ctx, 1024, 0)
+    with pytest.raises(capi.LrcError) as e:                 # assert!(din.len() == block_size) kissfft.rs:24
+        f.run(dev(np.zeros(1000, np.complex64), ctx))
+    assert e.value.status == capi.ERR_LENGTH
+    with pytest.raises(capi.LrcError) as e:
+        f.run_host(np.zeros(1000, np.complex64))
+    assert e.value.status == capi.ERR_LENGTH
+    with pytest.raises(capi.LrcError) as e:                 # kissfft accepts 1000 = 2^3 5^3; we say so loudly
+        blocks.Fft(ctx, 1000, 0)
+    assert e.value.status == capi.ERR_UNSUPPORTED
+    f.close()
+
+
+def test_fft_host_entry_point(ctx):
+    from libredio_b200 import blocks
+    x = synth.cf32_noise_tones(1024 * 3, seed=11)
+    f = blocks.Fft(ctx, 1024, 0)
+    got = f.run_host(x)
+    assert_close_rms(got.reshape(3, 1024), oracle.fft(x.reshape(3, 1024)))
+    f.close()
+
+
+# ---- window + |X|^2 averaging ------------------------------------------------------------------------
+@pytest.mark.parametrize("nfft,k,frames", [(1024, 1, 3), (1024, 64, 256), (1024, 20, 47), (1024, 300, 650),
+                                           (256, 8, 64), (64, 5, 100), (4096, 4, 16), (16, 3, 10)])
+def test_psd_rows_vs_f64(ctx, nfft, k, frames):
+    from libredio_b200 import blocks
+    x = synth.cf32_noise_tones(nfft * frames, seed=nfft + k)
+    p = blocks.Psd(ctx, nfft, capi.WINDOW_HANN)
+    got = p.run(dev(x, ctx), k).cpu().numpy()
+    ref = D.psd_rows(x, nfft, k, D.hann_periodic(nfft))
+    assert got.shape == ref.shape == (frames // k, nfft)
+    assert np.max(np.abs(got - ref)) <= TOL * np.sqrt(np.mean(ref ** 2))
+    p.close()
+
+
+def test_psd_no_window_matches_psdpng_accumulation(ctx):
+    """tools/psdpng.c:165-166: mag2 += r^2 + i^2 per frame on kiss_fft output, no window."""
+    from libredio_b200 import blocks
+    nfft, k = 1024, 20                                       # navg = 20, psdpng.c:29
+    x = synth.cf32_noise_tones(nfft * k * 2, seed=21)
+    p = blocks.Psd(ctx, nfft, capi.WINDOW_NONE)
+    got = p.run(dev(x, ctx), k).cpu().numpy()
+    spec = oracle.fft(x.reshape(-1, nfft))
+    mag2 = (spec.real.astype(np.float64) ** 2 + spec.imag.astype(np.float64) ** 2).reshape(2, k, nfft).sum(1) / k
+    assert np.max(np.abs(got - mag2)) <= TOL * np.sqrt(np.mean(mag2 ** 2))
+    p.close()
+
+
+# ---- fused chain ---------------------------------------------------------------------------------------
+def chain_ref(x, taps, decim, nfft, k):
+    z = oracle.fir_decimate(x, taps, decim)                  # strict-f32 reference FIR
+    return D.psd_rows(z, nfft, k, D.hann_periodic(nfft))
+
+
+@pytest.mark.parametrize("frames,k", [(1, 1), (3, 1), (16, 16), (40, 8), (70, 35), (130, 64), (50, 50)])
+def test_chain_fused_vs_oracle(ctx, frames, k):
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    n = frames * 10240 + 54 + 17                             # a few samples more than whole frames
+    x = synth.cf32_noise_tones(n, seed=frames)
+    ch = blocks.Chain(ctx, taps, 10, 1024)
+    assert ch.frames(n) == frames
+    got = ch.run(dev(x, ctx), k).cpu().numpy()
+    ref = chain_ref(x, taps, 10, 1024, k)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL * np.sqrt(np.mean(ref ** 2))
+    ch.close()
+
+
+def test_chain_fused_equals_unfused_kernels(ctx):
+    """linearity/consistency at a size the oracle would not finish quickly: the fused kernel must agree with
+    FIR kernel -> PSD kernel to float rounding."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    frames, k = 2048, 64
+    n = frames * 10240 + 54
+    g = torch.Generator(device=ctx.tdev).manual_seed(1)
+    x = torch.randn(n, 2, device=ctx.tdev, generator=g)
+    x = torch.view_as_complex(x)
+    ch, fir, psd = blocks.Chain(ctx, taps, 10, 1024), blocks.Fir(ctx, taps, 10), blocks.Psd(ctx, 1024)
+    a = ch.run(x, k)
+    b = psd.run(fir.run(x)[: frames * 1024], k)
+    assert a.shape == b.shape == (frames // k, 1024)
+    err = (a - b).abs().max().item()
+    assert err <= 1e-5 * b.pow(2).mean().sqrt().item()
+    ch.close(); fir.close(); psd.close()
+
+
+def test_chain_generic_shape_falls_back_to_unfused(ctx):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(0)
+    taps = (rng.standard_normal(33) / 6).astype(np.float32)
+    frames, k, nfft, decim = 24, 4, 256, 4
+    n = frames * nfft * decim + 33 - decim
+    x = synth.cf32_noise_tones(n, seed=5)
+    ch = blocks.Chain(ctx, taps, decim, nfft)
+    got = ch.run(dev(x, ctx), k).cpu().numpy()
+    ref = chain_ref(x, taps, decim, nfft, k)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL * np.sqrt(np.mean(ref ** 2))
+    ch.close()
+
+
+@pytest.mark.parametrize("frames,k", [(100, 10), (900, 900), (1000, 64), (37, 1)])
+def test_chain_host_ring_matches_device_path(ctx, frames, k):
+    """the HOST-buffer entry point (pinned ring, chunked H2D overlapped with the kernel) must give the
+    same rows as the device-resident call."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    n = frames * 10240 + 54
+    xh = torch.from_numpy(synth.cf32_noise_tones(n, seed=k)).pin_memory()
+    ch = blocks.Chain(ctx, taps, 10, 1024)
+    a = ch.run(xh.to(ctx.tdev), k).cpu()
+    b = ch.run_host(xh, k)
+    assert a.shape == b.shape == (frames // k, 1024)
+    # rows that span several ring segments are summed in a different order: float rounding only
+    assert (a - b).abs().max().item() <= 1e-5 * a.pow(2).mean().sqrt().item()
+    ch.close()

@@ -1,0 +1,136 @@
+"""GPU parity, part 2: quadrature FM discriminator and rational polyphase resampler (north_star subsystem 4).
+
+Tolerance (BASELINE.json): output SNR >= 100 dB against the f64 oracle (oracle/defined_f64.py).
+The resampler oracle is OUR definition -- libsamplerate parity is unpinned.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import defined_f64 as D
+from libredio_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+MIN_SNR_DB = 100.0
+
+
+def dev(a, ctx):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
+
+
+def fm_signal(n, seed):
+    iq = synth.fm_iq_u8(n * 10 + 64, seed=seed)
+    return oracle.fir_decimate(oracle.data_to_samples(iq), synth.lpf_taps(64, 0.04), 10)[:n]
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 60_001])
+def test_fm_discriminator_snr(ctx, n):
+    from libredio_b200 import blocks
+    x = fm_signal(n, seed=3)
+    got = blocks.fm_demod(ctx, dev(x, ctx)).cpu().numpy()
+    ref = D.fm_discriminator(x)
+    assert got.shape == ref.shape
+    assert got[0] == 0.0                                     # x[-1] = 0 -> atan2(0, 0) = 0
+    if n > 1:
+        assert D.snr_db(ref, got) >= MIN_SNR_DB
+
+
+def test_fm_discriminator_state_is_carried_across_chunks(ctx):
+    from libredio_b200 import blocks
+    n_ch, n = 4, 30_000
+    x = np.stack([fm_signal(n, seed=3 + c) for c in range(n_ch)])
+    whole = blocks.fm_demod(ctx, dev(x, ctx)).cpu().numpy()
+    state = torch.zeros(n_ch, dtype=torch.complex64, device=ctx.tdev)
+    parts, pos = [], 0
+    for c in (1, 999, 14_000, 15_000):
+        parts.append(blocks.fm_demod(ctx, dev(x[:, pos:pos + c], ctx), state).cpu().numpy())
+        pos += c
+    got = np.concatenate(parts, axis=1)
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    for c in range(n_ch):
+        assert D.snr_db(D.fm_discriminator(x[c]), got[c]) >= MIN_SNR_DB
+
+
+@pytest.mark.parametrize("ratio,n", [(0.2, 48_000), (0.5, 10_000), (2.0, 1000), (48000 / 44100, 8820), (3 / 7, 7001), (1.0, 500)])
+def test_resampler_snr_vs_f64_definition(ctx, ratio, n):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(int(ratio * 1000) + n)
+    t = np.arange(n)
+    x = (np.sin(2 * np.pi * 0.01 * t) + 0.5 * np.sin(2 * np.pi * 0.037 * t + 1) + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    rs = blocks.Resampler(ctx, ratio, 1, n)
+    L, M = D.resampler_ratio(ratio)
+    assert (rs.L, rs.M) == (L, M)
+    # the device-side filter design equals the oracle's definition
+    h_ref = D.resampler_taps(L, M)
+    assert rs.taps().shape == h_ref.shape and np.max(np.abs(rs.taps() - h_ref)) < 1e-12 * np.max(np.abs(h_ref)) + 1e-15
+    got = rs.process(dev(x, ctx)).cpu().numpy()
+    ref = D.resample(x, ratio)
+    assert got.shape == ref.shape == ((n * L - 1) // M + 1,)
+    assert got.size <= int(ratio * n + 1) + 1                # fits the reference's output sizing (samplerate.rs:64)
+    assert D.snr_db(ref, got) >= MIN_SNR_DB
+    rs.close()
+
+
+def test_resampler_smoke_case_of_reference(ctx):
+    """the only 'test' in the reference: resample a 1000-sample sine by 2.0 and print the length
+    (samplerate.rs:89-96)."""
+    from libredio_b200 import blocks
+    v = np.sin(np.arange(1000, dtype=np.float32) / 1000.0).astype(np.float32)
+    rs = blocks.Resampler(ctx, 2.0, 1, 1000)
+    out = rs.process(dev(v, ctx))
+    assert out.numel() == 2000 - 1 or out.numel() == 2000
+    rs.close()
+
+
+def test_resampler_streaming_is_chunk_independent(ctx):
+    from libredio_b200 import blocks
+    n_ch, n, ratio = 3, 24_000, 0.2
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((n_ch, n)).astype(np.float32)
+    rs = blocks.Resampler(ctx, ratio, n_ch, n)
+    whole = rs.process(dev(x, ctx)).cpu().numpy()
+    rs.reset()
+    parts, pos = [], 0
+    for c in (1, 4, 5, 990, 11_000, 12_000):
+        parts.append(rs.process(dev(x[:, pos:pos + c], ctx)).cpu().numpy())
+        pos += c
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == whole.shape
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    for c in range(n_ch):
+        assert D.snr_db(D.resample(x[c], ratio), got[c]) >= MIN_SNR_DB
+    rs.close()
+
+
+def test_resampler_unsupported_ratio_is_loud(ctx):
+    from libredio_b200 import blocks
+    with pytest.raises(capi.LrcError) as e:
+        blocks.Resampler(ctx, np.pi / 3, 1, 100)
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
+def test_fm_broadcast_chain_config3(ctx):
+    """config 3 end to end on a few channels: u8 IQ 2.4 Msps -> fused unpack+FIR64/10 -> discriminator ->
+    resample 1/5 -> 48 kHz; every stage against its oracle on the previous stage's GPU output."""
+    from libredio_b200 import blocks
+    n_ch, n = 4, 240_000
+    taps = synth.lpf_taps(64, 0.04)
+    iq = np.stack([synth.fm_iq_u8(n, seed=3 + c) for c in range(n_ch)])
+    fir = blocks.Fir(ctx, taps, 10)
+    bb = fir.run_u8(dev(iq, ctx))
+    d = blocks.fm_demod(ctx, bb)
+    rs = blocks.Resampler(ctx, 0.2, n_ch, d.shape[1])
+    audio = rs.process(d).cpu().numpy()
+    bb_h, d_h = bb.cpu().numpy(), d.cpu().numpy()
+    for c in range(n_ch):
+        ref_bb = oracle.fir_decimate(oracle.data_to_samples(iq[c]), taps, 10)
+        assert np.max(np.abs(bb_h[c] - ref_bb)) <= 1e-4 * np.sqrt(np.mean(np.abs(ref_bb) ** 2))
+        assert D.snr_db(D.fm_discriminator(bb_h[c]), d_h[c]) >= MIN_SNR_DB
+        assert D.snr_db(D.resample(d_h[c], 0.2), audio[c]) >= MIN_SNR_DB
+    assert audio.shape[1] == (d.shape[1] - 1) // 5 + 1
+    # the 1 kHz programme tone must dominate the demodulated audio spectrum
+    spec = np.abs(np.fft.rfft(audio[0][2000:] * np.hanning(audio[0][2000:].size)))
+    f = np.fft.rfftfreq(audio[0][2000:].size, 1 / 48000.0)
+    assert abs(f[np.argmax(spec[5:]) + 5] - 1000.0) < 30.0
+    fir.close(); rs.close()
