@@ -55,6 +55,8 @@ int lrc_ctx_sm_count(lrc_ctx *ctx, int *n_sm);
 /* pinned host memory for the ring / *_host entry points */
 int lrc_host_alloc(lrc_ctx *ctx, size_t bytes, void **h_ptr);
 int lrc_host_free(lrc_ctx *ctx, void *h_ptr);
+/* synchronous device -> host copy (for the debug views below and bindings without a CUDA runtime) */
+int lrc_copy_to_host(lrc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * (1) u8 IQ -> complex f32.   Replaces rtlsdr::i2f / rtlsdr::data_to_samples

@@ -288,3 +288,104 @@ class Resampler:
         if self.h:
             self.ctx.lib.lrc_resampler_destroy(self.h)
             self.h = C.c_void_p()
+
+
+# ---- long FIR (config 5) ----------------------------------------------------------------------------
+class FastFir:
+    """kiss_fastfir: overlap-save convolution with the nh-1 transient removed (tools/kiss_fastfir.c)."""
+
+    def __init__(self, ctx: Context, h, nfft: int = 0):
+        self.ctx = ctx
+        self.taps = np.ascontiguousarray(h, dtype=np.complex64)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_fastfir_create(ctx.h, _p(self.taps), self.taps.size, nfft, C.byref(self.h)), "lrc_fastfir_create")
+        self.nfft = int(ctx.lib.lrc_fastfir_nfft(self.h))
+        self.ngood = self.nfft - self.taps.size + 1
+
+    def out_len(self, n_in: int, flush: bool = False) -> int:
+        return int(self.ctx.lib.lrc_fastfir_out_len(self.h, n_in, int(flush)))
+
+    def run(self, x: torch.Tensor, flush: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+        assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous() and x.dim() == 1
+        no = self.out_len(x.numel(), flush)
+        if out is None:
+            out = torch.empty(max(no, 1), dtype=torch.complex64, device=x.device)
+        n = C.c_size_t()
+        check(self.ctx.lib.lrc_fastfir_run(self.h, _p(x), x.numel(), _p(out), int(flush), C.byref(n), _stream()),
+              "lrc_fastfir_run")
+        assert n.value == no
+        return out[:no]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_fastfir_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+# ---- (5) OOK ------------------------------------------------------------------------------------------
+class Ook:
+    """The OOK chain of ratpak.rs:60-111 over n_streams finite u8-IQ captures of n_blocks*512 samples."""
+
+    FIELDS_A1 = (4, 8, 4, 12, 8)      # binconv, ratpak.rs:115
+    FIELDS_A2 = (4, 8, 2, 10, 12)     # binconv, ratpak.rs:119
+
+    def __init__(self, ctx: Context, n_streams: int, n_blocks: int, sample_rate: int = 256000,
+                 max_runs: int = 4096, max_packets: int = 64):
+        self.ctx, self.n_streams, self.n_blocks = ctx, n_streams, n_blocks
+        self.max_runs, self.max_packets = max_runs, max_packets
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_ook_create(ctx.h, n_streams, n_blocks, sample_rate, max_runs, max_packets, C.byref(self.h)),
+              "lrc_ook_create")
+
+    def decode(self, iq: torch.Tensor):
+        """iq: uint8 [n_streams, n_blocks*1024] on the device.  Asynchronous."""
+        assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous()
+        assert iq.shape == (self.n_streams, self.n_blocks * 1024)
+        check(self.ctx.lib.lrc_ook_decode(self.h, _p(iq), iq.shape[1], _stream()), "lrc_ook_decode")
+
+    def packets(self):
+        """-> list of (stream, proto, seq, bits uint8[nbits]) ordered by (stream, proto, seq)."""
+        n = C.c_size_t()
+        cap = self.n_streams * 2 * self.max_packets
+        buf = (capi.OokPacket * max(cap, 1))()
+        check(self.ctx.lib.lrc_ook_fetch_packets(self.h, buf, cap, C.byref(n)), "lrc_ook_fetch_packets")
+        out = []
+        for k in range(n.value):
+            p = buf[k]
+            out.append((p.stream, p.proto, p.seq, np.frombuffer(bytes(p.bits)[: p.nbits], dtype=np.uint8).copy()))
+        return out
+
+    def debug(self) -> dict:
+        """Intermediate products copied to the host: block_sums [S, B] f32, n_runs [S], runs [S, max_runs]
+        as (value << 31 | length), n_bits [S]."""
+        ps = [C.c_void_p() for _ in range(4)]
+        check(self.ctx.lib.lrc_ook_debug_ptrs(self.h, *[C.byref(p) for p in ps]), "lrc_ook_debug_ptrs")
+        S, B, R = self.n_streams, self.n_blocks, self.max_runs
+        out = {}
+        for name, ptr, shape, dt in (("block_sums", ps[0], (S, B), np.float32), ("n_runs", ps[1], (S,), np.uint32),
+                                     ("runs", ps[2], (S, R), np.uint32), ("n_bits", ps[3], (S,), np.uint32)):
+            host = np.empty(shape, dtype=dt)
+            check(self.ctx.lib.lrc_copy_to_host(self.ctx.h, _p(host), ptr, host.nbytes), "lrc_copy_to_host")
+            out[name] = host
+        return out
+
+    @staticmethod
+    def eat(bits, widths):
+        lib = capi.load()
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        w = np.ascontiguousarray(widths, dtype=np.uint64)
+        out = np.empty(w.size, dtype=np.uint64)
+        check(lib.lrc_eat(_p(b), b.size, _p(w), w.size, _p(out)), "lrc_eat")
+        return [int(v) for v in out]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_ook_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def ook_envelope_table(ctx: Context) -> torch.Tensor:
+    """|i2f(b0) + j i2f(b1)| for all 65536 byte pairs, computed by the device routine the OOK kernels use."""
+    t = torch.empty(65536, dtype=torch.float32, device=ctx.tdev)
+    check(ctx.lib.lrc_ook_envelope_table(ctx.h, _p(t), _stream()), "lrc_ook_envelope_table")
+    return t.reshape(256, 256)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lrc_ctx_sm_count": (_i, [_vp, C.POINTER(_i)]),
     "lrc_host_alloc": (_i, [_vp, _sz, _pp]),
     "lrc_host_free": (_i, [_vp, _vp]),
+    "lrc_copy_to_host": (_i, [_vp, _vp, _vp, _sz]),
     "lrc_unpack_u8_cf32": (_i, [_vp, _u8p, _sz, _fp, _vp]),
     "lrc_fir_create": (_i, [_vp, _fp, _i, _i, _pp]),
     "lrc_fir_destroy": (_i, [_vp]),

@@ -97,3 +97,13 @@ extern "C" int lrc_host_free(lrc_ctx *c, void *h_ptr)
     if (h_ptr) LRC_CUDA(cudaFreeHost(h_ptr));
     return LRC_OK;
 }
+
+extern "C" int lrc_copy_to_host(lrc_ctx *c, void *h_dst, const void *d_src, size_t bytes)
+{
+    LRC_BIND(c);
+    if (bytes == 0) return LRC_OK;
+    LRC_REQUIRE(h_dst && d_src, LRC_ERR_INVALID, "lrc_copy_to_host: null pointer");
+    LRC_CUDA(cudaDeviceSynchronize());
+    LRC_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return LRC_OK;
+}

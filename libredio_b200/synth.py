@@ -86,7 +86,7 @@ def _ook_runs_proto_b(bits, rng):
     return runs
 
 
-def ook_capture_u8(n_blocks: int, seed: int = 4, n_packets: int = 2, noise_lsb: float = 2.0):
+def ook_capture_u8(n_blocks: int, seed: int = 4, n_packets: int = 2, noise_lsb: float = 1.0, amp: float = 0.7):
     """One stream: noise floor + OOK bursts carrying proto-A (36-bit) / proto-B (24-bit) packets.
     Returns (iq u8 [n_blocks*1024], list of (proto, bits))."""
     rng = np.random.default_rng(seed)
@@ -109,10 +109,14 @@ def ook_capture_u8(n_blocks: int, seed: int = 4, n_packets: int = 2, noise_lsb: 
         for v, d in runs:
             m = max(1, int(round(d * OOK_RATE)))
             if v:
-                env[p:p + m] = 0.55 + 0.05 * rng.standard_normal()
+                env[p:p + m] = amp + 0.05 * rng.standard_normal()
             p += m
         sent.append((proto, bits))
         pos = p + 70 * OOK_BLOCK + int(rng.integers(0, 20000))
+    # kpn::rle never flushes the final run (kpn.rs:17-29), so the last packet only comes out once a LATER
+    # burst changes the bit value again: end the capture with a lone terminator pulse
+    if pos + 64 * OOK_BLOCK < n:
+        env[pos:pos + 300] = amp
     ph = rng.uniform(0, 2 * np.pi, n)
     z = env * np.exp(1j * ph)
     i = 127.0 + 127.0 * z.real + noise_lsb * rng.standard_normal(n)

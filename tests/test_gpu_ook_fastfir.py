@@ -1,0 +1,203 @@
+"""GPU parity, part 3: the bit-exact OOK chain (north_star subsystem 5) and the overlap-save long FIR.
+
+OOK: every intermediate that the reference computes in f32 (envelope, block sums) must be BIT-identical to
+the CPU restatement, and so must the run lengths and decoded packet bits.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from libredio_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, ctx):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
+
+
+# ---- OOK -------------------------------------------------------------------------------------------------
+def test_envelope_exhaustive_65536_pairs_bit_exact(ctx):
+    """inputs come from u8, so there are only 65536 distinct (re, im) pairs: CPU == GPU is checked exhaustively"""
+    from libredio_b200 import blocks
+    got = blocks.ook_envelope_table(ctx).cpu().numpy()
+    ref = oracle.norm_table()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert got[127, 127] == 0.0 and got[254, 127] == 1.0
+    # spot-check the table builder against the scalar C function
+    for b0, b1 in ((0, 0), (255, 255), (3, 200), (128, 126)):
+        assert ref[b0, b1] == oracle.norm(oracle.i2f(b0), oracle.i2f(b1))
+
+
+def noisy_burst_capture(seed, n_blocks=400):
+    """quiet floor with two stretches of full-scale random bytes: the envelope crosses max/2 thousands of times"""
+    rng = np.random.default_rng(seed)
+    iq = np.clip(np.rint(127 + 1.0 * rng.standard_normal(n_blocks * 1024)), 0, 255).astype(np.uint8)
+    for start, length in ((100, 30), (250, 5)):
+        iq[start * 1024:(start + length) * 1024] = rng.integers(0, 256, length * 1024, dtype=np.uint8)
+    return iq
+
+
+def run_ook(ctx, caps, max_runs=4096):
+    from libredio_b200 import blocks
+    iq = np.stack(caps)
+    n_streams, nbytes = iq.shape
+    ook = blocks.Ook(ctx, n_streams, nbytes // 1024, 256000, max_runs, 64)
+    ook.decode(dev(iq, ctx))
+    pk = ook.packets()
+    dbg = ook.debug()
+    ook.close()
+    return pk, dbg
+
+
+def check_against_oracle(caps, pk, dbg):
+    for s, iq in enumerate(caps):
+        r = oracle.ook_decode(iq)
+        # f32 block sums: bit-identical (sequential order + exact envelope)
+        assert np.array_equal(dbg["block_sums"][s].view(np.uint32), r["block_sums"].view(np.uint32)), f"stream {s} sums"
+        assert dbg["n_bits"][s] == r["bits"].size, f"stream {s} bit count"
+        nr = int(dbg["n_runs"][s])
+        assert nr == r["run_val"].size, f"stream {s} run count"
+        runs = dbg["runs"][s][:nr]
+        assert np.array_equal(runs >> 31, r["run_val"]) and np.array_equal(runs & 0x7FFFFFFF, r["run_len"])
+        a = [p[3] for p in pk if p[0] == s and p[1] == 0]
+        b = [p[3] for p in pk if p[0] == s and p[1] == 1]
+        assert len(a) == len(r["a_packets"]) and len(b) == len(r["b_packets"])
+        for x, y in zip(a, r["a_packets"]):
+            assert np.array_equal(x, y)
+        for x, y in zip(b, r["b_packets"]):
+            assert np.array_equal(x, y)
+
+
+def test_ook_decodes_known_packets_bit_exact(ctx):
+    caps, sent = [], []
+    for s in range(16):
+        iq, snt = synth.ook_capture_u8(800, seed=4 + s, n_packets=3)
+        caps.append(iq); sent.append(snt)
+    pk, dbg = run_ook(ctx, caps)
+    check_against_oracle(caps, pk, dbg)
+    # and the decoded bits are the bits the generator sent (known by construction)
+    for s in range(16):
+        for proto in (0, 1):
+            got = [p[3] for p in pk if p[0] == s and p[1] == proto]
+            want = [b for pr, b in sent[s] if pr == proto]
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w)
+    assert sum(len(x) for x in sent) == len(pk) > 16
+
+
+@pytest.mark.parametrize("case", ["noise_only", "loud_noise", "ragged_blocks", "all_zero", "saturated", "burst_at_end"])
+def test_ook_edge_cases_match_oracle(ctx, case):
+    rng = np.random.default_rng(hash(case) % 1000)
+    if case == "noise_only":
+        caps = [np.clip(np.rint(127 + 1.5 * rng.standard_normal(300 * 1024)), 0, 255).astype(np.uint8) for _ in range(3)]
+    elif case == "loud_noise":      # thousands of short runs, nothing decodable
+        caps = [noisy_burst_capture(70 + s) for s in range(3)]
+    elif case == "ragged_blocks":   # n_blocks not a multiple of the 32-block warp group
+        caps = [synth.ook_capture_u8(401, seed=80 + s, n_packets=1)[0] for s in range(5)]
+    elif case == "all_zero":
+        caps = [np.zeros(64 * 1024, np.uint8), np.full(64 * 1024, 127, np.uint8)]
+    elif case == "saturated":
+        caps = [np.full(200 * 1024, 255, np.uint8), rng.integers(0, 256, 200 * 1024, dtype=np.uint8)]
+    else:                           # a burst still open when the capture ends is never sent (bitfount.rs:78-81)
+        iq, _ = synth.ook_capture_u8(500, seed=90, n_packets=1)
+        iq = iq.copy(); iq[-40 * 1024:] = np.clip(np.rint(127 + 90 * rng.standard_normal(40 * 1024)), 0, 255).astype(np.uint8)
+        caps = [iq]
+    pk, dbg = run_ook(ctx, caps, max_runs=1 << 18)
+    check_against_oracle(caps, pk, dbg)
+
+
+def test_ook_run_capacity_overflow_is_reported(ctx):
+    caps = [noisy_burst_capture(70)]
+    assert oracle.ook_decode(caps[0])["run_val"].size > 64
+    with pytest.raises(capi.LrcError) as e:
+        run_ook(ctx, caps, max_runs=64)
+    assert e.value.status == capi.ERR_CAPACITY
+
+
+def test_eat_and_b2d_micro_cases():
+    """kpn.rs:111-124 on the two field layouts of ratpak.rs:115,119 (host helper, no GPU work)"""
+    from libredio_b200 import blocks
+    assert blocks.Ook.eat([1, 0, 1], [3]) == [5] == [oracle.b2d([1, 0, 1])]
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2, 36).astype(np.uint8)
+    for w in (blocks.Ook.FIELDS_A1, blocks.Ook.FIELDS_A2):
+        assert blocks.Ook.eat(bits, w) == oracle.eat(bits, w)
+    with pytest.raises(capi.LrcError):
+        blocks.Ook.eat(bits[:24], blocks.Ook.FIELDS_A1)
+
+
+def test_ook_many_streams_sharded_equals_whole(ctx):
+    """config 4 shards streams across GPUs with no exchange: decoding a subset of the streams must give the
+    same packets as decoding them inside the full batch."""
+    caps = [synth.ook_capture_u8(450, seed=200 + s, n_packets=2)[0] for s in range(24)]
+    whole, _ = run_ook(ctx, caps)
+    for lo, hi in ((0, 12), (12, 24)):
+        part, _ = run_ook(ctx, caps[lo:hi])
+        want = [(p[0] - lo, p[1], p[2], p[3].tobytes()) for p in whole if lo <= p[0] < hi]
+        assert [(p[0], p[1], p[2], p[3].tobytes()) for p in part] == want
+
+
+# ---- overlap-save long FIR ---------------------------------------------------------------------------------
+def rms(a):
+    return float(np.sqrt(np.mean(np.abs(np.asarray(a, dtype=np.complex128)) ** 2)))
+
+
+def test_fastfir_vs_reference_golden(ctx, golden):
+    """outputs of the vendored tools/kiss_fastfir.c on the fixture of tests/golden/make_golden.py"""
+    from libredio_b200 import blocks
+    import tests.golden.make_golden as mg
+    h, x = mg.fastfir_case()
+    ff = blocks.FastFir(ctx, h, 0)
+    assert ff.nfft == 1024                                   # auto size: next pow2 >= 2*300, floor 1024
+    for flush, key in ((False, "fastfir_noflush"), (True, "fastfir_flush")):
+        got = ff.run(dev(x, ctx), flush).cpu().numpy()
+        ref = golden[key]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+    ff.close()
+
+
+@pytest.mark.parametrize("nh,n,nfft", [(1, 3000, 0), (50, 10_000, 128), (300, 6000, 0), (1024, 40_000, 0),
+                                       (4096, 70_000, 0), (4096, 8192, 0), (4096, 8191, 0), (17, 16, 64)])
+def test_fastfir_vs_oracle_and_direct_convolution(ctx, nh, n, nfft):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(nh + n)
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / np.sqrt(nh)).astype(np.complex64)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    ff = blocks.FastFir(ctx, h, nfft)
+    for flush in (False, True):
+        got = ff.run(dev(x, ctx), flush).cpu().numpy()
+        ref = oracle.fastfir(h, x, nfft, flush)
+        assert got.shape == ref.shape == (ff.out_len(n, flush),)
+        if ref.size:
+            assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+            # true convolution with the transient removed: y[k] = sum_j h[j] x[k + nh - 1 - j]
+            full = np.convolve(x.astype(np.complex128), h.astype(np.complex128))[nh - 1:]
+            assert np.max(np.abs(got - full[: got.size])) <= 1e-4 * rms(full)
+    ff.close()
+
+
+def test_fastfir_config5_shape_spot_windows(ctx):
+    """config 5 at a size the CPU cannot filter whole: 4096 taps, 2^24 samples generated on the device;
+    check random output windows (incl. block seams) against an f64 direct convolution."""
+    from libredio_b200 import blocks
+    nh, n = 4096, 1 << 24
+    rng = np.random.default_rng(6)
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64).astype(np.complex64)
+    g = torch.Generator(device=ctx.tdev).manual_seed(5)
+    x = torch.view_as_complex(torch.randn(n, 2, device=ctx.tdev, generator=g))
+    ff = blocks.FastFir(ctx, h, 0)
+    assert ff.nfft == 8192 and ff.ngood == 4097
+    y = ff.run(x)
+    assert y.numel() == ff.out_len(n) == ((n - 8192) // 4097 + 1) * 4097
+    hr = h[::-1].astype(np.complex128)
+    starts = [0, 4097 - 8, 4097 * 100 - 3, y.numel() - 64] + [int(v) for v in rng.integers(0, y.numel() - 64, 8)]
+    for s0 in starts:
+        seg = x[s0: s0 + 64 + nh - 1].cpu().numpy().astype(np.complex128)
+        ref = np.array([np.dot(seg[k:k + nh], hr) for k in range(64)])
+        got = y[s0:s0 + 64].cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+    ff.close()
