@@ -1,0 +1,201 @@
+"""CPU suite, part 1: the oracle against the reference's own golden vectors, known-answer tests and the
+fixtures generated from the vendored kissfft (tests/golden/make_golden.py).  No GPU, no product code."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import defined_f64 as D
+
+
+# ---- (1) i2f / data_to_samples: rtlsdr.rs:159-162 ----------------------------------------------------
+def test_i2f_hand_computed_micro_cases():
+    assert oracle.i2f(0) == np.float32(-1.0)
+    assert oracle.i2f(127) == np.float32(0.0)
+    assert oracle.i2f(254) == np.float32(1.0)
+    assert oracle.i2f(255) == np.float32(1.007874)
+    assert oracle.i2f(128) == np.float32(np.float32(128) / np.float32(127)) - np.float32(1)
+
+
+def test_data_to_samples_all_bytes_against_numpy_f32_ops():
+    b = np.arange(256, dtype=np.uint8).repeat(2)
+    got = oracle.data_to_samples(b)
+    ref = b.astype(np.float32) / np.float32(127.0) - np.float32(1.0)      # one f32 div, one f32 sub
+    assert np.array_equal(got.view(np.float32), ref)
+    with pytest.raises(IndexError):
+        oracle.data_to_samples(np.zeros(3, np.uint8))
+
+
+# ---- (2) convolve: dsputils.rs:30-32 --------------------------------------------------------------------
+def test_convolve_is_valid_mode_correlation_left_fold():
+    u = np.array([1, 2, 3, 4, 5], np.float32)
+    v = np.array([10, 1], np.float32)
+    assert oracle.convolve(u, v).tolist() == [12.0, 23.0, 34.0, 45.0]      # taps NOT reversed
+    assert oracle.convolve(u[:1], v).size == 0
+    # left fold from 0 in f32: (((0 + a) + b) + c), visible with cancellation
+    u = np.array([1e8, 1.0, -1e8], np.float32)
+    v = np.ones(3, np.float32)
+    assert oracle.convolve(u, v)[0] == np.float32(np.float32(np.float32(0 + 1e8) + 1) - 1e8) == 0.0
+
+
+def test_fir_decimate_definition():
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(np.complex64)
+    taps = rng.standard_normal(64).astype(np.float32)
+    for d in (1, 3, 10, 64, 100):
+        z = oracle.fir_decimate(x, taps, d)
+        assert z.size == (1000 - 64) // d + 1
+        assert np.array_equal(z.view(np.float32), oracle.fir_decimate(x, taps, d, full=True).view(np.float32))
+        assert np.array_equal(z.real, oracle.convolve(x.real.copy(), taps)[::d])
+        assert np.array_equal(z.imag, oracle.convolve(x.imag.copy(), taps)[::d])
+        ref = np.correlate(x.astype(np.complex128), taps.astype(np.float64), "valid")[::d]
+        assert np.max(np.abs(z - ref)) < 1e-4 * np.sqrt(np.mean(np.abs(ref) ** 2))
+
+
+def test_window_bug_of_reference_is_reproduced_and_corrected_designer_is_finite():
+    w = oracle.window(64, faithful=True)                 # dsputils.rs:49 swapped arguments
+    assert w.size == 65 and not np.isfinite(w[1])
+    assert not np.all(np.isfinite(oracle.lpf(64, 0.04, faithful=True)))
+    good = oracle.lpf(64, 0.04, faithful=False)
+    assert np.all(np.isfinite(good)) and abs(good.sum() - 1.0) < 0.05
+    from libredio_b200 import synth
+    assert np.max(np.abs(synth.lpf_taps(64, 0.04) - good)) < 1e-6
+
+
+# ---- (3) FFT vs the reference's outputs -----------------------------------------------------------------
+def test_restated_fft_vs_golden_fixtures_from_vendored_kissfft(golden):
+    import tests.golden.make_golden as mg
+    for n in golden["fft_sizes"]:
+        n = int(n)
+        x = mg.fft_input(n)
+        for inv, key in ((False, f"fwd_{n}"), (True, f"inv_{n}")):
+            got = oracle.fft(x, inv)
+            ref = golden[key]
+            if n & (n - 1) == 0:     # radix-4/2 path restated operation by operation: bit-identical
+                assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (n, inv)
+            else:                    # radix 3/5 use the generic O(p^2) sum: last-bit differences only
+                assert np.max(np.abs(got - ref)) < 2e-6 * np.sqrt(np.mean(np.abs(ref) ** 2)), (n, inv)
+
+
+def test_only_golden_vector_of_the_reference_tree(golden):
+    """test/fft.py:95-98, tolerance 1e-5 (:104)"""
+    F = oracle.fft(golden["fftpy_tvec"].astype(np.complex64))
+    assert np.max(np.abs(F - golden["fftpy_Ftvec"])) < 1e-5
+
+
+@pytest.mark.parametrize("n", [8, 36, 240, 1024, 1800])
+def test_fft_self_test_thresholds_of_reference(n):
+    """test_vs_dft.c / mk_test.py:30: SNR vs an exact DFT >= 100 dB for float"""
+    rng = np.random.default_rng(n)
+    x = (rng.integers(-32768, 32768, n) + 1j * rng.integers(-32768, 32768, n)).astype(np.complex64)
+    assert D.snr_db(np.fft.fft(x.astype(np.complex128)), oracle.fft(x)) >= 100.0
+    assert D.snr_db(np.fft.ifft(x.astype(np.complex128)) * n, oracle.fft(x, True)) >= 100.0
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_restated_fft_and_fastfir_bit_exact_vs_vendored_build():
+    rng = np.random.default_rng(1)
+    for n in (2, 64, 1024, 8192, 7, 11):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        for inv in (False, True):
+            assert np.array_equal(oracle.fft(x, inv).view(np.uint32), oracle.ref_kissfft(x, inv).view(np.uint32))
+    h = (rng.standard_normal(77) + 1j * rng.standard_normal(77)).astype(np.complex64)
+    x = (rng.standard_normal(5000) + 1j * rng.standard_normal(5000)).astype(np.complex64)
+    for flush in (False, True):
+        assert np.array_equal(oracle.fastfir(h, x, 0, flush).view(np.uint32), oracle.ref_fastfir(h, x, 0, flush).view(np.uint32))
+    assert np.max(np.abs(oracle.ref_fftr(np.arange(8, dtype=np.float32)) - np.fft.rfft(np.arange(8)))) < 1e-5
+
+
+def test_fastfir_vs_golden_and_definition(golden):
+    import tests.golden.make_golden as mg
+    h, x = mg.fastfir_case()
+    for flush, key in ((False, "fastfir_noflush"), (True, "fastfir_flush")):
+        got = oracle.fastfir(h, x, 0, flush)
+        assert np.array_equal(got.view(np.uint32), golden[key].view(np.uint32))
+    full = np.convolve(x.astype(np.complex128), h.astype(np.complex128))[h.size - 1:]
+    got = oracle.fastfir(h, x, 0, True)
+    assert got.size == x.size - h.size + 1                       # flush recovers every valid output
+    assert np.max(np.abs(got - full[: got.size])) < 1e-4 * np.sqrt(np.mean(np.abs(full) ** 2))
+    assert oracle.fastfir(h, x[:500], 0, False).size == 0        # less than one block (nfft = 1024)
+
+
+# ---- (5) OOK chain ------------------------------------------------------------------------------------------
+def f32(x):
+    return np.float32(x)
+
+
+def test_trigger_state_machine_hand_traced():
+    """bitfount.rs:46-81 traced by hand in numpy f32 on constant blocks"""
+    env = np.full(512, 0.01, np.float32)
+    s = f32(0)
+    for v in env:
+        s = f32(s + v)
+    quiet = np.zeros(20 * 1024, np.uint8) + 127                   # envelope exactly 0 -> s = 0 every block
+    r = oracle.ook_decode(quiet)
+    assert r["n_bursts"] == 0 and np.all(r["block_sums"] == 0) and r["bits"].size == 0
+    # threshold evolution for a constant block sum s: thr0 = s; each block thr += s/1000; thr -= thr*0.002
+    thr = s
+    for _ in range(5):
+        thr = f32(thr + f32(s / f32(1000)))
+        thr = f32(thr - f32(thr * f32(0.002)))
+    assert thr < s and not (s > f32(thr * f32(4)))                 # a constant floor never fires
+
+
+def test_first_burst_has_leading_zero_and_49_blocks():
+    rng = np.random.default_rng(3)
+    n_blocks = 200
+    iq = np.clip(np.rint(127 + rng.standard_normal(n_blocks * 1024)), 0, 255).astype(np.uint8)
+    iq[100 * 1024:101 * 1024] = 255                                # one loud block fires the trigger
+    r = oracle.ook_decode(iq)
+    assert r["n_bursts"] == 1
+    # counter 50 (the firing block) .. 2 are collected = 49 blocks, plus the 0.0 of vec!(0.0) (bitfount.rs:43)
+    assert r["bits"].size == 49 * 512 + 1
+    assert r["bits"][0] == 0 and r["bits"][1:513].all() and not r["bits"][513:].any()
+    # rle: (0,1) then (1,512) are emitted; the trailing zero run is never flushed (kpn.rs:17-29)
+    assert r["run_val"].tolist() == [0, 1] and r["run_len"].tolist() == [1, 512]
+
+
+def test_discretize_and_norm_definition():
+    b = oracle.discretize(np.array([0.0, 1.0, 0.5, 0.50001, 2.0], np.float32))
+    assert b.tolist() == [0, 0, 0, 0, 1]                           # x > max/2, strict
+    assert oracle.norm(3.0, 4.0) == 5.0
+    t = oracle.norm_table()
+    assert t.shape == (256, 256) and t[127, 127] == 0 and np.array_equal(t, t.T)
+
+
+def test_b2d_and_eat_micro_cases():
+    assert oracle.b2d([1, 0, 1]) == 5 and oracle.b2d([]) == 0 and oracle.b2d([1] * 12) == 4095
+    bits = [0, 1, 0, 1] + [1, 0, 0, 0, 0, 1, 1, 1] + [0, 1, 1, 0] + [0] * 11 + [1] + [1] * 8
+    assert oracle.eat(bits, [4, 8, 4, 12, 8]) == [5, 135, 6, 1, 255]
+    assert oracle.eat(bits, [4, 8, 2, 10, 12]) == [5, 135, 1, 512, 511]
+
+
+def test_ook_chain_decodes_constructed_packets():
+    from libredio_b200 import synth
+    for seed in range(6):
+        iq, sent = synth.ook_capture_u8(800, seed=seed, n_packets=3)
+        r = oracle.ook_decode(iq)
+        assert [tuple(p) for p in r["a_packets"]] == [tuple(b) for pr, b in sent if pr == 0]
+        assert [tuple(p) for p in r["b_packets"]] == [tuple(b) for pr, b in sent if pr == 1]
+
+
+# ---- north-star-defined stages ---------------------------------------------------------------------------------
+def test_defined_stages_sanity():
+    w = D.hann_periodic(1024)
+    assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3
+    x = np.exp(2j * np.pi * 0.05 * np.arange(100))
+    d = D.fm_discriminator(x)
+    assert d[0] == 0 and np.allclose(d[1:], 2 * np.pi * 0.05)
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
+    rows = D.psd_rows(z, 1024, 2, None)
+    assert rows.shape == (2, 1024) and np.isclose(rows.sum(), 1024 * np.sum(np.abs(z) ** 2) / 2)   # Parseval
+    assert D.resampler_ratio(0.2) == (1, 5) and D.resampler_ratio(48000 / 44100) == (160, 147)
+    with pytest.raises(ValueError):
+        D.resampler_ratio(np.pi)
+    h = D.resampler_taps(1, 5)
+    assert h.size == 321 and abs(h.sum() - 1) < 1e-12
+    y = D.resample(np.ones(4000), 0.2)
+    assert y.size == 800 and np.allclose(y[200:], 1.0, atol=1e-6)    # unity DC gain once the filter is full
+    assert D.resample(np.ones(1000), 2.0).size == 2000
