@@ -180,6 +180,10 @@ int    lrc_resampler_get_taps(const lrc_resampler *rs, double *h_taps, size_t ca
 size_t lrc_resampler_next_out_len(const lrc_resampler *rs, size_t n_in);
 int    lrc_resampler_process(lrc_resampler *rs, const float *d_in, size_t n_in, size_t in_stride,
                              float *d_out, size_t out_stride, size_t *n_out, void *stream);
+/* host-buffer variant with the calling convention of src_process (samplerate.rs:66-84): channel-major
+ * host input, caller-allocated host output of `out_cap` frames per channel; synchronous */
+int    lrc_resampler_process_host(lrc_resampler *rs, const float *h_in, size_t n_in, float *h_out,
+                                  size_t out_cap, size_t *n_out);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) OOK packet decode, bit-exact.   Replaces, per stream, the chain of src/ratpak.rs:60-111:

@@ -1,0 +1,69 @@
+/* A C program written against the reference's own FFI declarations -- the prototypes of
+ * libkissfft/kiss_fft.h:81-102 (what src/kissfft/src/kissfft.rs:11-16 binds) and of libsamplerate
+ * (src/samplerate/src/samplerate.rs:32-42) -- linked with -lkissfft -lsamplerate from libredio_b200/:
+ * the drop-in seams, exercised exactly as the unmodified reference would. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+typedef struct { float r, i; } kiss_fft_cpx;
+typedef struct kiss_fft_state *kiss_fft_cfg;
+kiss_fft_cfg kiss_fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem);
+void kiss_fft(kiss_fft_cfg cfg, const kiss_fft_cpx *fin, kiss_fft_cpx *fout);
+void kiss_fft_cleanup(void);
+
+typedef struct {
+    const float *data_in; float *data_out;
+    long input_frames, output_frames, input_frames_used, output_frames_gen;
+    int end_of_input; double src_ratio;
+} SRC_DATA;
+typedef struct SRC_STATE SRC_STATE;
+SRC_STATE *src_new(int converter_type, int channels, int *error);
+SRC_STATE *src_delete(SRC_STATE *state);
+int src_process(SRC_STATE *state, SRC_DATA *data);
+const char *src_strerror(int error);
+
+#define CHECK(c) do { if (!(c)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main(void)
+{
+    /* kissfft.rs:19-27: alloc once, then kiss_fft per frame */
+    const int n = 1024;
+    kiss_fft_cfg cfg = kiss_fft_alloc(n, 0, NULL, NULL);
+    CHECK(cfg != NULL);
+    kiss_fft_cpx *in = malloc(sizeof(kiss_fft_cpx) * n), *out = malloc(sizeof(kiss_fft_cpx) * n);
+    for (int k = 0; k < n; ++k) { in[k].r = (float)cos(2 * M_PI * 37 * k / n) + 0.25f; in[k].i = (float)sin(2 * M_PI * 37 * k / n); }
+    kiss_fft(cfg, in, out);
+    CHECK(fabs(out[37].r - n) < 1e-2 && fabs(out[37].i) < 1e-2);       /* unit tone in bin 37, unscaled */
+    CHECK(fabs(out[0].r - 0.25 * n) < 1e-2);
+    CHECK(fabs(out[38].r) < 1e-2 && fabs(out[500].i) < 1e-2);
+    kiss_fft(cfg, in, in);                                               /* fin == fout (kiss_fft.c:373-379) */
+    CHECK(fabs(in[37].r - n) < 1e-2);
+    size_t need = 0;
+    CHECK(kiss_fft_alloc(n, 1, NULL, &need) == NULL && need > 0);        /* size query protocol, kiss_fft.h:66-78 */
+    kiss_fft_cleanup();
+    free(cfg);                                                           /* "can be simply free()d" kiss_fft.h:100-102 */
+
+    /* samplerate.rs:89-96: resample a 1000-sample sine by 2.0 and look at the length */
+    int err = -1;
+    SRC_STATE *st = src_new(1, 1, &err);
+    CHECK(st != NULL && err == 0);
+    float v[1000], o[2001];
+    for (int k = 0; k < 1000; ++k) v[k] = sinf((float)k / 1000.0f);
+    SRC_DATA d = { v, o, 1000, 2001, 0, 0, 0, 2.0 };
+    CHECK(src_process(st, &d) == 0);
+    CHECK(d.input_frames_used == 1000 && d.output_frames_gen == 2000);
+    /* streaming: a second chunk continues the same stream */
+    d.data_in = v; d.input_frames = 10; d.output_frames = 2001;
+    CHECK(src_process(st, &d) == 0 && d.output_frames_gen == 20);
+    /* a too-small output buffer consumes less input instead of overflowing */
+    d.input_frames = 100; d.output_frames = 50;
+    CHECK(src_process(st, &d) == 0 && d.output_frames_gen <= 50 && d.input_frames_used == 25);
+    d.src_ratio = 1e-9;
+    int rc = src_process(st, &d);
+    CHECK(rc != 0 && src_strerror(rc) != NULL);                          /* samplerate.rs:77-83 would panic with this text */
+    src_delete(st);
+    CHECK(src_new(1, 2, &err) == NULL && err != 0);
+    printf("shims OK\n");
+    return 0;
+}

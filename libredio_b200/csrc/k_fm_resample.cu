@@ -77,6 +77,7 @@ struct lrc_resampler {
     float   *d_hp;                               // [L][tpp] polyphase rows, f32
     float   *d_buf;                              // [n_ch][cap]: tpp-1 history + chunk
     float   *d_carry;                            // [n_ch][tpp]
+    float   *d_hin, *d_hout; size_t hin_cap, hout_cap;   // staging for the host entry point (floats)
     unsigned long long n_total, m_next;          // inputs consumed / next output index (same for all channels)
 };
 
@@ -184,6 +185,7 @@ extern "C" int lrc_resampler_create(lrc_ctx *ctx, double ratio, size_t n_ch, siz
         }
     r->cap = (r->tpp + max_chunk + 3) / 4 * 4;
     r->d_hp = r->d_buf = r->d_carry = nullptr;
+    r->d_hin = r->d_hout = nullptr; r->hin_cap = r->hout_cap = 0;
     r->n_total = 0; r->m_next = 0;
     if (cudaMalloc(&r->d_hp, hp.size() * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&r->d_buf, n_ch * r->cap * sizeof(float)) != cudaSuccess ||
@@ -201,7 +203,7 @@ extern "C" int lrc_resampler_destroy(lrc_resampler *r)
 {
     if (!r) return LRC_OK;
     cudaSetDevice(r->ctx->device);
-    cudaFree(r->d_hp); cudaFree(r->d_buf); cudaFree(r->d_carry);
+    cudaFree(r->d_hp); cudaFree(r->d_buf); cudaFree(r->d_carry); cudaFree(r->d_hin); cudaFree(r->d_hout);
     delete r;
     return LRC_OK;
 }
@@ -273,5 +275,38 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
     r->n_total += n_in;
     r->m_next += no;
     *n_out = no;
+    return LRC_OK;
+}
+
+extern "C" int lrc_resampler_process_host(lrc_resampler *r, const float *h_in, size_t n_in, float *h_out,
+                                          size_t out_cap, size_t *n_out)
+{
+    LRC_REQUIRE(r && n_out, LRC_ERR_INVALID, "lrc_resampler_process_host: null argument");
+    LRC_BIND(r->ctx);
+    *n_out = 0;
+    if (n_in == 0) return LRC_OK;
+    LRC_REQUIRE(h_in != nullptr, LRC_ERR_INVALID, "lrc_resampler_process_host: null input");
+    const size_t no = lrc_resampler_next_out_len(r, n_in);
+    LRC_REQUIRE(no == 0 || (h_out && out_cap >= no), LRC_ERR_CAPACITY, "lrc_resampler_process_host: output too small");
+    if (r->hin_cap < r->n_ch * n_in) {
+        cudaFree(r->d_hin); r->d_hin = nullptr; r->hin_cap = 0;
+        LRC_CUDA(cudaMalloc(&r->d_hin, r->n_ch * n_in * sizeof(float)));
+        r->hin_cap = r->n_ch * n_in;
+    }
+    if (r->hout_cap < r->n_ch * (no + 1)) {
+        cudaFree(r->d_hout); r->d_hout = nullptr; r->hout_cap = 0;
+        LRC_CUDA(cudaMalloc(&r->d_hout, r->n_ch * (no + 1) * sizeof(float)));
+        r->hout_cap = r->n_ch * (no + 1);
+    }
+    cudaStream_t s = r->ctx->stream;
+    LRC_CUDA(cudaMemcpyAsync(r->d_hin, h_in, r->n_ch * n_in * sizeof(float), cudaMemcpyHostToDevice, s));
+    size_t got = 0;
+    int rc = lrc_resampler_process(r, r->d_hin, n_in, n_in, r->d_hout, no + 1, &got, s);
+    if (rc) return rc;
+    if (got)
+        LRC_CUDA(cudaMemcpy2DAsync(h_out, out_cap * sizeof(float), r->d_hout, (no + 1) * sizeof(float), got * sizeof(float),
+                                   r->n_ch, cudaMemcpyDeviceToHost, s));
+    LRC_CUDA(cudaStreamSynchronize(s));
+    *n_out = got;
     return LRC_OK;
 }
