@@ -13,6 +13,7 @@
 // existing graph can be wired unchanged around the GPU blocks of gpu_blocks.hpp.
 #pragma once
 #include <condition_variable>
+#include <cstdio>
 #include <cstddef>
 #include <deque>
 #include <functional>
@@ -122,12 +123,16 @@ std::pair<Sender<T>, Receiver<T>> channel()
     return {Sender<T>(c), Receiver<T>(c)};
 }
 
-// one named task per block (ratpak.rs:60-185).  A block that dies on a closed port just ends its thread.
+// one named task per block (ratpak.rs:60-185).  A Rust panic kills only the panicking thread, whose
+// ports are then dropped: a block that throws -- on a closed port, a failed assert, or a non-zero status of
+// the GPU library -- ends its thread the same way, and the teardown cascades through the dropped ports.
 template <class F>
 std::thread spawn(F &&f)
 {
     return std::thread([fn = std::forward<F>(f)]() mutable {
-        try { fn(); } catch (const PortClosed &) { /* teardown cascades through the dropped ports */ }
+        try { fn(); }
+        catch (const PortClosed &) {}
+        catch (const std::exception &e) { std::fprintf(stderr, "kpn: block thread panicked: %s\n", e.what()); }
     });
 }
 
