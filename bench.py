@@ -193,16 +193,29 @@ def run_ours(args):
             ph = (2 * np.pi * f) * torch.arange(s, e, device=dev, dtype=torch.float64)
             x[s:e] += torch.polar(torch.full((e - s,), a, device=dev, dtype=torch.float32), (ph % (2 * np.pi)).float())
     rows = frames // K_AVG
-    out = torch.empty((rows, NFFT), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) if world > 1 else None
+    # two output slots: the NVLink gather of step i (NCCL's stream) overlaps the kernel of step i+1
+    outs = [torch.empty((rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
+    gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
 
-    def step():
-        chain.run(x, K_AVG, out)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)     # the only exchange: NVLink gather of the output rows
+    def step(i):
+        b = i & 1
+        if pending[b] is not None:
+            pending[b].wait()                              # slot reuse: its previous gather must be done
+            pending[b] = None
+        chain.run(x, K_AVG, outs[b])
+        if world > 1:                                      # the only exchange: all-gather of the output rows
+            pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    drain()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -215,11 +228,17 @@ def run_ours(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev[0].record()
     for i in range(args.steps):
+        b = i & 1
+        if pending[b] is not None:
+            pending[b].wait()
+            pending[b] = None
         kev[i][0].record()
-        chain.run(x, K_AVG, out)
+        chain.run(x, K_AVG, outs[b])
         kev[i][1].record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
+        if i == args.steps - 1:
+            drain()                                        # the last gathers are inside the timed region
         ev[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:

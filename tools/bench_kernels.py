@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Per-kernel roofline table for every BASELINE.json config (device-resident inputs, CUDA events, inputs
+>> L2).  Not the headline bench (that is bench.py); this feeds DESIGN.md / profiles/ and tells which kernel
+to tune next.  Usage: python tools/bench_kernels.py [--quick] > gpurun_out/kernels.jsonl"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libredio_b200 import blocks, synth, capi  # noqa: E402
+
+PEAK = 6551.4
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def report(name, samples, alg_bytes, ms, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    line = {"kernel": name, "Msamples/s": samples / (ms * 1e-3) / 1e6, "ms": ms, "GB/s": gbs, "frac_hbm": gbs / PEAK,
+            "alg_bytes": alg_bytes}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    q = 4 if a.quick else 1
+    ctx = blocks.Context(0)
+    dev = ctx.tdev
+    g = torch.Generator(device=dev).manual_seed(0)
+    taps = synth.lpf_taps(64, 0.04)
+    want = lambda k: (not a.only) or (k in a.only.split(","))
+
+    if want("unpack"):
+        n = (1 << 30) // q
+        iq = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+        out = torch.empty(n // 2, dtype=torch.complex64, device=dev)
+        import ctypes as C
+        def f():
+            capi.check(ctx.lib.lrc_unpack_u8_cf32(ctx.h, C.c_void_p(iq.data_ptr()), n, C.c_void_p(out.data_ptr()), blocks._stream()), "unpack")
+        ms, _ = timeit(f)
+        report("unpack u8->cf32 (K1)", n // 2, n + n * 4, ms)
+        del iq, out
+
+    if want("fir"):
+        # config 1/3 shape: 1024 channels x 2.4 Msps x 0.1 s
+        n_ch, n = 1024 // q, 240_000
+        x = torch.view_as_complex(torch.randn(n_ch, n, 2, device=dev, generator=g))
+        fir = blocks.Fir(ctx, taps, 10)
+        ms, _ = timeit(lambda: fir.run(x))
+        report("FIR64/10 cf32 (K2 tile)", n_ch * n, n_ch * n * 8.8, ms, {"n_ch": n_ch})
+        iq = torch.randint(0, 256, (n_ch, 2 * n), dtype=torch.uint8, device=dev, generator=g)
+        ms, _ = timeit(lambda: fir.run_u8(iq))
+        report("unpack+FIR64/10 u8 fused (K1+K2)", n_ch * n, n_ch * n * 2.8, ms,
+               {"flop_per_sample": 25.6, "TFLOP/s": n_ch * n * 25.6 / (ms * 1e-3) / 1e12})
+        del x, iq
+        fir.close()
+
+    if want("fft"):
+        n = (1 << 26) // q * 4
+        x = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
+        f = blocks.Fft(ctx, 1024, 0)
+        y = torch.empty_like(x)
+        xv = x.view(-1, 1024)
+        import ctypes as C
+        def run():
+            capi.check(ctx.lib.lrc_fft_run(f.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), n // 1024, blocks._stream()), "fft")
+        ms, _ = timeit(run)
+        report("FFT1024 batched out-of-place (K3)", n, n * 16, ms)
+        p = blocks.Psd(ctx, 1024)
+        ms, _ = timeit(lambda: p.run(x, 64))
+        report("Hann+FFT1024+|X|^2 avg K=64 (config 2, K3 fused)", n, n * 8, ms,
+               {"flop_per_sample": 55, "TFLOP/s": n * 55 / (ms * 1e-3) / 1e12})
+        del x, y
+        f.close(); p.close()
+
+    if want("fm"):
+        n_ch, n = 1024 // q, 240_000
+        x = torch.view_as_complex(torch.randn(n_ch, n, 2, device=dev, generator=g))
+        ms, _ = timeit(lambda: blocks.fm_demod(ctx, x))
+        report("FM discriminator (K5)", n_ch * n, n_ch * n * 12, ms)
+        d = torch.randn(n_ch, n, device=dev, generator=g)
+        rs = blocks.Resampler(ctx, 0.2, n_ch, n)
+        ms, _ = timeit(lambda: rs.process(d))
+        report("resample 240k->48k, 321 taps (K6)", n_ch * n, n_ch * n * 4.8, ms,
+               {"flop_per_sample": 2 * 321 / 5, "TFLOP/s": n_ch * n * 2 * 321 / 5 / (ms * 1e-3) / 1e12})
+        del x, d
+        rs.close()
+
+    if want("fastfir"):
+        n = (1 << 28) // q
+        x = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
+        rng = np.random.default_rng(6)
+        h = ((rng.standard_normal(4096) + 1j * rng.standard_normal(4096)) / 64).astype(np.complex64)
+        ff = blocks.FastFir(ctx, h, 0)
+        out = torch.empty(ff.out_len(n) + 1, dtype=torch.complex64, device=dev)
+        ms, _ = timeit(lambda: ff.run(x, out=out), iters=5)
+        report("overlap-save FIR 4096 taps nfft 8192 (config 5, K4)", n, n * 16, ms,
+               {"flop_per_sample": 272, "TFLOP/s": n * 272 / (ms * 1e-3) / 1e12})
+        del x, out
+        ff.close()
+
+    if want("ook"):
+        n_streams, n_blocks = 4096 // q, 500
+        caps = [synth.ook_capture_u8(n_blocks, seed=4 + s, n_packets=2)[0] for s in range(32)]
+        iq = torch.from_numpy(np.stack(caps)).to(dev).repeat(n_streams // 32, 1).contiguous()
+        ook = blocks.Ook(ctx, n_streams, n_blocks, 256000, 4096, 64)
+        ms, _ = timeit(lambda: ook.decode(iq), iters=5)
+        ns = n_streams * n_blocks * 512
+        report("OOK chain 4 kernels (config 4, K7)", ns, ns * 2, ms, {"packets": len(ook.packets())})
+        ook.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
