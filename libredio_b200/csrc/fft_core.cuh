@@ -118,9 +118,55 @@ struct CtaFFT {
     static constexpr int SMEM_CPX = N + (N >> 4);    // padded exchange buffer (float2 units)
     __device__ __forceinline__ static int pad(int i) { return i + (i >> 4); }
 
-    template <int NS, class Sync>
+    // ---- twiddle bookkeeping: stage NS needs NB*(R-1) twiddles per thread, all fixed for a given t ----
+    template <int NS>
+    static constexpr int tw_count()
+    {
+        constexpr int REM = N / NS, R = REM >= E ? E : REM, NB = E / R;
+        return NS > 1 ? NB * (R - 1) : 0;
+    }
+    template <int NS>
+    static constexpr int tw_off()
+    {
+        if constexpr (NS <= 1) return 0;
+        else return tw_off<NS / E>() + tw_count<NS / E>();      // every stage before the last has radix E
+    }
+    template <int NS>
+    static constexpr int tw_total_from()
+    {
+        constexpr int REM = N / NS, R = REM >= E ? E : REM;
+        if constexpr (NS * R == N) return tw_off<NS>() + tw_count<NS>();
+        else return tw_total_from<NS * R>();
+    }
+    static constexpr int TW_REGS = tw_total_from<1>() > 0 ? tw_total_from<1>() : 1;   // 27 for N = 1024
+
+    template <int NS>
+    __device__ __forceinline__ static void load_stage_twiddles(const float2 *__restrict__ tw, int t, float2 *twr)
+    {
+        constexpr int REM = N / NS, R = REM >= E ? E : REM, NB = E / R;
+        if constexpr (NS > 1) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int k = (t + q * T) & (NS - 1);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    float2 w = __ldg(&tw[r * k * (N / (NS * R))]);
+                    if (INV) w.y = -w.y;
+                    twr[tw_off<NS>() + q * (R - 1) + (r - 1)] = w;
+                }
+            }
+        }
+        if constexpr (NS * R != N) load_stage_twiddles<NS * R>(tw, t, twr);
+    }
+    // a persistent thread (fixed t) can fetch its twiddles once and keep them in registers
+    __device__ __forceinline__ static void load_twiddles(const float2 *__restrict__ tw, int t, float2 *twr)
+    {
+        load_stage_twiddles<1>(tw, t, twr);
+    }
+
+    template <int NS, bool TWREG, class Sync>
     __device__ __forceinline__ static void stage(float2 *v, float2 *sm, const float2 *__restrict__ tw,
-                                                 int t, const Sync &sync)
+                                                 const float2 *twr, int t, const Sync &sync)
     {
         constexpr int REM = N / NS;
         constexpr int R = REM >= E ? E : REM;   // radix of this pass
@@ -132,8 +178,13 @@ struct CtaFFT {
                 const int k = (t + q * T) & (NS - 1);
 #pragma unroll
                 for (int r = 1; r < R; ++r) {
-                    float2 w = __ldg(&tw[r * k * (N / (NS * R))]);
-                    if (INV) w.y = -w.y;
+                    float2 w;
+                    if constexpr (TWREG) {
+                        w = twr[tw_off<NS>() + q * (R - 1) + (r - 1)];
+                    } else {
+                        w = __ldg(&tw[r * k * (N / (NS * R))]);
+                        if (INV) w.y = -w.y;
+                    }
                     v[q + r * NB] = cmulf(v[q + r * NB], w);
                 }
             }
@@ -156,7 +207,7 @@ struct CtaFFT {
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = sm[pad(t + e * T)];
             sync();
-            stage<NS * R, Sync>(v, sm, tw, t, sync);
+            stage<NS * R, TWREG, Sync>(v, sm, tw, twr, t, sync);
         }
     }
 
@@ -165,7 +216,13 @@ struct CtaFFT {
     __device__ __forceinline__ static void run(float2 *v, float2 *sm, const float2 *__restrict__ tw, int t,
                                                const Sync &sync)
     {
-        stage<1, Sync>(v, sm, tw, t, sync);
+        stage<1, false, Sync>(v, sm, tw, nullptr, t, sync);
+    }
+    // same with the thread's twiddles already in registers (load_twiddles)
+    template <class Sync>
+    __device__ __forceinline__ static void run_twreg(float2 *v, float2 *sm, const float2 *twr, int t, const Sync &sync)
+    {
+        stage<1, true, Sync>(v, sm, nullptr, twr, t, sync);
     }
 };
 

@@ -196,6 +196,8 @@ psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const f
     float w[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) w[e] = win[t + e * T];
+    float2 twr[F::TW_REGS];                       // this thread's twiddles never change: fetch them once
+    F::load_twiddles(tw, t, twr);
 
     for (size_t item = (size_t)blockIdx.x * G + g; item < n_items; item += (size_t)gridDim.x * G) {
         const size_t row = item / ipr, c = item % ipr;
@@ -214,11 +216,11 @@ psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const f
                 v[e] = make_float2(x.x * w[e], x.y * w[e]);
             }
             if constexpr (T >= 32) {
-                F::run(v, sm, tw, t, SyncNamed{1 + g, T});
+                F::run_twreg(v, sm, twr, t, SyncNamed{1 + g, T});
             } else {
                 const unsigned lane = threadIdx.x & 31;
                 const unsigned mask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (lane / T * T));
-                F::run(v, sm, tw, t, SyncWarp{mask});
+                F::run_twreg(v, sm, twr, t, SyncWarp{mask});
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));

@@ -14,20 +14,28 @@
 // ---------------------------------------------------------------------------------------------
 // FM discriminator
 // ---------------------------------------------------------------------------------------------
+// blockIdx.y = channel; each thread turns two consecutive samples (one 128-bit load) into two phases
 __global__ void __launch_bounds__(256)
-fmdemod_kernel(const float2 *__restrict__ in, size_t n_ch, size_t n, size_t in_stride,
-               const float2 *__restrict__ state, float *__restrict__ out, size_t out_stride)
+fmdemod_kernel(const float2 *__restrict__ in, size_t n, size_t in_stride, const float2 *__restrict__ state,
+               float *__restrict__ out, size_t out_stride, int vec_ok)
 {
-    const size_t total = n_ch * n;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t c = i / n, k = i % n;
-        const float2 *x = in + c * in_stride;
-        const float2 cur = x[k];
-        float2 prev;
-        if (k > 0) prev = x[k - 1];
-        else prev = state ? state[c] : make_float2(0.f, 0.f);
-        const float2 z = cmul_conjb(cur, prev);
-        out[c * out_stride + k] = atan2f(z.y, z.x);
+    const size_t c = blockIdx.y;
+    const float2 *x = in + c * in_stride;
+    float *y = out + c * out_stride;
+    const float2 first_prev = state ? state[c] : make_float2(0.f, 0.f);
+    const size_t n_pairs = vec_ok ? n / 2 : 0;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ldg_stream_f4(reinterpret_cast<const float4 *>(x) + p);
+        const float2 prev = p ? x[2 * p - 1] : first_prev;      // neighbour's sample: same cache line, L1/L2 hit
+        const float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
+        const float2 z0 = cmul_conjb(a, prev), z1 = cmul_conjb(b, a);
+        *reinterpret_cast<float2 *>(y + 2 * p) = make_float2(atan2f(z0.y, z0.x), atan2f(z1.y, z1.x));
+    }
+    // odd tail, or the whole row when it is not 16-byte aligned
+    for (size_t k = 2 * n_pairs + (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const float2 prev = k ? x[k - 1] : first_prev;
+        const float2 z = cmul_conjb(x[k], prev);
+        y[k] = atan2f(z.y, z.x);
     }
 }
 
@@ -47,11 +55,15 @@ extern "C" int lrc_fmdemod_run(lrc_ctx *ctx, const float *d_in, size_t n_ch, siz
     LRC_REQUIRE(in_stride >= n && out_stride >= n, LRC_ERR_INVALID, "lrc_fmdemod_run: stride shorter than length");
     LRC_REQUIRE(((uintptr_t)d_in & 7) == 0, LRC_ERR_INVALID, "lrc_fmdemod_run: input must be 8-byte aligned");
     cudaStream_t s = lrc_stream(ctx, stream);
-    size_t blocks = ceil_div(n_ch * n, 256);
-    const size_t cap = (size_t)ctx->n_sm * 16;
-    if (blocks > cap) blocks = cap;
-    fmdemod_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2 *)d_in, n_ch, n, in_stride, (const float2 *)d_state,
-                                                   d_out, out_stride);
+    LRC_REQUIRE(n_ch <= 65535, LRC_ERR_UNSUPPORTED, "lrc_fmdemod_run: more than 65535 channels per call");
+    size_t bx = ceil_div(ceil_div(n, 2), 256);
+    const size_t cap = ceil_div((size_t)ctx->n_sm * 16, n_ch);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    // 128-bit loads / 64-bit stores need every row start aligned
+    const int vec_ok = (((uintptr_t)d_in & 15) == 0) && (in_stride % 2 == 0) && (((uintptr_t)d_out & 7) == 0) && (out_stride % 2 == 0);
+    fmdemod_kernel<<<dim3((unsigned)bx, (unsigned)n_ch), 256, 0, s>>>((const float2 *)d_in, n, in_stride,
+                                                                    (const float2 *)d_state, d_out, out_stride, vec_ok);
     LRC_CUDA(cudaGetLastError());
     if (d_state) {
         fmdemod_state_kernel<<<(unsigned)ceil_div(n_ch, 256), 256, 0, s>>>((const float2 *)d_in, n_ch, n, in_stride,
@@ -145,6 +157,93 @@ resample_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, const fl
         for (int u = 0; u < UNROLL; ++u) s += acc[u];
         out[c * out_stride + k] = s;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// L == 1 (pure decimation by M, e.g. 240 kHz -> 48 kHz): y[m] = sum_i g[i] x[m M + i], g = reversed h.
+// Same register-blocked shared-memory scheme as the FIR tile (fir_core.cuh) on real samples: a thread owns
+// R consecutive outputs, streams its window once through LDS.128 (4 samples each) and feeds every sample to
+// the accumulators it belongs to; taps are kernel parameters (constant bank).  R*M*4 bytes is an odd
+// multiple of 16 bytes, so the eight threads of an LDS.128 phase hit eight distinct bank groups.
+// ---------------------------------------------------------------------------------------------
+template <int NT_>
+struct RsTaps { float g[NT_]; };
+
+template <int M, int R, int NT>
+struct RsDecCfg {
+    static constexpr int TPP = 2 * RS_ZERO_CROSSINGS * M + 1;             // taps (L = 1)
+    static constexpr int WIN = (R - 1) * M + TPP;
+    static constexpr int WIN4 = (WIN + 3) / 4 * 4;                         // whole LDS.128s
+    static constexpr int STEP = R * M;                                     // samples between thread windows
+    static constexpr int TILE_OUT = R * NT;
+    static constexpr int TILE_IN = (NT - 1) * STEP + WIN4;                 // floats a tile reads
+    static constexpr int SMEM_BYTES = TILE_IN * 4;
+    static_assert((STEP * 4) % 16 == 0, "thread windows must start 16-byte aligned");
+};
+
+template <int M, int R, int NT>
+__global__ void __launch_bounds__(NT)
+resample_dec_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, size_t valid, size_t s0, size_t n_out,
+                    float *__restrict__ out, size_t out_stride, const __grid_constant__ RsTaps<2 * RS_ZERO_CROSSINGS * M + 1> taps)
+{
+    using Cfg = RsDecCfg<M, R, NT>;
+    extern __shared__ __align__(16) float rs_tile[];
+    const int t = threadIdx.x;
+    const size_t tiles_per_ch = (n_out + Cfg::TILE_OUT - 1) / Cfg::TILE_OUT;
+    const size_t n_tiles = tiles_per_ch * n_ch;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t c = tile / tiles_per_ch, o0 = (tile % tiles_per_ch) * Cfg::TILE_OUT;
+        const size_t first = s0 + o0 * M;                                   // window of output o0 starts here
+        const float *src = buf + c * cap + first;
+        const size_t avail = valid - first;                                 // floats of this row that exist
+        for (int i = t; i < Cfg::TILE_IN; i += NT) rs_tile[i] = (size_t)i < avail ? src[i] : 0.f;
+        __syncthreads();
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        const float *sx = rs_tile + t * Cfg::STEP;
+#pragma unroll
+        for (int j = 0; j < Cfg::WIN4; j += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(sx + j);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int k = j + u - r * M;
+                    if (k >= 0 && k < Cfg::TPP) acc[r] = fmaf(xs[u], taps.g[k], acc[r]);
+                }
+        }
+        float *dst = out + c * out_stride + o0 + (size_t)t * R;
+        const size_t left = n_out - o0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if ((size_t)(t * R + r) < left) dst[r] = acc[r];
+        __syncthreads();
+    }
+}
+
+template <int M, int R>
+static int launch_resample_dec(lrc_resampler *r, size_t n_in, size_t no, float *d_out, size_t out_stride, cudaStream_t s)
+{
+    constexpr int NT = 128;
+    using Cfg = RsDecCfg<M, R, NT>;
+    auto kern = resample_dec_kernel<M, R, NT>;
+    LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 1;
+    LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, Cfg::SMEM_BYTES));
+    if (occ < 1) occ = 1;
+    const size_t n_tiles = ceil_div(no, (size_t)Cfg::TILE_OUT) * r->n_ch;
+    size_t blocks = (size_t)r->ctx->n_sm * occ;
+    if (blocks > n_tiles) blocks = n_tiles;
+    RsTaps<Cfg::TPP> taps;
+    for (int i = 0; i < Cfg::TPP; ++i) taps.g[i] = (float)r->h[Cfg::TPP - 1 - i];      // reversed: correlation form
+    // buffer index of x[m_next*M - (TPP-1)]: the row starts at global input index n_total - (TPP-1)
+    const size_t s0 = (size_t)(r->m_next * (unsigned long long)M - r->n_total);
+    const size_t valid = (r->tpp - 1) + n_in;
+    kern<<<(unsigned)blocks, NT, Cfg::SMEM_BYTES, s>>>(r->d_buf, r->cap, r->n_ch, valid, s0, no, d_out, out_stride, taps);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
 }
 
 extern "C" int lrc_resampler_create(lrc_ctx *ctx, double ratio, size_t n_ch, size_t max_chunk, lrc_resampler **out)
@@ -257,12 +356,26 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
     if (no) {
         LRC_REQUIRE(d_out && out_stride >= no, LRC_ERR_CAPACITY, "lrc_resampler_process: output too small "
                     "(the reference sizes it ratio*len + 1, samplerate.rs:64)");
-        size_t blocks = ceil_div(r->n_ch * no, 256);
-        const size_t cap = (size_t)r->ctx->n_sm * 16;
-        if (blocks > cap) blocks = cap;
-        resample_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(r->d_buf, r->cap, r->n_ch, r->d_hp, r->L, r->M, (int)r->tpp,
-                                                           r->n_total, r->m_next, no, d_out, out_stride);
-        LRC_CUDA(cudaGetLastError());
+        int rc = -1;
+        if (r->L == 1) {                       // decimators with a register-blocked tile instance
+            switch (r->M) {
+                case 2: rc = launch_resample_dec<2, 6>(r, n_in, no, d_out, out_stride, s); break;
+                case 3: rc = launch_resample_dec<3, 4>(r, n_in, no, d_out, out_stride, s); break;
+                case 4: rc = launch_resample_dec<4, 5>(r, n_in, no, d_out, out_stride, s); break;
+                case 5: rc = launch_resample_dec<5, 4>(r, n_in, no, d_out, out_stride, s); break;
+                case 6: rc = launch_resample_dec<6, 6>(r, n_in, no, d_out, out_stride, s); break;
+                default: break;
+            }
+        }
+        if (rc > 0) return rc;
+        if (rc < 0) {                          // general L/M: one thread per output
+            size_t blocks = ceil_div(r->n_ch * no, 256);
+            const size_t cap = (size_t)r->ctx->n_sm * 16;
+            if (blocks > cap) blocks = cap;
+            resample_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(r->d_buf, r->cap, r->n_ch, r->d_hp, r->L, r->M, (int)r->tpp,
+                                                               r->n_total, r->m_next, no, d_out, out_stride);
+            LRC_CUDA(cudaGetLastError());
+        }
     }
     // new history = the last tpp-1 floats of [history | chunk]
     if (hist) {

@@ -37,6 +37,36 @@ __device__ __forceinline__ float lr_envelope(uint32_t b0, uint32_t b1)
     return __double2float_rn(__dsqrt_rn(s));
 }
 
+// The envelope depends on the two bytes only and is symmetric in them (the f64 add commutes), so the hot
+// kernels read it from a triangular table of 256*257/2 = 32896 floats (131.6 KB) held in shared memory.
+// The table is filled ON THE DEVICE by lr_envelope above when the plan is created; the u8 domain being
+// finite, table == formula for all 65536 pairs is a proof of equivalence, checked exhaustively by
+// tests/test_gpu_ook_fastfir.py::test_envelope_exhaustive_65536_pairs_bit_exact (formula vs CPU) and by the
+// bit-exact block sums of every OOK test (table vs CPU).
+constexpr int OOK_LUT_N = 256 * 257 / 2;
+constexpr int OOK_LUT_BYTES = OOK_LUT_N * 4;
+
+__device__ __forceinline__ float lut_envelope(const float *lut, uint32_t b0, uint32_t b1)
+{
+    const uint32_t hi = max(b0, b1), lo = min(b0, b1);
+    return lut[((hi * (hi + 1u)) >> 1) + lo];
+}
+
+__device__ __forceinline__ void lut_load(float *s_lut, const float *__restrict__ g_lut)
+{
+    for (int i = threadIdx.x; i < OOK_LUT_N / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(s_lut)[i] = __ldg(reinterpret_cast<const float4 *>(g_lut) + i);
+    __syncthreads();
+}
+
+__global__ void ook_build_lut_kernel(float *__restrict__ lut)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536u) return;
+    const uint32_t hi = i >> 8, lo = i & 0xffu;
+    if (lo <= hi) lut[((hi * (hi + 1u)) >> 1) + lo] = lr_envelope(hi, lo);
+}
+
 struct lrc_ook {
     lrc_ctx *ctx;
     size_t   n_streams, n_blocks, max_runs, max_packets, max_bursts;
@@ -52,6 +82,7 @@ struct lrc_ook {
     unsigned long long *d_packets;    // [n_streams][2][max_packets] packets packed MSB-first
     uint32_t *d_npackets;             // [n_streams][2]
     uint32_t *d_runs_dbg;             // [n_streams][max_runs] (value << 31 | length), filled by K-D
+    float    *d_lut;                  // triangular envelope table, OOK_LUT_N floats
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -59,19 +90,23 @@ struct lrc_ook {
 // stream: 32-sample slabs are loaded coalesced (4 lanes x 16 B per block row), turned into envelopes
 // by the loading lane, parked in a padded shared tile, and lane b then adds row b in sample order.
 // ---------------------------------------------------------------------------------------------
-constexpr int KA_WARPS = 8;
+constexpr int KA_WARPS = 16;
 constexpr int KA_SLAB = 32;                  // samples per block row per slab
 constexpr int KA_LPR = KA_SLAB * 2 / 16;     // lanes (16-byte loads) per block row
 constexpr int KA_RPI = 32 / KA_LPR;          // block rows per load iteration
 constexpr int KA_LD = KA_SLAB + 1;           // padded row length (floats)
 
-__global__ void __launch_bounds__(KA_WARPS * 32)
+constexpr int KA_SMEM_BYTES = OOK_LUT_BYTES + KA_WARPS * 32 * KA_LD * 4;
+
+__global__ void __launch_bounds__(KA_WARPS * 32, 1)
 ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
-                 float *__restrict__ d_sum, float *__restrict__ d_max)
+                 const float *__restrict__ g_lut, float *__restrict__ d_sum, float *__restrict__ d_max)
 {
-    __shared__ float tile[KA_WARPS][32 * KA_LD];
+    extern __shared__ __align__(16) float ka_smem[];
+    float *lut = ka_smem;
+    lut_load(lut, g_lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *env = tile[warp];
+    float *env = ka_smem + OOK_LUT_N + warp * (32 * KA_LD);
     const size_t groups_per_stream = (n_blocks + 31) / 32;
     const size_t n_groups = groups_per_stream * n_streams;
     const size_t warps_total = (size_t)gridDim.x * KA_WARPS;
@@ -80,28 +115,41 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
         const int nb = (int)((n_blocks - b0) < 32 ? (n_blocks - b0) : 32);
         const uint8_t *base = iq + st * stream_stride + b0 * (size_t)(OOK_BLOCK * 2);
         float s = 0.0f, mx = 0.0f;
+        // slab loads are software-pipelined: slab i+1 is in flight while slab i is converted and summed
+        constexpr int NIT = 32 / KA_RPI;
+        uint4 nxt[NIT];
+        auto load_slab = [&](int slab) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int row = it * KA_RPI + lane / KA_LPR, col = lane % KA_LPR;
+                nxt[it] = row < nb ? ldg_stream_u4(reinterpret_cast<const uint4 *>(
+                                         base + (size_t)row * (OOK_BLOCK * 2) + slab * (KA_SLAB * 2) + col * 16))
+                                   : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        load_slab(0);
         for (int slab = 0; slab < OOK_BLOCK / KA_SLAB; ++slab) {
+            uint4 cur[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) cur[it] = nxt[it];
+            if (slab + 1 < OOK_BLOCK / KA_SLAB) load_slab(slab + 1);
             // 32 rows x 64 B: 4 iterations of (8 rows x 4 lanes x 16 B); the padded tile makes both the
             // envelope stores here and the row-wise reads below bank-conflict free
 #pragma unroll
-            for (int it = 0; it < 32 / KA_RPI; ++it) {
+            for (int it = 0; it < NIT; ++it) {
                 const int row = it * KA_RPI + lane / KA_LPR, col = lane % KA_LPR;
-                if (row < nb) {
-                    const uint4 q = ldg_stream_u4(reinterpret_cast<const uint4 *>(
-                        base + (size_t)row * (OOK_BLOCK * 2) + slab * (KA_SLAB * 2) + col * 16));
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    float *dst = env + row * KA_LD + col * 8;
+                const uint32_t w[4] = {cur[it].x, cur[it].y, cur[it].z, cur[it].w};
+                float *dst = env + row * KA_LD + col * 8;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        dst[2 * k]     = lr_envelope(w[k] & 0xffu, (w[k] >> 8) & 0xffu);
-                        dst[2 * k + 1] = lr_envelope((w[k] >> 16) & 0xffu, w[k] >> 24);
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    dst[2 * k]     = lut_envelope(lut, w[k] & 0xffu, (w[k] >> 8) & 0xffu);
+                    dst[2 * k + 1] = lut_envelope(lut, (w[k] >> 16) & 0xffu, w[k] >> 24);
                 }
             }
             __syncwarp();
             if (lane < nb) {
                 const float *r = env + lane * KA_LD;
-#pragma unroll 16
+#pragma unroll
                 for (int j = 0; j < KA_SLAB; ++j) {
                     const float e = r[j];
                     s = __fadd_rn(s, e);                 // samples.iter().sum(): left to right from 0.0
@@ -139,37 +187,60 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     uint32_t burst = 0;                       // index of the burst being collected
     size_t burst_first_block = 0;
     bool burst_has_blocks = false;
-    for (size_t b = 0; b < n_blocks; ++b) {
-        trigger -= 1;                                                       // :46
-        const float s = sum[b];                                             // :48
-        if (buf_len > 1000ull * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
-            if (burst_has_blocks)
-                for (size_t k = burst_first_block; k < b; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
-            buf_len = 1; lead0 = true; cur_max = 0.0f; burst_has_blocks = false;
-        }
-        if (threshold == 0.0f) threshold = s;                               // :57-59
-        if (trigger < 0) {                                                  // :62-65
-            threshold = __fadd_rn(threshold, __fdiv_rn(s, 1000.0f));
-            threshold = __fsub_rn(threshold, __fmul_rn(threshold, 0.002f));
-        }
-        if (s > __fmul_rn(threshold, 4.0f)) trigger = OOK_TRIGGER_DURATION; // :68-70
-        int32_t tg = -1;
-        if (trigger > 1) {                                                  // :73-75 push_all
-            if (burst < max_bursts) {
-                tg = (int32_t)burst;
-                if (!burst_has_blocks) { burst_first_block = b; burst_has_blocks = true; }
+    // blocks are walked four at a time; the next four sums/maxima are already in flight (the state machine
+    // itself is sequential, the loads are not)
+    const bool vec = (n_blocks % 4 == 0);
+    auto load4 = [&](size_t b, float *s4, float *m4) {
+        if (vec && b + 4 <= n_blocks) {
+            const float4 a = *reinterpret_cast<const float4 *>(sum + b), c = *reinterpret_cast<const float4 *>(bmax + b);
+            s4[0] = a.x; s4[1] = a.y; s4[2] = a.z; s4[3] = a.w;
+            m4[0] = c.x; m4[1] = c.y; m4[2] = c.z; m4[3] = c.w;
+        } else {
+            for (int u = 0; u < 4; ++u) {
+                s4[u] = (b + u < n_blocks) ? sum[b + u] : 0.0f;
+                m4[u] = (b + u < n_blocks) ? bmax[b + u] : 0.0f;
             }
-            buf_len += OOK_BLOCK;
-            cur_max = fmaxf(cur_max, bmax[b]);
         }
-        tag[b] = tg;
-        if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
-            if (burst < max_bursts) {
-                half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
-                flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+    };
+    float ns[4], nm[4];
+    load4(0, ns, nm);
+    for (size_t b4 = 0; b4 < n_blocks; b4 += 4) {
+        float cs[4], cm[4];
+        for (int u = 0; u < 4; ++u) { cs[u] = ns[u]; cm[u] = nm[u]; }
+        if (b4 + 4 < n_blocks) load4(b4 + 4, ns, nm);
+        for (int u = 0; u < 4 && b4 + u < n_blocks; ++u) {
+            const size_t b = b4 + u;
+            trigger -= 1;                                                       // :46
+            const float s = cs[u];                                             // :48
+            if (buf_len > 1000ull * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
+                if (burst_has_blocks)
+                    for (size_t k = burst_first_block; k < b; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
+                buf_len = 1; lead0 = true; cur_max = 0.0f; burst_has_blocks = false;
             }
-            burst += 1;
-            buf_len = 0; lead0 = false; cur_max = 0.0f; burst_has_blocks = false;
+            if (threshold == 0.0f) threshold = s;                               // :57-59
+            if (trigger < 0) {                                                  // :62-65
+                threshold = __fadd_rn(threshold, __fdiv_rn(s, 1000.0f));
+                threshold = __fsub_rn(threshold, __fmul_rn(threshold, 0.002f));
+            }
+            if (s > __fmul_rn(threshold, 4.0f)) trigger = OOK_TRIGGER_DURATION; // :68-70
+            int32_t tg = -1;
+            if (trigger > 1) {                                                  // :73-75 push_all
+                if (burst < max_bursts) {
+                    tg = (int32_t)burst;
+                    if (!burst_has_blocks) { burst_first_block = b; burst_has_blocks = true; }
+                }
+                buf_len += OOK_BLOCK;
+                cur_max = fmaxf(cur_max, cm[u]);
+            }
+            tag[b] = tg;
+            if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
+                if (burst < max_bursts) {
+                    half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
+                    flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                }
+                burst += 1;
+                buf_len = 0; lead0 = false; cur_max = 0.0f; burst_has_blocks = false;
+            }
         }
     }
     // a burst still open when the capture ends is never sent: un-tag its blocks
@@ -183,12 +254,16 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
 // collected block (32 contiguous bytes).  The positions (in the flattened bit stream) where the value
 // changes are appended to the stream's transition list in order.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 1)
 ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
-               size_t max_bursts, size_t max_runs, const int32_t *__restrict__ d_tag,
+               size_t max_bursts, size_t max_runs, const float *__restrict__ g_lut,
+               const int32_t *__restrict__ d_tag,
                const float *__restrict__ d_half, const uint8_t *__restrict__ d_bflags,
                uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans, uint32_t *__restrict__ d_nbits)
 {
+    extern __shared__ __align__(16) float kc_lut[];
+    lut_load(kc_lut, g_lut);
+    const float *lut = kc_lut;
     const int lane = threadIdx.x & 31;
     const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (st >= n_streams) return;
@@ -207,11 +282,21 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         const size_t bi = b0 + lane;
         const int32_t tg_l = bi < n_blocks ? tag[bi] : -1;
         unsigned live = __ballot_sync(0xffffffffu, tg_l >= 0);
+        uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+        if (live) {                                     // first live block of this group
+            const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + __ffs(live) - 1) * (size_t)(OOK_BLOCK * 2) + lane * 32);
+            n0 = ldg_stream_u4(p); n1 = ldg_stream_u4(p + 1);
+        }
         while (live) {
             const int k = __ffs(live) - 1;
             live &= live - 1;
             const int32_t tg = __shfl_sync(0xffffffffu, tg_l, k);
             const size_t b = b0 + k;
+            const uint4 q0 = n0, q1 = n1;
+            if (live) {                                 // the next live block is already on its way
+                const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + __ffs(live) - 1) * (size_t)(OOK_BLOCK * 2) + lane * 32);
+                n0 = ldg_stream_u4(p); n1 = ldg_stream_u4(p + 1);
+            }
             if (tg != cur_burst) {
                 cur_burst = tg;
                 h = half[tg];
@@ -221,14 +306,13 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
                     prev = 0u; pos += 1;
                 }
             }
-            const uint4 *p = reinterpret_cast<const uint4 *>(base + b * (size_t)(OOK_BLOCK * 2) + lane * 32);
-            const uint4 q0 = ldg_stream_u4(p), q1 = ldg_stream_u4(p + 1);
+            (void)b;
             const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float e0 = lr_envelope(w[i] & 0xffu, (w[i] >> 8) & 0xffu);
-                const float e1 = lr_envelope((w[i] >> 16) & 0xffu, w[i] >> 24);
+                const float e0 = lut_envelope(lut, w[i] & 0xffu, (w[i] >> 8) & 0xffu);
+                const float e1 = lut_envelope(lut, (w[i] >> 16) & 0xffu, w[i] >> 24);
                 m |= (e0 > h ? 1u : 0u) << (2 * i);                          // (x > max/2f32) as usize  :91
                 m |= (e1 > h ? 1u : 0u) << (2 * i + 1);
             }
@@ -353,7 +437,15 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     OOK_ALLOC(d_trans, n_streams * o->max_runs); OOK_ALLOC(d_ntrans, n_streams); OOK_ALLOC(d_nbits, n_streams);
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
     OOK_ALLOC(d_runs_dbg, n_streams * o->max_runs);
+    OOK_ALLOC(d_lut, (size_t)OOK_LUT_N);
 #undef OOK_ALLOC
+    if (e == cudaSuccess) {
+        ook_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(o->d_lut);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_LUT_BYTES);
+    }
     if (e != cudaSuccess) {
         lrc_set_error("lrc_ook_create: %s", cudaGetErrorString(e));
         lrc_ook_destroy(o);
@@ -369,7 +461,7 @@ extern "C" int lrc_ook_destroy(lrc_ook *o)
     cudaSetDevice(o->ctx->device);
     cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags);
     cudaFree(o->d_nbursts); cudaFree(o->d_trans); cudaFree(o->d_ntrans); cudaFree(o->d_nbits);
-    cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg);
+    cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut);
     delete o;
     return LRC_OK;
 }
@@ -385,16 +477,16 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     cudaStream_t s = lrc_stream(o->ctx, stream);
     const size_t groups = ((o->n_blocks + 31) / 32) * o->n_streams;
     size_t blocks = ceil_div(groups, (size_t)KA_WARPS);
-    const size_t cap = (size_t)o->ctx->n_sm * 8;
+    const size_t cap = (size_t)o->ctx->n_sm;           // one persistent CTA per SM (the table fills its shared memory)
     if (blocks > cap) blocks = cap;
-    ook_block_kernel<<<(unsigned)blocks, KA_WARPS * 32, 0, s>>>(d_iq, stream_stride_bytes, o->n_streams, o->n_blocks,
-                                                               o->d_sum, o->d_max);
+    ook_block_kernel<<<(unsigned)blocks, KA_WARPS * 32, KA_SMEM_BYTES, s>>>(d_iq, stream_stride_bytes, o->n_streams,
+                                                                           o->n_blocks, o->d_lut, o->d_sum, o->d_max);
     LRC_CUDA(cudaGetLastError());
     ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, 128), 128, 0, s>>>(
         o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
     LRC_CUDA(cudaGetLastError());
-    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams * 32, 256), 256, 0, s>>>(
-        d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_tag, o->d_half,
+    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams * 32, 512), 512, OOK_LUT_BYTES, s>>>(
+        d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_lut, o->d_tag, o->d_half,
         o->d_bflags, o->d_trans, o->d_ntrans, o->d_nbits);
     LRC_CUDA(cudaGetLastError());
     ook_match_kernel<<<(unsigned)ceil_div(o->n_streams, 128), 128, 0, s>>>(

@@ -1,31 +1,38 @@
 // k_unpack.cu -- u8 IQ -> interleaved complex f32, bit-exact with rtlsdr::i2f
 // (src/rtlsdr/src/rtlsdr.rs:159-162):  i2f(b) = fl(fl(b)/127) - 1.
 //
-// HBM-bound: 2 B in, 8 B out per sample.  Each thread converts 16 input bytes (one 128-bit load)
-// into 8 complex samples (four 128-bit stores).
+// HBM-bound: 2 B in, 8 B out per sample; 6 full-rate instructions per value (unpack.cuh).
 #include "common.cuh"
 #include "unpack.cuh"
+
+// One 32-bit word (two samples) per lane per step: the warp reads 128 contiguous bytes and writes 512
+// contiguous bytes with one STG.128 per lane, so both directions are perfectly coalesced; UNROLL steps are
+// issued back to back to keep enough loads in flight.
+constexpr int UNPACK_UNROLL = 8;
 
 __global__ void __launch_bounds__(256)
 unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t n_bytes)
 {
-    const size_t n_vec = n_bytes / 16;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        const uint4 q = ldg_stream_u4(reinterpret_cast<const uint4 *>(in) + i);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        float4 *dst = reinterpret_cast<float4 *>(out) + i * 4;
+    const size_t n_words = n_bytes / 4;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(in);
+    float4 *dst = reinterpret_cast<float4 *>(out);
+    const size_t chunk = (size_t)blockDim.x * UNPACK_UNROLL;
+    for (size_t base = (size_t)blockIdx.x * chunk; base < n_words; base += (size_t)gridDim.x * chunk) {
+        uint32_t w[UNPACK_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float4 o;
-            o.x = lr_i2f(w[k] & 0xffu);
-            o.y = lr_i2f((w[k] >> 8) & 0xffu);
-            o.z = lr_i2f((w[k] >> 16) & 0xffu);
-            o.w = lr_i2f(w[k] >> 24);
-            stg_stream_f4(dst + k, o);
+        for (int u = 0; u < UNPACK_UNROLL; ++u) {
+            const size_t i = base + (size_t)u * blockDim.x + threadIdx.x;
+            w[u] = i < n_words ? __ldcs(src + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNPACK_UNROLL; ++u) {
+            const size_t i = base + (size_t)u * blockDim.x + threadIdx.x;
+            if (i < n_words)
+                stg_stream_f4(dst + i, make_float4(lr_i2f_byte(w[u], 0), lr_i2f_byte(w[u], 1),
+                                                   lr_i2f_byte(w[u], 2), lr_i2f_byte(w[u], 3)));
         }
     }
-    // tail (< 16 bytes) and unaligned heads are handled by the scalar kernel below
+    // tail (< 4 bytes) and unaligned buffers are handled by the scalar kernel below
 }
 
 __global__ void unpack_scalar_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t first,
@@ -47,11 +54,11 @@ extern "C" int lrc_unpack_u8_cf32(lrc_ctx *ctx, const uint8_t *d_iq, size_t n_by
     LRC_REQUIRE(d_iq && d_out, LRC_ERR_INVALID, "lrc_unpack_u8_cf32: null buffer");
     cudaStream_t s = lrc_stream(ctx, stream);
     size_t vec_bytes = 0;
-    if (((uintptr_t)d_iq & 15) == 0 && ((uintptr_t)d_out & 15) == 0) {
-        vec_bytes = n_bytes / 16 * 16;
+    if (((uintptr_t)d_iq & 3) == 0 && ((uintptr_t)d_out & 15) == 0) {
+        vec_bytes = n_bytes / 4 * 4;
         if (vec_bytes) {
-            size_t blocks = ceil_div(vec_bytes / 16, 256);
-            const size_t cap = (size_t)ctx->n_sm * 8;
+            size_t blocks = ceil_div(vec_bytes / 4, (size_t)256 * UNPACK_UNROLL);
+            const size_t cap = (size_t)ctx->n_sm * 16;
             if (blocks > cap) blocks = cap;
             unpack_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_iq, d_out, vec_bytes);
             LRC_CUDA(cudaGetLastError());
