@@ -72,11 +72,92 @@ fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, size_t
     }
 }
 
+// batched FFT with TMA-staged input (N = 512..2048, 16-byte aligned input): each transform group keeps
+// FFT_STAGES-1 frame loads in flight in its own shared-memory ring; results go straight from registers to
+// global memory in the coalesced "thread t holds X[t + e*T]" layout.
+constexpr int FFT_STAGES = 3;
+
+template <int LOG2N, bool INV>
+struct FftTmaCfg {
+    using F = CtaFFT<LOG2N, INV>;
+    static constexpr int THREADS = F::T > 128 ? F::T : 128;
+    static constexpr int G = THREADS / F::T;
+    static constexpr int FRAME_BYTES = F::N * 8;
+    static constexpr int GROUP_BYTES = ((FFT_STAGES * FRAME_BYTES + F::SMEM_CPX * 8 + FFT_STAGES * 8) + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+};
+
+template <int LOG2N, bool INV>
+__global__ void __launch_bounds__(FftTmaCfg<LOG2N, INV>::THREADS)
+fft_tma_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, size_t batch, const float2 *__restrict__ tw)
+{
+    using Cfg = FftTmaCfg<LOG2N, INV>;
+    using F = CtaFFT<LOG2N, INV>;
+    constexpr int N = F::N, E = F::E, T = F::T, G = Cfg::G;
+    extern __shared__ __align__(128) uint8_t fft_smem[];
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    uint8_t *gbase = fft_smem + (size_t)g * Cfg::GROUP_BYTES;
+    float2 *stg = reinterpret_cast<float2 *>(gbase);
+    float2 *sm = reinterpret_cast<float2 *>(gbase + FFT_STAGES * Cfg::FRAME_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + FFT_STAGES * Cfg::FRAME_BYTES + F::SMEM_CPX * 8);
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < FFT_STAGES; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    float2 twr[F::TW_REGS];
+    F::load_twiddles(tw, t, twr);
+    const size_t stride = (size_t)gridDim.x * G;
+    size_t f = (size_t)blockIdx.x * G + g;                 // current frame of this group
+    size_t fa = f;                                         // next frame to request
+    int requested = 0;
+    auto request = [&]() {
+        const int stage = requested % FFT_STAGES;
+        mbar_expect_tx(&bars[stage], Cfg::FRAME_BYTES);
+        tma_load_1d_evict_first(stg + (size_t)stage * N, in + fa * N, Cfg::FRAME_BYTES, &bars[stage]);
+        ++requested;
+        fa += stride;
+    };
+    if (t == 0)
+        for (int i = 0; i < FFT_STAGES - 1 && fa < batch; ++i) request();
+    for (int i = 0; f < batch; ++i, f += stride) {
+        const int stage = i % FFT_STAGES;
+        if (t == 0 && fa < batch) request();
+        mbar_wait(&bars[stage], (uint32_t)((i / FFT_STAGES) & 1));
+        float2 v[E];
+        const float2 *src = stg + (size_t)stage * N + t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = src[e * T];
+        F::run_twreg(v, sm, twr, t, SyncNamed{1 + g, T});
+        float2 *dst = out + f * N + t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) __stcs(dst + e * T, v[e]);
+    }
+}
+
 template <int LOG2N, bool INV>
 static int launch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t batch, cudaStream_t s)
 {
     using F = CtaFFT<LOG2N, INV>;
     constexpr int T = F::T;
+    if constexpr (T >= 32 && T <= 128) {
+        // in-place calls are safe here too: a frame is fully in shared memory before its slot is written
+        if (((uintptr_t)in & 15) == 0 && batch >= 64) {
+            using Cfg = FftTmaCfg<LOG2N, INV>;
+            auto kern = fft_tma_kernel<LOG2N, INV>;
+            LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            int occ = 1;
+            LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+            if (occ < 1) occ = 1;
+            size_t blocks = ceil_div(batch, (size_t)Cfg::G);
+            const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+            if (blocks > max_blocks) blocks = max_blocks;
+            kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(in, out, batch, p->d_tw);
+            LRC_CUDA(cudaGetLastError());
+            return LRC_OK;
+        }
+    }
     const int threads = T > 128 ? T : 128;
     const int G = threads / T;
     const size_t smem = (size_t)G * F::SMEM_CPX * sizeof(float2);
@@ -231,6 +312,107 @@ psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const f
     }
 }
 
+// Same work, frames staged by the TMA engine: every transform group owns a PSD_STAGES-deep ring of frame
+// buffers in shared memory; its leader thread keeps PSD_STAGES-1 bulk copies in flight while the group
+// transforms the current frame, so HBM latency is hidden inside the group instead of by occupancy alone.
+// Used for N = 512..2048 (T = 32..128 threads per transform) when the input is 16-byte aligned.
+constexpr int PSD_STAGES = 3;
+
+template <int LOG2N>
+struct PsdTmaCfg {
+    using F = CtaFFT<LOG2N, false>;
+    static constexpr int THREADS = F::T > 128 ? F::T : 128;
+    static constexpr int G = THREADS / F::T;
+    static constexpr int FRAME_BYTES = F::N * 8;
+    static constexpr int GROUP_BYTES = ((PSD_STAGES * FRAME_BYTES + F::SMEM_CPX * 8 + PSD_STAGES * 8) + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(PsdTmaCfg<LOG2N>::THREADS)
+psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
+               float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
+{
+    using Cfg = PsdTmaCfg<LOG2N>;
+    using F = CtaFFT<LOG2N, false>;
+    constexpr int N = F::N, E = F::E, T = F::T, G = Cfg::G;
+    extern __shared__ __align__(128) uint8_t psd_smem[];
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    uint8_t *gbase = psd_smem + (size_t)g * Cfg::GROUP_BYTES;
+    float2 *stg = reinterpret_cast<float2 *>(gbase);
+    float2 *sm = reinterpret_cast<float2 *>(gbase + PSD_STAGES * Cfg::FRAME_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + PSD_STAGES * Cfg::FRAME_BYTES + F::SMEM_CPX * 8);
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < PSD_STAGES; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    float w[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) w[e] = win[t + e * T];
+    float2 twr[F::TW_REGS];
+    F::load_twiddles(tw, t, twr);
+
+    // the group's frame sequence: items item0, item0 + stride, ...; frames f0..f1-1 inside each
+    const size_t stride = (size_t)gridDim.x * G;
+    auto item_range = [&](size_t item, size_t &f0, size_t &f1) {
+        const size_t row = item / ipr, c = item % ipr;
+        f0 = row * k_avg + c * fpi;
+        f1 = f0 + fpi;
+        if (f1 > (row + 1) * k_avg) f1 = (row + 1) * k_avg;
+    };
+    struct Cursor { size_t item, f, f1; };
+    auto advance = [&](Cursor &c) {
+        if (++c.f == c.f1) {
+            c.item += stride;
+            if (c.item < n_items) item_range(c.item, c.f, c.f1);
+        }
+    };
+    Cursor cur{(size_t)blockIdx.x * G + g, 0, 0};
+    if (cur.item >= n_items) return;
+    item_range(cur.item, cur.f, cur.f1);
+    Cursor ahead = cur;                                   // next frame to request
+    int requested = 0;
+    auto request = [&]() {                                // leader only
+        const int stage = requested % PSD_STAGES;
+        mbar_expect_tx(&bars[stage], Cfg::FRAME_BYTES);
+        tma_load_1d_evict_first(stg + (size_t)stage * N, in + ahead.f * N, Cfg::FRAME_BYTES, &bars[stage]);
+        ++requested;
+        advance(ahead);
+    };
+    if (t == 0)
+        for (int i = 0; i < PSD_STAGES - 1 && ahead.item < n_items; ++i) request();
+
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    for (int i = 0; cur.item < n_items; ++i) {
+        const int stage = i % PSD_STAGES;
+        // the stage being refilled now was read (into registers) one iteration ago, and every thread has
+        // passed a group barrier of that transform since
+        if (t == 0 && ahead.item < n_items) request();
+        mbar_wait(&bars[stage], (uint32_t)((i / PSD_STAGES) & 1));
+        float2 v[E];
+        const float2 *src = stg + (size_t)stage * N + t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float2 x = src[e * T];
+            v[e] = make_float2(x.x * w[e], x.y * w[e]);
+        }
+        F::run_twreg(v, sm, twr, t, SyncNamed{1 + g, T});
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));
+        if (cur.f + 1 == cur.f1) {                        // last frame of the item: hand the partial spectrum out
+            float *dst = partial + cur.item * N + t;
+#pragma unroll
+            for (int e = 0; e < E; ++e) { dst[e * T] = acc[e]; acc[e] = 0.f; }
+        }
+        advance(cur);
+    }
+}
+
 __global__ void psd_reduce_kernel(const float *__restrict__ partial, float *__restrict__ rows, int nfft,
                                   size_t ipr, size_t n_rows, float scale, int accumulate)
 {
@@ -250,6 +432,22 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
 {
     using F = CtaFFT<LOG2N, false>;
     constexpr int T = F::T;
+    if constexpr (T >= 32 && T <= 128) {            // N = 512 .. 2048: the ring fits several CTAs per SM
+        if (((uintptr_t)in & 15) == 0) {
+            using Cfg = PsdTmaCfg<LOG2N>;
+            auto kern = psd_tma_kernel<LOG2N>;
+            LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            int occ = 1;
+            LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+            if (occ < 1) occ = 1;
+            size_t blocks = ceil_div(n_items, (size_t)Cfg::G);
+            const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+            if (blocks > max_blocks) blocks = max_blocks;
+            kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
+            LRC_CUDA(cudaGetLastError());
+            return LRC_OK;
+        }
+    }
     const int threads = T > 128 ? T : 128;
     const int G = threads / T;
     const size_t smem = (size_t)G * F::SMEM_CPX * sizeof(float2);
