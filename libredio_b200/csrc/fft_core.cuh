@@ -199,13 +199,29 @@ struct CtaFFT {
             for (int r = 0; r < R; ++r) v[q + r * NB] = u[r];
         }
         if constexpr (!LAST) {
-            // not the last pass => R == E, one butterfly per thread (j = t)
+            // not the last pass => R == E == 16, one butterfly per thread (j = t).  The padded addresses
+            // are written as one base plus compile-time offsets (pad() is linear across multiples of 16),
+            // so every access is a single LDS/STS with an immediate offset and no per-access integer math.
             const int base = (t / NS) * (NS * R) + (t & (NS - 1));
+            float2 *wp = sm + pad(base);
+            if constexpr (NS == 1) {
+                // base = 16 t: pad(16 t + r) = pad(16 t) + r for r < 16
 #pragma unroll
-            for (int r = 0; r < R; ++r) sm[pad(base + r * NS)] = v[r];
+                for (int r = 0; r < R; ++r) wp[r] = v[r];
+            } else {
+                // NS is a multiple of 16: pad(base + r NS) = pad(base) + r (NS + NS/16)
+#pragma unroll
+                for (int r = 0; r < R; ++r) wp[r * (NS + NS / 16)] = v[r];
+            }
             sync();
+            if constexpr (T % 16 == 0) {
+                const float2 *rp = sm + pad(t);          // pad(t + e T) = pad(t) + e (T + T/16)
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = sm[pad(t + e * T)];
+                for (int e = 0; e < E; ++e) v[e] = rp[e * (T + T / 16)];
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = sm[pad(t + e * T)];
+            }
             sync();
             stage<NS * R, TWREG, Sync>(v, sm, tw, twr, t, sync);
         }

@@ -4,6 +4,7 @@
 // libkissfft/kiss_fft.c:339-388); |X|^2 averaging after tools/psdpng.c:157-178.
 #include "fft_core.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 using namespace lrfft;
@@ -316,10 +317,10 @@ psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const f
 // buffers in shared memory; its leader thread keeps PSD_STAGES-1 bulk copies in flight while the group
 // transforms the current frame, so HBM latency is hidden inside the group instead of by occupancy alone.
 // Used for N = 512..2048 (T = 32..128 threads per transform) when the input is 16-byte aligned.
-constexpr int PSD_STAGES = 3;
 
-template <int LOG2N>
+template <int LOG2N, int PSD_STAGES>
 struct PsdTmaCfg {
+    static constexpr int STAGES = PSD_STAGES;
     using F = CtaFFT<LOG2N, false>;
     static constexpr int THREADS = F::T > 128 ? F::T : 128;
     static constexpr int G = THREADS / F::T;
@@ -328,12 +329,12 @@ struct PsdTmaCfg {
     static constexpr int SMEM_BYTES = G * GROUP_BYTES;
 };
 
-template <int LOG2N>
-__global__ void __launch_bounds__(PsdTmaCfg<LOG2N>::THREADS)
+template <int LOG2N, int PSD_STAGES, int MINB>
+__global__ void __launch_bounds__(PsdTmaCfg<LOG2N, PSD_STAGES>::THREADS, MINB)
 psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
                float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
 {
-    using Cfg = PsdTmaCfg<LOG2N>;
+    using Cfg = PsdTmaCfg<LOG2N, PSD_STAGES>;
     using F = CtaFFT<LOG2N, false>;
     constexpr int N = F::N, E = F::E, T = F::T, G = Cfg::G;
     extern __shared__ __align__(128) uint8_t psd_smem[];
@@ -434,8 +435,23 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
     constexpr int T = F::T;
     if constexpr (T >= 32 && T <= 128) {            // N = 512 .. 2048: the ring fits several CTAs per SM
         if (((uintptr_t)in & 15) == 0) {
-            using Cfg = PsdTmaCfg<LOG2N>;
-            auto kern = psd_tma_kernel<LOG2N>;
+            static const int variant = getenv("LRC_PSD_VARIANT") ? atoi(getenv("LRC_PSD_VARIANT")) : 0;
+            if (variant == 1) {
+                using Cfg = PsdTmaCfg<LOG2N, 2>;
+                auto kern = psd_tma_kernel<LOG2N, 2, 4>;
+                LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+                int occ = 1;
+                LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+                if (occ < 1) occ = 1;
+                size_t blocks = ceil_div(n_items, (size_t)Cfg::G);
+                const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+                if (blocks > max_blocks) blocks = max_blocks;
+                kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
+                LRC_CUDA(cudaGetLastError());
+                return LRC_OK;
+            }
+            using Cfg = PsdTmaCfg<LOG2N, 3>;
+            auto kern = psd_tma_kernel<LOG2N, 3, 1>;
             LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
             int occ = 1;
             LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
