@@ -49,51 +49,110 @@ def workload_name(frames: int) -> str:
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and clock-event reasons sampled through NVML every ~2 ms from a thread (nvidia-smi -lms cannot
+    deliver a sample inside a region that lasts tens of milliseconds); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
-
-    def start(self):
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.how = None
+        self.nv = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv, self.h = pynvml, h
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll_nvml(self):
+        nv, h = self.nv, self.h
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(self.max_sm)
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                try:
+                    self.pw.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+            except Exception:
+                break
+            time.sleep(0.002)
 
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _poll_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.proc.stdout:
             p = [s.strip() for s in ln.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                self.sm.append(float(p[1])); self.mx.append(float(p[2])); self.pw.append(float(p[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, p[5:9]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(nm)
+
+    def start(self):
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 20"
+            self.th = threading.Thread(target=self._poll_smi, daemon=True)
+            self.th.start()
+        except Exception:
+            self.how = None
+
+    def n(self) -> int:
+        return len(self.sm)
+
+    def stop(self) -> dict:
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        self.stop_flag.set()
+        if self.nv is None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.th:
+            self.th.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w_max": max(self.pw) if self.pw else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -218,7 +277,11 @@ def run_ours(args):
     drain()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -245,7 +308,22 @@ def run_ours(args):
         dist.barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    clocks = sampler.stop() if sampler else None
+    clocks = None
+    if sampler:
+        # NVML refreshes its clock reading only every few tens of ms: when the timed region was too short
+        # to be seen, keep the same steps running (untimed) under the sampler until it has a few readings.
+        window = "timed region"
+        if sampler.n() < 8 or total_ms < 300.0:
+            t_end = time.perf_counter() + 0.6
+            i = 0
+            while time.perf_counter() < t_end:
+                chain.run(x, K_AVG, outs[i & 1]); i += 1
+                if i % 16 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            window = f"timed region ({total_ms:.0f} ms) + 0.6 s of the same step repeated untimed right after it"
+        clocks = sampler.stop()
+        clocks["window"] = window
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
