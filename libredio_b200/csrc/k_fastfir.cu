@@ -8,6 +8,7 @@
 // registers/shared memory (the forward output layout "thread t holds bin t + e*T" is exactly the
 // inverse input layout), so HBM sees nfft reads and ngood writes per block and nothing else.
 #include "fft_core.cuh"
+#include <cstdlib>
 #include <vector>
 
 using namespace lrfft;
@@ -21,6 +22,7 @@ struct lrc_fastfir {
     int      log2n;
     float2  *d_tw;
     float2  *d_H;
+    float2  *d_Hc;     // nfft == 8192: H in the order fastfir8k_kernel uses
 };
 
 template <int LOG2N>
@@ -59,6 +61,187 @@ fastfir_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// nfft = 8192 (kiss_fastfir's automatic size for 2048 < nh <= 4096, the config-5 shape): in-place
+// shared-memory variant.  The register-resident Stockham kernel above fills half the register file
+// with one transform, so only one CTA fits an SM and every barrier and global load is exposed.  Here
+// the block lives in shared memory (68 KB), a thread only ever holds one butterfly, and two CTAs per
+// SM cover each other's barriers and loads.
+//
+//   8192 = 16 x 16 x 32.  Forward = decimation in frequency, in place:
+//     P1  radix 16, stride 512, inputs straight from global memory, twiddle W_8192^(q j)
+//     P2  radix 16 inside each 512-block, stride 32, twiddle W_512^(q j)
+//     MID the 256 contiguous 32-point sub-blocks: DFT32 -> .* H -> IDFT32 in registers
+//   and the inverse mirrors it as decimation in time (P2', then P1' whose outputs go straight to
+//   global memory), so the digit-reversed order produced by the DIF passes is never undone: H is
+//   stored in that order instead (position 512 b + 32 q2 + k2 holds bin b + 16 q2 + 256 k2).
+//   Shared-memory index i is padded to i + 2 (i / 32): the strided passes stay conflict-free and
+//   the contiguous 32-point blocks of MID start 17 x 16 bytes apart (conflict-free LDS.128).
+// ---------------------------------------------------------------------------------------------
+namespace ff8k {
+constexpr int N = 8192, NT = 256;
+constexpr int DATA_CPX = N + 2 * (N / 32);                 // 8704 float2
+constexpr int TW1_CPX = 15 * 256, TW2_CPX = 15 * 32;
+constexpr int SMEM_BYTES = (DATA_CPX + TW1_CPX + TW2_CPX) * 8;
+__host__ __device__ constexpr int pad(int i) { return i + 2 * (i >> 5); }
+
+// exp(-2 pi j n / 32), n < 16
+__device__ __forceinline__ float2 w32(int n)
+{
+    constexpr float C[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                             0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                             -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                             -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float S[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                             0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+                             0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                             0.38268343236508977173f, 0.19509032201612826785f};
+    return make_float2(C[n], -S[n]);
+}
+}  // namespace ff8k
+
+__global__ void __launch_bounds__(ff8k::NT, 2)
+fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict__ out, size_t n_blocks_full,
+                 size_t n_blocks, size_t ngood, size_t flush_keep, const float2 *__restrict__ tw,
+                 const float2 *__restrict__ Hc)
+{
+    using namespace ff8k;
+    extern __shared__ __align__(16) float2 ff8k_smem[];
+    float2 *sd = ff8k_smem;
+    float2 *tw1 = ff8k_smem + DATA_CPX;            // [q-1][j], j < 256 : W_8192^(q j)
+    float2 *tw2 = tw1 + TW1_CPX;             // [q-1][j], j < 32  : W_512^(q j)
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < TW1_CPX; i += NT) tw1[i] = __ldg(tw + ((i >> 8) + 1) * (i & 255));
+    for (int i = t; i < TW2_CPX; i += NT) tw2[i] = __ldg(tw + 16 * ((i >> 5) + 1) * (i & 31));
+    __syncthreads();
+
+    for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const size_t s0 = b * ngood;
+        const size_t avail = n_in - s0;                  // < N only for the flush block
+        const float2 *src = in + s0;
+        // ---- P1 forward: butterflies j = t and t + 256, inputs from global memory -----------------
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = t + 256 * h;
+            float2 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const size_t i = (size_t)(j + 512 * r);
+                v[r] = i < avail ? __ldg(src + i) : make_float2(0.f, 0.f);
+            }
+            RegFFT<16, false>::run(v);
+            float2 *dst = sd + pad(j);               // pad(j + 512 q) = pad(j) + 544 q
+            dst[0] = v[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) {
+                float2 w = tw1[(q - 1) * 256 + t];
+                if (h) w = cmulf(w, w32(q));             // W_8192^(256 q) = W_32^q
+                dst[544 * q] = cmulf(v[q], w);
+            }
+        }
+        __syncthreads();
+        // ---- P2 forward: (block bb, j = lane), bb = warp and warp + 8 ---------------------------------
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 *p = sd + 544 * (warp + 8 * h) + lane;    // pad(512 bb + j + 32 r) = 544 bb + 34 r + j
+            float2 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = p[34 * r];
+            RegFFT<16, false>::run(v);
+            p[0] = v[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) p[34 * q] = cmulf(v[q], tw2[(q - 1) * 32 + lane]);
+        }
+        __syncthreads();
+        // ---- MID: sub-block t, 32 contiguous points: DFT32, .* H, IDFT32 --------------------------------
+        {
+            float4 *p4 = reinterpret_cast<float4 *>(sd + 34 * t);
+            float2 u[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 x = p4[i];
+                u[2 * i] = make_float2(x.x, x.y);
+                u[2 * i + 1] = make_float2(x.z, x.w);
+            }
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float2 a = cadd(u[n], u[n + 16]);
+                const float2 d = csub(u[n], u[n + 16]);
+                u[n] = a;
+                u[n + 16] = n ? cmulf(d, w32(n)) : d;
+            }
+            RegFFT<16, false>::run(u);                   // u[m]      = X2[2 m]
+            RegFFT<16, false>::run(u + 16);              // u[16 + m] = X2[2 m + 1]
+#pragma unroll
+            for (int m = 0; m < 32; ++m) u[m] = cmulf(u[m], __ldg(Hc + m * 256 + t));   // C_MUL  :180-184
+            RegFFT<16, true>::run(u);
+            RegFFT<16, true>::run(u + 16);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float2 c = n ? cmul_conjb(u[n + 16], w32(n)) : u[n + 16];
+                const float2 a = u[n];
+                u[n] = cadd(a, c);
+                u[n + 16] = csub(a, c);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p4[i] = make_float4(u[2 * i].x, u[2 * i].y, u[2 * i + 1].x, u[2 * i + 1].y);
+        }
+        __syncthreads();
+        // ---- P2 inverse ------------------------------------------------------------------------------
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 *p = sd + 544 * (warp + 8 * h) + lane;
+            float2 v[16];
+            v[0] = p[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v[q] = cmul_conjb(p[34 * q], tw2[(q - 1) * 32 + lane]);
+            RegFFT<16, true>::run(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) p[34 * r] = v[r];
+        }
+        __syncthreads();
+        // ---- P1 inverse: outputs straight to global memory, the first `keep` of them ------------------
+        const size_t keep = (b < n_blocks_full) ? ngood : flush_keep;
+        float2 *dstg = out + s0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = t + 256 * h;
+            const float2 *p = sd + pad(j);
+            float2 v[16];
+            v[0] = p[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) {
+                float2 w = tw1[(q - 1) * 256 + t];
+                if (h) w = cmulf(w, w32(q));
+                v[q] = cmul_conjb(p[544 * q], w);
+            }
+            RegFFT<16, true>::run(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const size_t i = (size_t)(j + 512 * r);
+                if (i < keep) __stcs(dstg + i, v[r]);
+            }
+        }
+        __syncthreads();                                   // the next block's P1 overwrites the buffer
+    }
+}
+
+// H (natural order, already scaled by 1/nfft) -> the order fastfir8k_kernel's MID stage meets it in:
+// Hc[m * 256 + s], s = 16 b + q2 the 32-point sub-block, m the register index after the split DFT32
+// (m < 16: k2 = 2 m, else k2 = 2 (m - 16) + 1), bin = b + 16 q2 + 256 k2.
+static void fastfir8k_permute_H(const std::vector<float2> &H, std::vector<float2> &Hc)
+{
+    Hc.resize(8192);
+    for (int s = 0; s < 256; ++s)
+        for (int m = 0; m < 32; ++m) {
+            const int bb = s >> 4, q2 = s & 15, k2 = m < 16 ? 2 * m : 2 * (m - 16) + 1;
+            Hc[m * 256 + s] = H[bb + 16 * q2 + 256 * k2];
+        }
+}
+
 extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t nh, size_t nfft, lrc_fastfir **out)
 {
     LRC_BIND(ctx);
@@ -77,7 +260,7 @@ extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t 
         return LRC_ERR_UNSUPPORTED;
     }
     LRC_REQUIRE(nfft >= nh, LRC_ERR_INVALID, "lrc_fastfir_create: nfft shorter than the impulse response");
-    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr};
+    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr, nullptr};
     LRC_REQUIRE(f != nullptr, LRC_ERR_NOMEM, "out of host memory");
     int rc = lrc_make_twiddles((int)nfft, &f->d_tw);
     if (rc) { delete f; return rc; }
@@ -98,6 +281,13 @@ extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t 
         const float scale = (float)(1.0 / (double)nfft);
         for (size_t i = 0; i < nfft; ++i) { rot[i].x *= scale; rot[i].y *= scale; }
         e = cudaMemcpy(f->d_H, rot.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nfft == 8192) {
+            std::vector<float2> hc;
+            fastfir8k_permute_H(rot, hc);
+            e = cudaMalloc(&f->d_Hc, nfft * sizeof(float2));
+            if (e == cudaSuccess) e = cudaMemcpy(f->d_Hc, hc.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fastfir8k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ff8k::SMEM_BYTES);
+        }
     }
     lrc_fft_destroy(plan);
     if (rc || e != cudaSuccess) {
@@ -113,7 +303,7 @@ extern "C" int lrc_fastfir_destroy(lrc_fastfir *f)
 {
     if (!f) return LRC_OK;
     cudaSetDevice(f->ctx->device);
-    cudaFree(f->d_tw); cudaFree(f->d_H);
+    cudaFree(f->d_tw); cudaFree(f->d_H); cudaFree(f->d_Hc);
     delete f;
     return LRC_OK;
 }
@@ -171,6 +361,15 @@ extern "C" int lrc_fastfir_run(lrc_fastfir *f, const float *d_in, size_t n_in, f
     cudaStream_t s = lrc_stream(f->ctx, stream);
     const float2 *in = (const float2 *)d_in;
     float2 *out = (float2 *)d_out;
+    static const int variant = getenv("LRC_FASTFIR_VARIANT") ? atoi(getenv("LRC_FASTFIR_VARIANT")) : 1;
+    if (f->d_Hc && variant == 1) {
+        size_t blocks = (size_t)f->ctx->n_sm * 2;
+        if (blocks > nblk) blocks = nblk;
+        fastfir8k_kernel<<<(unsigned)blocks, ff8k::NT, ff8k::SMEM_BYTES, s>>>(in, n_in, out, full, nblk, f->ngood, keep,
+                                                                             f->d_tw, f->d_Hc);
+        LRC_CUDA(cudaGetLastError());
+        return LRC_OK;
+    }
     switch (f->log2n) {
 #define FF_CASE(L) case L: return launch_fastfir<L>(f, in, n_in, out, full, nblk, keep, s);
         FF_CASE(1) FF_CASE(2) FF_CASE(3) FF_CASE(4) FF_CASE(5) FF_CASE(6) FF_CASE(7)
