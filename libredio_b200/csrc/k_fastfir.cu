@@ -118,30 +118,53 @@ fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict_
     for (int i = t; i < TW2_CPX; i += NT) tw2[i] = __ldg(tw + 16 * ((i >> 5) + 1) * (i & 31));
     __syncthreads();
 
-    for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-        const size_t s0 = b * ngood;
-        const size_t avail = n_in - s0;                  // < N only for the flush block
+    // P1 forward of one column j of block `blk`: inputs from global memory, results into the column's
+    // 16 shared-memory slots (no other thread touches column j during the P1 phases)
+    auto p1_load = [&](size_t blk, int j, float2 *v) {
+        const size_t s0 = blk * ngood, avail = n_in - s0;        // avail < N only for the flush block
         const float2 *src = in + s0;
-        // ---- P1 forward: butterflies j = t and t + 256, inputs from global memory -----------------
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const size_t i = (size_t)(j + 512 * r);
+            v[r] = i < avail ? __ldg(src + i) : make_float2(0.f, 0.f);
+        }
+    };
+    auto p1_forward = [&](int h, float2 *v) {
+        RegFFT<16, false>::run(v);
+        float2 *dst = sd + pad(t + 256 * h);         // pad(j + 512 q) = pad(j) + 544 q
+        dst[0] = v[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) {
+            float2 w = tw1[(q - 1) * 256 + t];
+            if (h) w = cmulf(w, w32(q));                 // W_8192^(256 q) = W_32^q
+            dst[544 * q] = cmulf(v[q], w);
+        }
+    };
+
+    size_t b = blockIdx.x;
+    if (b < n_blocks) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int j = t + 256 * h;
             float2 v[16];
+            p1_load(b, t + 256 * h, v);
+            p1_forward(h, v);
+        }
+    }
+    for (; b < n_blocks; b += gridDim.x) {
+        // the next block's input (512 lines) is asked into L2 now; its P1 loads come four phases later
+        if (b + gridDim.x < n_blocks) {
+            const char *nsrc = reinterpret_cast<const char *>(in + (b + gridDim.x) * ngood);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const size_t i = (size_t)(j + 512 * r);
-                v[r] = i < avail ? __ldg(src + i) : make_float2(0.f, 0.f);
-            }
-            RegFFT<16, false>::run(v);
-            float2 *dst = sd + pad(j);               // pad(j + 512 q) = pad(j) + 544 q
-            dst[0] = v[0];
-#pragma unroll
-            for (int q = 1; q < 16; ++q) {
-                float2 w = tw1[(q - 1) * 256 + t];
-                if (h) w = cmulf(w, w32(q));             // W_8192^(256 q) = W_32^q
-                dst[544 * q] = cmulf(v[q], w);
+            for (int k = 0; k < 2; ++k) {
+                const size_t off = (size_t)(t + 256 * k) * 128;
+                if ((b + gridDim.x) * ngood * 8 + off < n_in * 8)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(nsrc + off));
             }
         }
+        // first half of this thread's H values (an L2 round trip): in flight across the whole P2 phase
+        float2 hv[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) hv[m] = __ldg(Hc + m * 256 + t);
         __syncthreads();
         // ---- P2 forward: (block bb, j = lane), bb = warp and warp + 8 ---------------------------------
 #pragma unroll
@@ -155,10 +178,10 @@ fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict_
 #pragma unroll
             for (int q = 1; q < 16; ++q) p[34 * q] = cmulf(v[q], tw2[(q - 1) * 32 + lane]);
         }
-        __syncthreads();
         // ---- MID: sub-block t, 32 contiguous points: DFT32, .* H, IDFT32 --------------------------------
         {
             float4 *p4 = reinterpret_cast<float4 *>(sd + 34 * t);
+            __syncthreads();
             float2 u[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -174,10 +197,14 @@ fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict_
                 u[n + 16] = n ? cmulf(d, w32(n)) : d;
             }
             RegFFT<16, false>::run(u);                   // u[m]      = X2[2 m]
+#pragma unroll
+            for (int m = 0; m < 16; ++m) u[m] = cmulf(u[m], hv[m]);               // C_MUL  :180-184
+#pragma unroll
+            for (int m = 0; m < 16; ++m) hv[m] = __ldg(Hc + (16 + m) * 256 + t);
+            RegFFT<16, true>::run(u);
             RegFFT<16, false>::run(u + 16);              // u[16 + m] = X2[2 m + 1]
 #pragma unroll
-            for (int m = 0; m < 32; ++m) u[m] = cmulf(u[m], __ldg(Hc + m * 256 + t));   // C_MUL  :180-184
-            RegFFT<16, true>::run(u);
+            for (int m = 0; m < 16; ++m) u[16 + m] = cmulf(u[16 + m], hv[m]);
             RegFFT<16, true>::run(u + 16);
 #pragma unroll
             for (int n = 0; n < 16; ++n) {
@@ -189,6 +216,11 @@ fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict_
 #pragma unroll
             for (int i = 0; i < 16; ++i) p4[i] = make_float4(u[2 * i].x, u[2 * i].y, u[2 * i + 1].x, u[2 * i + 1].y);
         }
+        // column t of the CTA's next block: requested now, used after this block's P1 inverse of column t
+        const size_t nb = b + gridDim.x;
+        const bool more = nb < n_blocks;
+        float2 nx0[16];
+        if (more) p1_load(nb, t, nx0);
         __syncthreads();
         // ---- P2 inverse ------------------------------------------------------------------------------
 #pragma unroll
@@ -203,29 +235,42 @@ fastfir8k_kernel(const float2 *__restrict__ in, size_t n_in, float2 *__restrict_
             for (int r = 0; r < 16; ++r) p[34 * r] = v[r];
         }
         __syncthreads();
-        // ---- P1 inverse: outputs straight to global memory, the first `keep` of them ------------------
+        // ---- P1 inverse of this block, column by column, fused with P1 forward of the CTA's next block:
+        // the next block's column is requested from global memory first, the inverse butterfly of the
+        // current column runs while those loads are in flight, and the forward results then reuse the
+        // column's slots -- no barrier between the two blocks' P1 phases.
+        const size_t s0 = b * ngood;
         const size_t keep = (b < n_blocks_full) ? ngood : flush_keep;
         float2 *dstg = out + s0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int j = t + 256 * h;
-            const float2 *p = sd + pad(j);
-            float2 v[16];
-            v[0] = p[0];
+            float2 nx[16];
+            if (h == 0) {
 #pragma unroll
-            for (int q = 1; q < 16; ++q) {
-                float2 w = tw1[(q - 1) * 256 + t];
-                if (h) w = cmulf(w, w32(q));
-                v[q] = cmul_conjb(p[544 * q], w);
+                for (int r = 0; r < 16; ++r) nx[r] = nx0[r];
+            } else if (more) {
+                p1_load(nb, j, nx);
             }
-            RegFFT<16, true>::run(v);
+            {
+                const float2 *p = sd + pad(j);
+                float2 v[16];
+                v[0] = p[0];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const size_t i = (size_t)(j + 512 * r);
-                if (i < keep) __stcs(dstg + i, v[r]);
+                for (int q = 1; q < 16; ++q) {
+                    float2 w = tw1[(q - 1) * 256 + t];
+                    if (h) w = cmulf(w, w32(q));
+                    v[q] = cmul_conjb(p[544 * q], w);
+                }
+                RegFFT<16, true>::run(v);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const size_t i = (size_t)(j + 512 * r);
+                    if (i < keep) __stcs(dstg + i, v[r]);
+                }
             }
+            if (more) p1_forward(h, nx);
         }
-        __syncthreads();                                   // the next block's P1 overwrites the buffer
     }
 }
 
