@@ -34,7 +34,7 @@ enum {
     LRC_OK = 0,
     LRC_ERR_INVALID = 1,      /* bad argument (NULL, zero size, ...) */
     LRC_ERR_CUDA = 2,         /* CUDA runtime/driver error, see lrc_last_error() */
-    LRC_ERR_UNSUPPORTED = 3,  /* valid for the reference but not implemented here (e.g. non-2^k nfft) */
+    LRC_ERR_UNSUPPORTED = 3,  /* valid for the reference but not implemented here (e.g. nfft > 8192) */
     LRC_ERR_NOMEM = 4,
     LRC_ERR_CAPACITY = 5,     /* caller-provided output capacity too small */
     LRC_ERR_ODD_LENGTH = 6,   /* odd byte count into the u8-IQ unpack (the reference panics) */
@@ -97,8 +97,10 @@ int lrc_fir_stream_push(lrc_fir_stream *st, const void *d_chunk, size_t n, size_
 /* ------------------------------------------------------------------------------------------------
  * (3) FFT.   Replaces the kissfft binding: kiss_fft_alloc / kiss_fft (src/kissfft/src/kissfft.rs:11-31,
  *     libkissfft/kiss_fft.c:339-388).  Unscaled, forward e^{-j..}, inverse e^{+j..} also unscaled.
- *     nfft must be a power of two in [2, 8192] (others: LRC_ERR_UNSUPPORTED).  `batch` frames of nfft
- *     samples, contiguous.  d_in == d_out is allowed (kiss_fft.c:373-379).
+ *     nfft in [2, 8192]: powers of two run the register/shared-memory Stockham kernels, every other
+ *     size (kissfft's mixed radix 2/3/4/5 + generic odd primes, kiss_fft.c:309-330) a shared-memory
+ *     mixed-radix kernel; larger sizes: LRC_ERR_UNSUPPORTED.  `batch` frames of nfft samples,
+ *     contiguous.  d_in == d_out is allowed (kiss_fft.c:373-379).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct lrc_fft lrc_fft;
 int lrc_fft_create(lrc_ctx *ctx, int nfft, int inverse, lrc_fft **fft);
@@ -107,6 +109,17 @@ int lrc_fft_run(lrc_fft *fft, const float *d_in, float *d_out, size_t batch, voi
 /* host-buffer convenience with the reference block's contract: n_samples must be a multiple of
  * block_size (LRC_ERR_LENGTH otherwise, the assert of kissfft.rs:24). Synchronous. */
 int lrc_fft_run_host(lrc_fft *fft, const float *h_in, float *h_out, size_t n_samples);
+
+/* real-input pair.   Replaces kiss_fftr_alloc / kiss_fftr / kiss_fftri (libkissfft/tools/kiss_fftr.c:
+ *     28-66, 67-119, 121-159).  nfft even (odd: LRC_ERR_INVALID, the reference prints "Real FFT
+ *     optimization must be even" and returns NULL).  Forward (inverse == 0): `batch` frames of nfft f32
+ *     -> batch frames of nfft/2+1 complex bins.  Inverse: nfft/2+1 bins -> nfft f32, unscaled (a round
+ *     trip multiplies by nfft, README:105).  nfft/2 follows lrc_fft_create's size rules. */
+typedef struct lrc_rfft lrc_rfft;
+int lrc_rfft_create(lrc_ctx *ctx, int nfft, int inverse, lrc_rfft **rfft);
+int lrc_rfft_destroy(lrc_rfft *rfft);
+int lrc_rfft_run(lrc_rfft *rfft, const float *d_in, float *d_out, size_t batch, void *stream);
+int lrc_rfft_run_host(lrc_rfft *rfft, const float *h_in, float *h_out, size_t batch);
 
 /* window + |X|^2 averaging (north-star stage; nearest reference code tools/psdpng.c:157-178):
  *     rows[r][b] = (1/k_avg) * sum_{f<k_avg} | FFT(w .* frame[r*k_avg + f]) [b] |^2

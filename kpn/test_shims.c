@@ -11,6 +11,12 @@ typedef struct kiss_fft_state *kiss_fft_cfg;
 kiss_fft_cfg kiss_fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem);
 void kiss_fft(kiss_fft_cfg cfg, const kiss_fft_cpx *fin, kiss_fft_cpx *fout);
 void kiss_fft_cleanup(void);
+int kiss_fft_next_fast_size(int n);
+/* tools/kiss_fftr.h:21-43 */
+typedef struct kiss_fftr_state *kiss_fftr_cfg;
+kiss_fftr_cfg kiss_fftr_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem);
+void kiss_fftr(kiss_fftr_cfg cfg, const float *timedata, kiss_fft_cpx *freqdata);
+void kiss_fftri(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, float *timedata);
 
 typedef struct {
     const float *data_in; float *data_out;
@@ -43,6 +49,33 @@ int main(void)
     CHECK(kiss_fft_alloc(n, 1, NULL, &need) == NULL && need > 0);        /* size query protocol, kiss_fft.h:66-78 */
     kiss_fft_cleanup();
     free(cfg);                                                           /* "can be simply free()d" kiss_fft.h:100-102 */
+
+    /* a size kissfft factors as 2^3 5^3 (kf_factor, kiss_fft.c:309-330) and the next-fast-size helper */
+    CHECK(kiss_fft_next_fast_size(997) == 1000 && kiss_fft_next_fast_size(1024) == 1024);
+    {
+        const int m = 1000;
+        kiss_fft_cfg c2 = kiss_fft_alloc(m, 0, NULL, NULL);
+        CHECK(c2 != NULL);
+        for (int k = 0; k < m; ++k) { in[k].r = (float)cos(2 * M_PI * 11 * k / m); in[k].i = (float)sin(2 * M_PI * 11 * k / m); }
+        kiss_fft(c2, in, out);
+        CHECK(fabs(out[11].r - m) < 1e-2 && fabs(out[12].r) < 1e-2 && fabs(out[999].i) < 1e-2);
+        free(c2);
+    }
+    /* the real-input pair the way tools/psdpng.c:139,165 and test/test_real.c use it */
+    {
+        const int m = 512;
+        kiss_fftr_cfg fr = kiss_fftr_alloc(m, 0, NULL, NULL), ir = kiss_fftr_alloc(m, 1, NULL, NULL);
+        CHECK(fr != NULL && ir != NULL);
+        CHECK(kiss_fftr_alloc(511, 0, NULL, NULL) == NULL);              /* "Real FFT optimization must be even." */
+        float t[512], back[512];
+        kiss_fft_cpx F[257];
+        for (int k = 0; k < m; ++k) t[k] = (float)cos(2 * M_PI * 5 * k / m) + 0.5f;
+        kiss_fftr(fr, t, F);
+        CHECK(fabs(F[5].r - m / 2) < 1e-2 && fabs(F[5].i) < 1e-2 && fabs(F[0].r - 0.5 * m) < 1e-2 && F[0].i == 0 && F[256].i == 0);
+        kiss_fftri(ir, F, back);
+        for (int k = 0; k < m; ++k) CHECK(fabs(back[k] - m * t[k]) < 2e-2);   /* unscaled round trip */
+        free(fr); free(ir);
+    }
 
     /* samplerate.rs:89-96: resample a 1000-sample sine by 2.0 and look at the length */
     int err = -1;

@@ -172,6 +172,34 @@ class Fft:
             self.h = C.c_void_p()
 
 
+class Rfft:
+    """kiss_fftr / kiss_fftri (tools/kiss_fftr.c:67-159): nfft reals <-> nfft/2+1 bins, unscaled both ways."""
+
+    def __init__(self, ctx: Context, nfft: int, inv: int = 0):
+        self.ctx, self.nfft, self.inv = ctx, int(nfft), int(inv)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_rfft_create(ctx.h, self.nfft, self.inv, C.byref(self.h)), "lrc_rfft_create")
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.is_cuda and x.is_contiguous()
+        nb = self.nfft // 2 + 1
+        if self.inv:
+            assert x.dtype == torch.complex64 and x.shape[-1] == nb
+            out = torch.empty(x.shape[:-1] + (self.nfft,), dtype=torch.float32, device=x.device)
+            batch = x.numel() // nb
+        else:
+            assert x.dtype == torch.float32 and x.shape[-1] == self.nfft
+            out = torch.empty(x.shape[:-1] + (nb,), dtype=torch.complex64, device=x.device)
+            batch = x.numel() // self.nfft
+        check(self.ctx.lib.lrc_rfft_run(self.h, _p(x), _p(out), batch, _stream()), "lrc_rfft_run")
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_rfft_destroy(self.h)
+            self.h = C.c_void_p()
+
+
 class Psd:
     def __init__(self, ctx: Context, nfft: int, window: int = capi.WINDOW_HANN):
         self.ctx, self.nfft = ctx, int(nfft)

@@ -55,6 +55,10 @@ SIGNATURES = {
     "lrc_fft_destroy": (_i, [_vp]),
     "lrc_fft_run": (_i, [_vp, _fp, _fp, _sz, _vp]),
     "lrc_fft_run_host": (_i, [_vp, _fp, _fp, _sz]),
+    "lrc_rfft_create": (_i, [_vp, _i, _i, _pp]),
+    "lrc_rfft_destroy": (_i, [_vp]),
+    "lrc_rfft_run": (_i, [_vp, _fp, _fp, _sz, _vp]),
+    "lrc_rfft_run_host": (_i, [_vp, _fp, _fp, _sz]),
     "lrc_psd_create": (_i, [_vp, _i, _i, _pp]),
     "lrc_psd_set_window": (_i, [_vp, _fp]),
     "lrc_psd_destroy": (_i, [_vp]),

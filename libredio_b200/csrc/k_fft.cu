@@ -9,10 +9,19 @@
 
 using namespace lrfft;
 
+// mixed-radix path (k_fft_mixed.cu) for sizes that are not powers of two
+constexpr int MIXED_MAX_FACTORS = 24;
+constexpr int MIXED_MAX_NFFT = 8192;
+struct MixedPlan { int nfac; int radix[MIXED_MAX_FACTORS]; };
+int lrc_fft_mixed_factor(int n, MixedPlan *mp);
+int lrc_fft_mixed_launch(const lrc_ctx *ctx, int nfft, int inverse, const MixedPlan *mp, const float2 *d_tw,
+                         const float2 *in, float2 *out, size_t batch, cudaStream_t s);
+
 struct lrc_fft {
     lrc_ctx *ctx;
-    int      nfft, log2n, inverse;
+    int      nfft, log2n, inverse;   // log2n < 0: mixed-radix plan
     float2  *d_tw;     // exp(-2 pi j k / nfft), k < nfft (forward table; kernels conjugate for inverse)
+    MixedPlan mixed;
 };
 
 struct lrc_psd {
@@ -198,13 +207,22 @@ extern "C" int lrc_fft_create(lrc_ctx *ctx, int nfft, int inverse, lrc_fft **out
 {
     LRC_BIND(ctx);
     LRC_REQUIRE(out != nullptr && nfft >= 1, LRC_ERR_INVALID, "lrc_fft_create: bad arguments");
-    const int l2 = lrc_log2_exact(nfft);
-    if (l2 < 1 || l2 > 13) {
-        lrc_set_error("lrc_fft_create: nfft=%d: only powers of two in [2, 8192] are implemented "
-                      "(kissfft also accepts mixed radix 3/5/odd sizes)", nfft);
+    int l2 = lrc_log2_exact(nfft);
+    MixedPlan mp{};
+    if (nfft == 1 || l2 > 13) {
+        lrc_set_error("lrc_fft_create: nfft=%d: supported sizes are 2..8192", nfft);
         return LRC_ERR_UNSUPPORTED;
     }
-    lrc_fft *p = new (std::nothrow) lrc_fft{ctx, nfft, l2, inverse ? 1 : 0, nullptr};
+    if (l2 < 1) {
+        // not a power of two: kissfft's mixed-radix sizes (kf_factor, kiss_fft.c:309-330)
+        if (nfft > MIXED_MAX_NFFT || lrc_fft_mixed_factor(nfft, &mp) != 0) {
+            lrc_set_error("lrc_fft_create: nfft=%d: sizes that are not powers of two are supported up to %d",
+                          nfft, MIXED_MAX_NFFT);
+            return LRC_ERR_UNSUPPORTED;
+        }
+        l2 = -1;
+    }
+    lrc_fft *p = new (std::nothrow) lrc_fft{ctx, nfft, l2, inverse ? 1 : 0, nullptr, mp};
     LRC_REQUIRE(p != nullptr, LRC_ERR_NOMEM, "out of host memory");
     int rc = lrc_make_twiddles(nfft, &p->d_tw);
     if (rc) { delete p; return rc; }
@@ -230,6 +248,9 @@ extern "C" int lrc_fft_run(lrc_fft *p, const float *d_in, float *d_out, size_t b
     LRC_REQUIRE(((uintptr_t)d_in & 7) == 0 && ((uintptr_t)d_out & 7) == 0, LRC_ERR_INVALID,
                 "lrc_fft_run: buffers must be 8-byte aligned");
     cudaStream_t s = lrc_stream(p->ctx, stream);
+    if (p->log2n < 0)
+        return lrc_fft_mixed_launch(p->ctx, p->nfft, p->inverse, &p->mixed, p->d_tw, (const float2 *)d_in,
+                                    (float2 *)d_out, batch, s);
     return p->inverse ? dispatch_fft<true>(p, (const float2 *)d_in, (float2 *)d_out, batch, s)
                       : dispatch_fft<false>(p, (const float2 *)d_in, (float2 *)d_out, batch, s);
 }

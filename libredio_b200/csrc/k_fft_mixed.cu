@@ -22,11 +22,7 @@ int lrc_make_twiddles(int nfft, float2 **d_tw);
 
 constexpr int MIXED_MAX_FACTORS = 24;
 constexpr int MIXED_MAX_NFFT = 8192;              // 2 x nfft x 8 B of shared memory
-
-struct MixedPlan {
-    int nfac;
-    int radix[MIXED_MAX_FACTORS];
-};
+struct MixedPlan { int nfac; int radix[MIXED_MAX_FACTORS]; };
 
 // kf_factor (kiss_fft.c:309-330): 4s first, then 2, 3, 5, 7, 9...; p*p > n -> n itself
 int lrc_fft_mixed_factor(int n, MixedPlan *mp)

@@ -80,10 +80,66 @@ void kiss_fft_cleanup(void) { /* nothing needed any more (kiss_fft.c:391-394) */
 
 int kiss_fft_next_fast_size(int n)
 {
-    // the reference returns the next 2^a 3^b 5^c; this library only transforms powers of two
-    int m = 1;
-    while (m < n) m <<= 1;
-    return m;
+    // kiss_fft.c:396-408: the next size whose only factors are 2, 3 and 5 (all run on the GPU up to 8192)
+    while (1) {
+        int m = n;
+        while ((m % 2) == 0) m /= 2;
+        while ((m % 3) == 0) m /= 3;
+        while ((m % 5) == 0) m /= 5;
+        if (m <= 1) break;
+        n++;
+    }
+    return n;
+}
+
+// ---- tools/kiss_fftr.h:21-43: real-input pair (used by psdpng and kiss_fastfir's real build) ----------
+struct kiss_fftr_state {
+    unsigned magic;
+    int nfft, inverse;
+    lrc_rfft *plan;
+};
+typedef struct kiss_fftr_state *kiss_fftr_cfg;
+
+kiss_fftr_cfg kiss_fftr_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem)
+{
+    if (nfft & 1) {
+        fprintf(stderr, "Real FFT optimization must be even.\n");   // kiss_fftr.c:34-37
+        return nullptr;
+    }
+    const size_t memneeded = sizeof(struct kiss_fftr_state);
+    kiss_fftr_cfg st = nullptr;
+    if (lenmem == nullptr) {
+        st = (kiss_fftr_cfg)malloc(memneeded);
+    } else {
+        if (mem != nullptr && *lenmem >= memneeded) st = (kiss_fftr_cfg)mem;
+        *lenmem = memneeded;
+    }
+    if (!st) return nullptr;
+    lrc_ctx *ctx = shim_ctx();
+    lrc_rfft *plan = nullptr;
+    if (!ctx || lrc_rfft_create(ctx, nfft, inverse_fft, &plan) != LRC_OK) {
+        fprintf(stderr, "libkissfft (libredio_b200 shim): kiss_fftr_alloc(%d) failed: %s\n", nfft, lrc_last_error());
+        if (lenmem == nullptr) free(st);
+        return nullptr;
+    }
+    st->magic = 0x4b465452u; st->nfft = nfft; st->inverse = inverse_fft; st->plan = plan;
+    return st;
+}
+
+void kiss_fftr(kiss_fftr_cfg cfg, const float *timedata, kiss_fft_cpx *freqdata)
+{
+    if (!cfg || cfg->magic != 0x4b465452u) { fprintf(stderr, "kiss_fftr: bad cfg\n"); abort(); }
+    if (cfg->inverse) { fprintf(stderr, "kiss fft usage error: improper alloc\n"); exit(1); }   // kiss_fftr.c:73-76
+    int rc = lrc_rfft_run_host(cfg->plan, timedata, (float *)freqdata, 1);
+    if (rc != LRC_OK) { fprintf(stderr, "kiss_fftr: %s [%s]\n", lrc_strerror(rc), lrc_last_error()); abort(); }
+}
+
+void kiss_fftri(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, float *timedata)
+{
+    if (!cfg || cfg->magic != 0x4b465452u) { fprintf(stderr, "kiss_fftri: bad cfg\n"); abort(); }
+    if (!cfg->inverse) { fprintf(stderr, "kiss fft usage error: improper alloc\n"); exit(1); }  // kiss_fftr.c:126-129
+    int rc = lrc_rfft_run_host(cfg->plan, (const float *)freqdata, timedata, 1);
+    if (rc != LRC_OK) { fprintf(stderr, "kiss_fftri: %s [%s]\n", lrc_strerror(rc), lrc_last_error()); abort(); }
 }
 
 }  // extern "C"

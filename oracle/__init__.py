@@ -268,6 +268,21 @@ def ref_fftr(x: np.ndarray) -> np.ndarray:
     return out
 
 
+def ref_fftri(X: np.ndarray) -> np.ndarray:
+    """kiss_fftri() of the vendored tools/kiss_fftr.c: nfft/2+1 bins -> nfft reals (unscaled)."""
+    L = _ref("libkissfftr_ref.so")
+    L.kiss_fftr_alloc.restype = C.c_void_p
+    L.kiss_fftr_alloc.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.kiss_fftri.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    X = np.ascontiguousarray(X, dtype=np.complex64)
+    n = 2 * (X.size - 1)
+    out = np.empty(n, dtype=np.float32)
+    cfg = L.kiss_fftr_alloc(n, 1, None, None)
+    L.kiss_fftri(cfg, _ptr(X), _ptr(out))
+    _libc.free(cfg)
+    return out
+
+
 def ref_fastfir(h: np.ndarray, x: np.ndarray, nfft: int = 0, flush: bool = False) -> np.ndarray:
     """kiss_fastfir() of the vendored tools/kiss_fastfir.c, driven the way do_file_filter (:341-390) does
     for one buffer holding the whole input."""

@@ -15,12 +15,20 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import oracle  # noqa: E402
 
 FFT_SIZES = [2, 4, 8, 16, 32, 64, 128, 240, 256, 512, 1000, 1024, 2048, 4096, 8192]
+# sizes that are not powers of two: kissfft's radix 3/5 and generic (odd prime) butterflies, kiss_fft.c:92-235
+MIXED_SIZES = [3, 5, 6, 7, 15, 30, 45, 97, 100, 243, 625, 1001, 1536, 3125, 6000, 7919]
+# real-input transform pair (tools/kiss_fftr.c), even sizes
+RFFT_SIZES = [4, 8, 30, 256, 1000, 1024, 4096]
 SEED = 20261017
 
 
 def fft_input(n: int, seed: int = SEED) -> np.ndarray:
     rng = np.random.default_rng(seed + n)
     return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def rfft_input(n: int, seed: int = SEED) -> np.ndarray:
+    return np.random.default_rng(seed + 7 * n + 1).standard_normal(n).astype(np.float32)
 
 
 def fastfir_case(seed: int = SEED):
@@ -37,6 +45,17 @@ def main() -> None:
         x = fft_input(n)
         out[f"fwd_{n}"] = oracle.ref_kissfft(x, False)
         out[f"inv_{n}"] = oracle.ref_kissfft(x, True)
+    out["mixed_sizes"] = np.array(MIXED_SIZES)
+    for n in MIXED_SIZES:
+        x = fft_input(n)
+        out[f"fwd_{n}"] = oracle.ref_kissfft(x, False)
+        out[f"inv_{n}"] = oracle.ref_kissfft(x, True)
+    out["rfft_sizes"] = np.array(RFFT_SIZES)
+    for n in RFFT_SIZES:
+        t = rfft_input(n)
+        F = oracle.ref_fftr(t)
+        out[f"rfft_{n}"] = F
+        out[f"irfft_{n}"] = oracle.ref_fftri(F)
     h, x = fastfir_case()
     out["fastfir_noflush"] = oracle.ref_fastfir(h, x, 0, False)     # nfft auto = 1024
     out["fastfir_flush"] = oracle.ref_fastfir(h, x, 0, True)

@@ -78,6 +78,27 @@ def test_restated_fft_vs_golden_fixtures_from_vendored_kissfft(golden):
                 assert np.max(np.abs(got - ref)) < 2e-6 * np.sqrt(np.mean(np.abs(ref) ** 2)), (n, inv)
 
 
+def test_restated_fft_vs_mixed_radix_and_real_fixtures(golden):
+    """radix 3/5/generic sizes and the kiss_fftr pair: fixtures from the vendored build vs the restatement
+    and vs f64 numpy (SNR thresholds of the reference's self tests, mk_test.py:30)."""
+    import tests.golden.make_golden as mg
+    for n in golden["mixed_sizes"]:
+        n = int(n)
+        x = mg.fft_input(n)
+        for inv, key in ((False, f"fwd_{n}"), (True, f"inv_{n}")):
+            ref = golden[key]
+            assert np.max(np.abs(oracle.fft(x, inv) - ref)) < 2e-5 * np.sqrt(np.mean(np.abs(ref) ** 2)), (n, inv)
+            exact = np.fft.ifft(x.astype(np.complex128)) * n if inv else np.fft.fft(x.astype(np.complex128))
+            assert D.snr_db(exact, ref) >= 100.0, (n, inv)
+    for n in golden["rfft_sizes"]:
+        n = int(n)
+        t = mg.rfft_input(n)
+        assert D.snr_db(np.fft.rfft(t.astype(np.float64)), golden[f"rfft_{n}"]) >= 100.0
+        assert D.snr_db(n * t.astype(np.float64), golden[f"irfft_{n}"]) >= 100.0
+        if oracle.have_ref():
+            assert np.array_equal(oracle.ref_fftr(t).view(np.uint32), golden[f"rfft_{n}"].view(np.uint32))
+
+
 def test_only_golden_vector_of_the_reference_tree(golden):
     """test/fft.py:95-98, tolerance 1e-5 (:104)"""
     F = oracle.fft(golden["fftpy_tvec"].astype(np.complex64))

@@ -242,10 +242,79 @@ def test_fft_block_size_mismatch_and_unsupported(ctx):
     with pytest.raises(capi.LrcError) as e:
         f.run_host(np.zeros(1000, np.complex64))
     assert e.value.status == capi.ERR_LENGTH
-    with pytest.raises(capi.LrcError) as e:                 # kissfft accepts 1000 = 2^3 5^3; we say so loudly
-        blocks.Fft(ctx, 1000, 0)
+    with pytest.raises(capi.LrcError) as e:                 # kissfft has no size limit; ours is said loudly
+        blocks.Fft(ctx, 10_000, 0)
+    assert e.value.status == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.LrcError) as e:
+        blocks.Fft(ctx, 16384, 0)
     assert e.value.status == capi.ERR_UNSUPPORTED
     f.close()
+
+
+# ---- sizes that are not powers of two (kissfft radix 3 / 5 / generic butterflies) --------------------
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 15, 30, 45, 97, 100, 240, 243, 625, 1000, 1001, 1536, 3125, 6000, 7919])
+@pytest.mark.parametrize("inv", [0, 1])
+def test_fft_mixed_radix_vs_golden_of_vendored_kissfft(ctx, golden, n, inv):
+    from libredio_b200 import blocks
+    import tests.golden.make_golden as mg
+    x = mg.fft_input(n)
+    f = blocks.Fft(ctx, n, inv)
+    got = f.run(dev(x, ctx)).cpu().numpy()
+    assert_close_rms(got, golden[f"{'inv' if inv else 'fwd'}_{n}"])          # the reference's own output
+    exact = np.fft.ifft(x.astype(np.complex128)) * n if inv else np.fft.fft(x.astype(np.complex128))
+    assert D.snr_db(exact, got) >= 100.0                                      # mk_test.py:30
+    f.close()
+
+
+@pytest.mark.parametrize("n,batch", [(1000, 1), (1000, 37), (15, 5000), (7919, 3), (6000, 20), (97, 300)])
+def test_fft_mixed_radix_batched_and_inplace(ctx, n, batch):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(n + batch)
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    f = blocks.Fft(ctx, n, 0)
+    d = dev(x, ctx)
+    got = f.run(d).cpu().numpy()
+    assert_close_rms(got, np.fft.fft(x.astype(np.complex128), axis=-1))
+    f.run(d, inplace=True)
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), got.view(np.uint32))
+    b = blocks.Fft(ctx, n, 1)
+    assert_close_rms(b.run(dev(got, ctx)).cpu().numpy(), n * x.astype(np.complex128))     # unscaled both ways
+    f.close(); b.close()
+
+
+# ---- real-input pair (tools/kiss_fftr.c) ---------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 8, 30, 256, 1000, 1024, 4096])
+def test_rfft_pair_vs_golden_of_vendored_kiss_fftr(ctx, golden, n):
+    from libredio_b200 import blocks
+    import tests.golden.make_golden as mg
+    t = mg.rfft_input(n)
+    fw, bw = blocks.Rfft(ctx, n, 0), blocks.Rfft(ctx, n, 1)
+    F = fw.run(dev(t, ctx)).cpu().numpy()
+    assert F.shape == (n // 2 + 1,)
+    assert_close_rms(F, golden[f"rfft_{n}"])
+    assert_close_rms(F, np.fft.rfft(t.astype(np.float64)))
+    assert F[0].imag == 0.0 and F[-1].imag == 0.0                              # kiss_fftr.c:101-106
+    back = bw.run(dev(golden[f"rfft_{n}"], ctx)).cpu().numpy()
+    assert_close_rms(back, golden[f"irfft_{n}"])
+    assert_close_rms(back, n * t.astype(np.float64))                           # unscaled: round trip = nfft x
+    fw.close(); bw.close()
+
+
+def test_rfft_batched_golden_vector_and_errors(ctx, golden):
+    from libredio_b200 import blocks
+    # the reference tree's only hard-coded vector is a REAL sequence (test/fft.py:95-98)
+    f8 = blocks.Rfft(ctx, 8, 0)
+    got = f8.run(dev(golden["fftpy_tvec"], ctx)).cpu().numpy()
+    assert np.max(np.abs(got - golden["fftpy_Ftvec"][:5])) < 1e-5
+    f8.close()
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((300, 1024)).astype(np.float32)
+    f = blocks.Rfft(ctx, 1024, 0)
+    assert_close_rms(f.run(dev(x, ctx)).cpu().numpy(), np.fft.rfft(x.astype(np.float64), axis=-1))
+    f.close()
+    with pytest.raises(capi.LrcError) as e:                 # "Real FFT optimization must be even." kiss_fftr.c:34-37
+        blocks.Rfft(ctx, 1023, 0)
+    assert e.value.status == capi.ERR_INVALID
 
 
 def test_fft_host_entry_point(ctx):
