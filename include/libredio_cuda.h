@@ -134,6 +134,14 @@ int lrc_psd_destroy(lrc_psd *psd);
 int lrc_psd_run(lrc_psd *psd, const float *d_in, size_t n_frames, size_t k_avg, float *d_rows,
                 void *stream);
 
+/* spectrogram rows of tools/psdpng.c (transform_signal, :120-185): 16-bit PCM, mono or interleaved
+ * stereo (channels summed, :141-146); n_samples counts samples PER CHANNEL.  Every nfft samples make a
+ * frame; optional frame-mean removal (the -a switch, :156-161); kiss_fftr; |X|^2 summed over navg frames;
+ * row[b] = 10 log10(sum/navg + 1), b < nfft/2+1 (:169-176).  Partial trailing frames/rows are dropped as
+ * the reference's read loop drops them.  *n_rows rows of nfft/2+1 f32 are written.  Synchronous. */
+int lrc_psdpng_rows(lrc_ctx *ctx, const int16_t *d_pcm, size_t n_samples, int nfft, int navg,
+                    int remove_dc, int stereo, float *d_rows, size_t *n_rows, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * headline chain, one fused kernel: cf32 -> FIR(ntaps)/decim -> frames of nfft -> window -> FFT ->
  * |X|^2 averaged over k_avg frames.  Frame f covers inputs [f*nfft*decim, f*nfft*decim +

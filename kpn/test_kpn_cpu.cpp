@@ -3,6 +3,10 @@
 #include <chrono>
 #include <cstdio>
 #include "kpn.hpp"
+#include "sources.hpp"
+#include <cstdint>
+#include <cstdlib>
+#include <string>
 using namespace kpn;
 
 #define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
@@ -103,6 +107,71 @@ int main()
         t0.send(3); t0.send(4); t0.drop();
         f.join();
         CHECK(ra.recv() == 3 && ra.recv() == 4 && rb.recv() == 3 && rb.recv() == 4);
+    }
+    // wavio sources (wavio.rs:12-46) over a WAV written here: s16 stereo, 8192 frames
+    {
+        const std::string path = std::string(std::getenv("TMPDIR") ? std::getenv("TMPDIR") : "/tmp") + "/kpn_test_iq.wav";
+        const uint32_t frames = 8192, rate = 2400000, ch = 2, bits = 16;
+        std::vector<int16_t> pcm(frames * ch);
+        for (uint32_t k = 0; k < frames * ch; ++k) pcm[k] = (int16_t)((int)(k * 37u % 65536u) - 32768);
+        {
+            FILE *f = std::fopen(path.c_str(), "wb");
+            CHECK(f != nullptr);
+            const uint32_t data_bytes = frames * ch * bits / 8, riff = 36 + data_bytes, fmt_len = 16, byte_rate = rate * ch * bits / 8;
+            const uint16_t fmt = 1, chs = (uint16_t)ch, align = (uint16_t)(ch * bits / 8), bps = (uint16_t)bits;
+            std::fwrite("RIFF", 1, 4, f); std::fwrite(&riff, 4, 1, f); std::fwrite("WAVE", 1, 4, f);
+            std::fwrite("fmt ", 1, 4, f); std::fwrite(&fmt_len, 4, 1, f); std::fwrite(&fmt, 2, 1, f); std::fwrite(&chs, 2, 1, f);
+            std::fwrite(&rate, 4, 1, f); std::fwrite(&byte_rate, 4, 1, f); std::fwrite(&align, 2, 1, f); std::fwrite(&bps, 2, 1, f);
+            std::fwrite("data", 1, 4, f); std::fwrite(&data_bytes, 4, 1, f); std::fwrite(pcm.data(), 2, pcm.size(), f);
+            std::fclose(f);
+        }
+        auto [tx, rx] = channel<cf32>();
+        std::thread t = spawn([s = std::move(tx), path]() mutable { wav_source_complex_f32(std::move(s), path, 2400000); });
+        t.join();
+        // (frames/2)/1024 = 4 reads of 1024 floats = 2048 complex samples: a quarter of the file (reference quirk)
+        size_t n = 0;
+        while (auto z = rx.try_recv()) {
+            CHECK(z->real() == (float)pcm[2 * n] / 32768.0f && z->imag() == (float)pcm[2 * n + 1] / 32768.0f);
+            ++n;
+        }
+        CHECK(n == 2048);
+        // the chunked variant delivers the whole file
+        auto [tc, rc] = channel<std::vector<cf32>>();
+        std::thread t2 = spawn([s = std::move(tc), path]() mutable { wav_source_complex_chunks(std::move(s), path, 2400000, 3000); });
+        t2.join();
+        size_t total = 0, msgs = 0;
+        while (auto v = rc.try_recv()) { total += v->size(); ++msgs; CHECK((*v)[0].real() == (float)pcm[2 * (total - v->size())] / 32768.0f); }
+        CHECK(total == frames && msgs == 3);
+        // a rate mismatch is the reference's assert_eq! panic: the block dies, the port closes
+        auto [tb, rb] = channel<cf32>();
+        std::thread t3 = spawn([s = std::move(tb), path]() mutable { wav_source_complex_f32(std::move(s), path, 48000); });
+        t3.join();
+        bool closed = false;
+        try { rb.recv(); } catch (const PortClosed &) { closed = true; }
+        CHECK(closed);
+        // raw .iq replay: 512-sample blocks = 1024 bytes, trailing partial block dropped
+        const std::string iqp = path + ".iq";
+        { FILE *f = std::fopen(iqp.c_str(), "wb"); std::vector<uint8_t> b(1024 * 3 + 100); for (size_t k = 0; k < b.size(); ++k) b[k] = (uint8_t)(k * 7); std::fwrite(b.data(), 1, b.size(), f); std::fclose(f); }
+        auto [ti, ri] = channel<std::vector<uint8_t>>();
+        std::thread t4 = spawn([s = std::move(ti), iqp]() mutable { iq_file_source_u8(std::move(s), iqp); });
+        t4.join();
+        size_t blocks = 0;
+        while (auto b = ri.try_recv()) { CHECK(b->size() == 1024 && (*b)[5] == (uint8_t)((blocks * 1024 + 5) * 7)); ++blocks; }
+        CHECK(blocks == 3);
+        std::remove(path.c_str()); std::remove(iqp.c_str());
+    }
+    // oblw.rs:17-49 run/bit/byte packing
+    {
+        std::vector<OblwRun> runs = {{1, 3}, {0, 2}, {1, 1}, {0, 4}};
+        CHECK((oblw_rld(runs) == std::vector<size_t>{1, 1, 1, 0, 0, 1, 0, 0, 0, 0}));
+        auto bytes = oblw_b2B(oblw_r2b(runs));                            // 1110 0100 | 00(pad)
+        CHECK(bytes.size() == 2 && bytes[0] == 0xE4 && bytes[1] == 0x00);
+        CHECK(oblw_B2b({0xE4})[0] && !oblw_B2b({0xE4})[3] && oblw_B2b({0xE4})[5]);
+        uint8_t y[2];
+        oblw_assemble_packet(y, bytes.data(), 2, false);
+        CHECK(y[0] == 0x1B && y[1] == 0xFF);
+        oblw_assemble_packet(y, bytes.data(), 2, true);
+        CHECK(y[0] == 0xE4);
     }
     std::printf("kpn cpu OK\n");
     return 0;

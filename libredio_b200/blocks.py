@@ -225,6 +225,19 @@ class Psd:
             self.h = C.c_void_p()
 
 
+def psdpng_rows(ctx: Context, pcm: torch.Tensor, nfft: int = 1024, navg: int = 20, remove_dc: bool = False,
+                stereo: bool = False) -> torch.Tensor:
+    """tools/psdpng.c transform_signal: int16 PCM -> rows of 10 log10(avg |X|^2 + 1), nfft/2+1 bins each."""
+    assert pcm.dtype == torch.int16 and pcm.is_cuda and pcm.is_contiguous()
+    n_samples = pcm.numel() // (2 if stereo else 1)
+    rows_max = (n_samples // nfft) // navg
+    out = torch.empty((max(rows_max, 1), nfft // 2 + 1), dtype=torch.float32, device=pcm.device)
+    n_rows = C.c_size_t(0)
+    check(ctx.lib.lrc_psdpng_rows(ctx.h, _p(pcm), n_samples, nfft, navg, int(remove_dc), int(stereo), _p(out),
+                                  C.byref(n_rows), _stream()), "lrc_psdpng_rows")
+    return out[: n_rows.value]
+
+
 class Chain:
     """cf32 -> FIR/decimate -> window -> FFT -> |X|^2 average, one fused kernel."""
 

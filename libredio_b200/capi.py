@@ -63,6 +63,7 @@ SIGNATURES = {
     "lrc_psd_set_window": (_i, [_vp, _fp]),
     "lrc_psd_destroy": (_i, [_vp]),
     "lrc_psd_run": (_i, [_vp, _fp, _sz, _sz, _fp, _vp]),
+    "lrc_psdpng_rows": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _fp, _szp, _vp]),
     "lrc_chain_create": (_i, [_vp, _fp, _i, _i, _i, _i, _pp]),
     "lrc_chain_destroy": (_i, [_vp]),
     "lrc_chain_frames": (_sz, [_vp, _sz]),

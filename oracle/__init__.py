@@ -329,3 +329,37 @@ def chain_psd_cpu(x: np.ndarray, taps: np.ndarray, d: int, nfft: int, win: np.nd
         a, f = C.c_void_p(None), C.c_void_p(None)
     nfr = lib().orc_chain_psd(_ptr(x), x.size, _ptr(taps), taps.size, d, nfft, _ptr(win), _ptr(psd), a, f)
     return psd, int(nfr)
+
+
+def psdpng_rows(pcm: np.ndarray, nfft: int = 1024, navg: int = 20, remove_dc: bool = False, stereo: bool = False,
+                fftr=None) -> np.ndarray:
+    """tools/psdpng.c transform_signal (:120-185) statement by statement in f32, with kiss_fftr supplied by the
+    vendored build (``fftr=ref_fftr``, the default when oracle/_ref exists) or by f64 numpy."""
+    if fftr is None:
+        fftr = ref_fftr if have_ref() else (lambda t: np.fft.rfft(t.astype(np.float64)).astype(np.complex64))
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nfreqs = nfft // 2 + 1
+    per = nfft * (2 if stereo else 1)
+    rows = []
+    mag2 = np.zeros(nfreqs, dtype=np.float32)
+    avgctr = 0
+    for f in range(pcm.size // per):
+        buf = pcm[f * per:(f + 1) * per]
+        if stereo:
+            t = (buf[0::2].astype(np.int32) + buf[1::2].astype(np.int32)).astype(np.float32)      # :146
+        else:
+            t = buf.astype(np.float32)                                                            # :152
+        if remove_dc:                                                                             # :156-161
+            avg = np.float32(0)
+            for v in t:
+                avg = np.float32(avg + v)
+            avg = np.float32(avg / np.float32(nfft))
+            t = (t - avg).astype(np.float32)
+        F = fftr(t)
+        mag2 = (mag2 + (F.real * F.real + F.imag * F.imag).astype(np.float32)).astype(np.float32)  # :167
+        avgctr += 1
+        if avgctr == navg:                                                                        # :169-177
+            avgctr = 0
+            rows.append((10 * np.log10((mag2 / np.float32(navg) + np.float32(1)).astype(np.float64))).astype(np.float32))
+            mag2 = np.zeros(nfreqs, dtype=np.float32)
+    return np.stack(rows) if rows else np.zeros((0, nfreqs), dtype=np.float32)

@@ -31,6 +31,18 @@ def rfft_input(n: int, seed: int = SEED) -> np.ndarray:
     return np.random.default_rng(seed + 7 * n + 1).standard_normal(n).astype(np.float32)
 
 
+def psdpng_input(stereo: bool, seed: int = SEED) -> np.ndarray:
+    """16-bit PCM: two tones + noise + a DC offset, 7 frames of 256 (the last row stays incomplete at navg 3)."""
+    rng = np.random.default_rng(seed + (99 if stereo else 98))
+    n = 7 * 256 + 100
+    t = np.arange(n)
+    x = 6000 * np.sin(2 * np.pi * 0.05 * t) + 2500 * np.sin(2 * np.pi * 0.21 * t) + 300 * rng.standard_normal(n) + 1234
+    if stereo:
+        y = 4000 * np.sin(2 * np.pi * 0.11 * t) + 300 * rng.standard_normal(n) - 500
+        return np.stack([x, y], axis=1).round().astype(np.int16).reshape(-1)
+    return x.round().astype(np.int16)
+
+
 def fastfir_case(seed: int = SEED):
     rng = np.random.default_rng(seed)
     h = (rng.standard_normal(300) + 1j * rng.standard_normal(300)).astype(np.complex64) / 16
@@ -56,6 +68,11 @@ def main() -> None:
         F = oracle.ref_fftr(t)
         out[f"rfft_{n}"] = F
         out[f"irfft_{n}"] = oracle.ref_fftri(F)
+    # tools/psdpng.c rows (restated loop around the vendored kiss_fftr): mono, stereo, with and without -a
+    for stereo in (False, True):
+        for dc in (False, True):
+            out[f"psdpng_{int(stereo)}{int(dc)}"] = oracle.psdpng_rows(psdpng_input(stereo), 256, 3, dc, stereo,
+                                                                        fftr=oracle.ref_fftr)
     h, x = fastfir_case()
     out["fastfir_noflush"] = oracle.ref_fastfir(h, x, 0, False)     # nfft auto = 1024
     out["fastfir_flush"] = oracle.ref_fastfir(h, x, 0, True)

@@ -99,6 +99,26 @@ def test_restated_fft_vs_mixed_radix_and_real_fixtures(golden):
             assert np.array_equal(oracle.ref_fftr(t).view(np.uint32), golden[f"rfft_{n}"].view(np.uint32))
 
 
+def test_psdpng_rows_restatement_vs_fixture_and_f64(golden):
+    """psdpng.c:120-185 restated around the vendored kiss_fftr == committed fixture; and close to an f64 model."""
+    import tests.golden.make_golden as mg
+    for stereo in (False, True):
+        for dc in (False, True):
+            pcm = mg.psdpng_input(stereo)
+            ref = golden[f"psdpng_{int(stereo)}{int(dc)}"]
+            if oracle.have_ref():
+                assert np.array_equal(oracle.psdpng_rows(pcm, 256, 3, dc, stereo).view(np.uint32), ref.view(np.uint32))
+            x = pcm.astype(np.float64)
+            x = x.reshape(-1, 2).sum(axis=1) if stereo else x
+            fr = x[: 6 * 256].reshape(6, 256)
+            if dc:
+                fr = fr - fr.mean(axis=1, keepdims=True)
+            p = (np.abs(np.fft.rfft(fr, axis=1)) ** 2).reshape(2, 3, 129).mean(axis=1)
+            # after -a the DC bin is rounding noise of the mean removal: compare above a 0 dB floor (the +1 of :173)
+            model = 10 * np.log10(p + 1)
+            assert np.max(np.abs(model - ref)) < 1e-3 * np.sqrt(np.mean(model ** 2))
+
+
 def test_only_golden_vector_of_the_reference_tree(golden):
     """test/fft.py:95-98, tolerance 1e-5 (:104)"""
     F = oracle.fft(golden["fftpy_tvec"].astype(np.complex64))

@@ -326,6 +326,32 @@ def test_fft_host_entry_point(ctx):
     f.close()
 
 
+# ---- tools/psdpng.c spectrogram rows ------------------------------------------------------------------
+@pytest.mark.parametrize("stereo", [False, True])
+@pytest.mark.parametrize("dc", [False, True])
+def test_psdpng_rows_vs_golden_and_oracle(ctx, golden, stereo, dc):
+    from libredio_b200 import blocks
+    import tests.golden.make_golden as mg
+    pcm = mg.psdpng_input(stereo)
+    got = blocks.psdpng_rows(ctx, dev(pcm, ctx), 256, 3, dc, stereo).cpu().numpy()
+    ref = golden[f"psdpng_{int(stereo)}{int(dc)}"]
+    assert got.shape == ref.shape == (2, 129)                  # 7 whole frames -> 2 rows of navg = 3, rest dropped
+    assert_close_rms(got, ref)
+    assert_close_rms(got, oracle.psdpng_rows(pcm, 256, 3, dc, stereo))
+    if dc:                                                     # -a removes the offset: the DC bin collapses
+        assert got[0, 0] < golden[f"psdpng_{int(stereo)}0"][0, 0] - 20.0
+
+
+def test_psdpng_default_shape_and_short_input(ctx):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(12)
+    pcm = (3000 * rng.standard_normal(1024 * 45 + 17)).astype(np.int16)
+    got = blocks.psdpng_rows(ctx, dev(pcm, ctx)).cpu().numpy()      # nfft 1024, navg 20 (psdpng.c:26,29)
+    assert got.shape == (2, 513)
+    assert_close_rms(got, oracle.psdpng_rows(pcm))
+    assert blocks.psdpng_rows(ctx, dev(pcm[:1024 * 19], ctx)).shape[0] == 0   # fewer than navg frames: no row
+
+
 # ---- window + |X|^2 averaging ------------------------------------------------------------------------
 @pytest.mark.parametrize("nfft,k,frames", [(1024, 1, 3), (1024, 64, 256), (1024, 20, 47), (1024, 300, 650),
                                            (256, 8, 64), (64, 5, 100), (4096, 4, 16), (16, 3, 10)])
