@@ -351,6 +351,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e * e2e_steps / float(te.item()) / 1e6
+    # what bounds e2e: a bare pinned-host -> device copy of the same buffer on this box's PCIe link
+    xd = torch.empty(n_e, dtype=torch.complex64, device=dev)
+    xd.copy_(xh, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        xd.copy_(xh, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * n_e * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del xd
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -383,7 +395,9 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "kernel": "chain_kernel<64,10,10,7> (+ psd_reduce)",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e * 8,
-                    "d2h_bytes_per_step": (e2e_frames // K_AVG) * NFFT * 4},
+                    "d2h_bytes_per_step": (e2e_frames // K_AVG) * NFFT * 4,
+                    "bound": "pcie h2d", "h2d_copy_gbs_measured": h2d_gbs,
+                    "frac_of_h2d_copy": (e2e_value / world) * 8e6 / (h2d_gbs * 1e9)},
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
         }

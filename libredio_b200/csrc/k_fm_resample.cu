@@ -14,6 +14,36 @@
 // ---------------------------------------------------------------------------------------------
 // FM discriminator
 // ---------------------------------------------------------------------------------------------
+// atan2 for the discriminator: octant reduction to t = min/max in [0, 1] with one fast division, then
+// atan(t) = t + t^3 P(t^2), P a degree-6 minimax fit (max abs error 1.1e-7 rad in f32 evaluation, i.e.
+// > 120 dB below any usable deviation; the stage's bar is 100 dB SNR vs the f64 definition).  About
+// 20 instructions instead of the ~45 of atan2f: the kernel drops from issue-bound to HBM-bound.
+__device__ __forceinline__ float lr_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;        // atan2(0, 0) = 0 like atan2f / numpy
+    const float u = __fmul_rn(t, t);
+    float r = -0.0043553938157856464f;
+    r = __fmaf_rn(r, u, 0.02304009348154068f);
+    r = __fmaf_rn(r, u, -0.05777352675795555f);
+    r = __fmaf_rn(r, u, 0.0979423001408577f);
+    r = __fmaf_rn(r, u, -0.13976579904556274f);
+    r = __fmaf_rn(r, u, 0.19962704181671143f);
+    r = __fmaf_rn(r, u, -0.3333165943622589f);
+    r = __fmaf_rn(__fmul_rn(r, u), t, t);
+    if (ay > ax) r = __fsub_rn(1.57079632679489661923f, r);
+    if (x < 0.f) r = __fsub_rn(3.14159265358979323846f, r);
+    return copysignf(r, y);
+}
+
+// x[n] * conj(x[n-1]) with the rounding pinned (explicit fma/mul): the vectorised body and the scalar tail
+// must give the same bits, or the output would depend on how a stream is chunked
+__device__ __forceinline__ float2 fm_mul_conj(float2 a, float2 b)
+{
+    return make_float2(__fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)), __fmaf_rn(a.y, b.x, -__fmul_rn(a.x, b.y)));
+}
+
 // blockIdx.y = channel; each thread turns two consecutive samples (one 128-bit load) into two phases
 __global__ void __launch_bounds__(256)
 fmdemod_kernel(const float2 *__restrict__ in, size_t n, size_t in_stride, const float2 *__restrict__ state,
@@ -23,19 +53,46 @@ fmdemod_kernel(const float2 *__restrict__ in, size_t n, size_t in_stride, const 
     const float2 *x = in + c * in_stride;
     float *y = out + c * out_stride;
     const float2 first_prev = state ? state[c] : make_float2(0.f, 0.f);
-    const size_t n_pairs = vec_ok ? n / 2 : 0;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = ldg_stream_f4(reinterpret_cast<const float4 *>(x) + p);
-        const float2 prev = p ? x[2 * p - 1] : first_prev;      // neighbour's sample: same cache line, L1/L2 hit
-        const float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
-        const float2 z0 = cmul_conjb(a, prev), z1 = cmul_conjb(b, a);
-        *reinterpret_cast<float2 *>(y + 2 * p) = make_float2(atan2f(z0.y, z0.x), atan2f(z1.y, z1.x));
+    // main loop: a thread owns 4 consecutive samples (two 128-bit loads, one 128-bit store); the sample before
+    // its first comes from the left neighbour's registers by shuffle, only lane 0 re-reads it (an L1/L2 hit).
+    // Two quads per thread are in flight per iteration so that enough bytes are outstanding per SM.
+    const size_t n_quads = vec_ok ? n / 4 : 0;
+    const size_t n_pairs = n_quads * 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t q0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;; q0 += 2 * stride) {
+        // whole warps stay in the loop together (shuffles); out-of-range quads are masked
+        const size_t qa = q0, qb = q0 + stride;
+        const bool oka = qa < n_quads, okb = qb < n_quads;
+        if (__all_sync(0xffffffffu, !oka && !okb)) break;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (oka) { a0 = ldg_stream_f4(x4 + 2 * qa); a1 = ldg_stream_f4(x4 + 2 * qa + 1); }
+        if (okb) { b0 = ldg_stream_f4(x4 + 2 * qb); b1 = ldg_stream_f4(x4 + 2 * qb + 1); }
+        float2 pa = make_float2(__shfl_up_sync(0xffffffffu, a1.z, 1), __shfl_up_sync(0xffffffffu, a1.w, 1));
+        float2 pb = make_float2(__shfl_up_sync(0xffffffffu, b1.z, 1), __shfl_up_sync(0xffffffffu, b1.w, 1));
+        if (lane == 0) {
+            if (oka) pa = qa ? x[4 * qa - 1] : first_prev;
+            if (okb) pb = qb ? x[4 * qb - 1] : first_prev;
+        }
+        if (oka) {
+            const float2 s0 = make_float2(a0.x, a0.y), s1 = make_float2(a0.z, a0.w), s2 = make_float2(a1.x, a1.y), s3 = make_float2(a1.z, a1.w);
+            const float2 z0 = fm_mul_conj(s0, pa), z1 = fm_mul_conj(s1, s0), z2 = fm_mul_conj(s2, s1), z3 = fm_mul_conj(s3, s2);
+            stg_stream_f4(reinterpret_cast<float4 *>(y) + qa, make_float4(lr_atan2(z0.y, z0.x), lr_atan2(z1.y, z1.x),
+                                                                          lr_atan2(z2.y, z2.x), lr_atan2(z3.y, z3.x)));
+        }
+        if (okb) {
+            const float2 s0 = make_float2(b0.x, b0.y), s1 = make_float2(b0.z, b0.w), s2 = make_float2(b1.x, b1.y), s3 = make_float2(b1.z, b1.w);
+            const float2 z0 = fm_mul_conj(s0, pb), z1 = fm_mul_conj(s1, s0), z2 = fm_mul_conj(s2, s1), z3 = fm_mul_conj(s3, s2);
+            stg_stream_f4(reinterpret_cast<float4 *>(y) + qb, make_float4(lr_atan2(z0.y, z0.x), lr_atan2(z1.y, z1.x),
+                                                                          lr_atan2(z2.y, z2.x), lr_atan2(z3.y, z3.x)));
+        }
     }
     // odd tail, or the whole row when it is not 16-byte aligned
     for (size_t k = 2 * n_pairs + (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
         const float2 prev = k ? x[k - 1] : first_prev;
-        const float2 z = cmul_conjb(x[k], prev);
-        y[k] = atan2f(z.y, z.x);
+        const float2 z = fm_mul_conj(x[k], prev);
+        y[k] = lr_atan2(z.y, z.x);
     }
 }
 
@@ -56,12 +113,12 @@ extern "C" int lrc_fmdemod_run(lrc_ctx *ctx, const float *d_in, size_t n_ch, siz
     LRC_REQUIRE(((uintptr_t)d_in & 7) == 0, LRC_ERR_INVALID, "lrc_fmdemod_run: input must be 8-byte aligned");
     cudaStream_t s = lrc_stream(ctx, stream);
     LRC_REQUIRE(n_ch <= 65535, LRC_ERR_UNSUPPORTED, "lrc_fmdemod_run: more than 65535 channels per call");
-    size_t bx = ceil_div(ceil_div(n, 2), 256);
+    size_t bx = ceil_div(ceil_div(n, 8), 256);
     const size_t cap = ceil_div((size_t)ctx->n_sm * 16, n_ch);
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    // 128-bit loads / 64-bit stores need every row start aligned
-    const int vec_ok = (((uintptr_t)d_in & 15) == 0) && (in_stride % 2 == 0) && (((uintptr_t)d_out & 7) == 0) && (out_stride % 2 == 0);
+    // 128-bit loads and stores need every row start aligned
+    const int vec_ok = (((uintptr_t)d_in & 15) == 0) && (in_stride % 2 == 0) && (((uintptr_t)d_out & 15) == 0) && (out_stride % 4 == 0);
     fmdemod_kernel<<<dim3((unsigned)bx, (unsigned)n_ch), 256, 0, s>>>((const float2 *)d_in, n, in_stride,
                                                                     (const float2 *)d_state, d_out, out_stride, vec_ok);
     LRC_CUDA(cudaGetLastError());

@@ -22,6 +22,7 @@
 //                          matcher A and B -> shaper_optional -> packed packets
 #include "common.cuh"
 #include "unpack.cuh"
+#include <algorithm>
 #include <vector>
 
 static const int OOK_BLOCK = 512;            // bitfount.rs:38
@@ -38,18 +39,23 @@ __device__ __forceinline__ float lr_envelope(uint32_t b0, uint32_t b1)
 }
 
 // The envelope depends on the two bytes only and is symmetric in them (the f64 add commutes), so the hot
-// kernels read it from a triangular table of 256*257/2 = 32896 floats (131.6 KB) held in shared memory.
+// kernels read it from a triangular table (32896 entries, rows padded: 139.7 KB) held in shared memory.
 // The table is filled ON THE DEVICE by lr_envelope above when the plan is created; the u8 domain being
 // finite, table == formula for all 65536 pairs is a proof of equivalence, checked exhaustively by
 // tests/test_gpu_ook_fastfir.py::test_envelope_exhaustive_65536_pairs_bit_exact (formula vs CPU) and by the
 // bit-exact block sums of every OOK test (table vs CPU).
-constexpr int OOK_LUT_N = 256 * 257 / 2;
+// Row hi of the triangle starts at hi (hi + 17) / 2 = tri(hi) + 8 hi: eight unused words per row, so that
+// consecutive rows start ~8 banks apart.  (With the plain tri(hi) the rows next to hi = 127 -- where a noise
+// floor lives -- start 0 or 1 bank apart and a warp's 32 lookups pile onto a handful of banks.)
+constexpr int OOK_LUT_N = 255 * (255 + 17) / 2 + 256;         // 34936 floats
 constexpr int OOK_LUT_BYTES = OOK_LUT_N * 4;
+static_assert(OOK_LUT_N % 4 == 0, "table is copied as float4");
+
+__device__ __forceinline__ uint32_t lut_index(uint32_t hi, uint32_t lo) { return ((hi * (hi + 17u)) >> 1) + lo; }
 
 __device__ __forceinline__ float lut_envelope(const float *lut, uint32_t b0, uint32_t b1)
 {
-    const uint32_t hi = max(b0, b1), lo = min(b0, b1);
-    return lut[((hi * (hi + 1u)) >> 1) + lo];
+    return lut[lut_index(max(b0, b1), min(b0, b1))];
 }
 
 __device__ __forceinline__ void lut_load(float *s_lut, const float *__restrict__ g_lut)
@@ -64,7 +70,7 @@ __global__ void ook_build_lut_kernel(float *__restrict__ lut)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 65536u) return;
     const uint32_t hi = i >> 8, lo = i & 0xffu;
-    if (lo <= hi) lut[((hi * (hi + 1u)) >> 1) + lo] = lr_envelope(hi, lo);
+    if (lo <= hi) lut[lut_index(hi, lo)] = lr_envelope(hi, lo);
 }
 
 struct lrc_ook {
@@ -83,20 +89,26 @@ struct lrc_ook {
     uint32_t *d_npackets;             // [n_streams][2]
     uint32_t *d_runs_dbg;             // [n_streams][max_runs] (value << 31 | length), filled by K-D
     float    *d_lut;                  // triangular envelope table, OOK_LUT_N floats
+    uint16_t *d_rank;                 // [65536] rank of the pair's envelope among the distinct envelope values
+    float    *d_uniq;                 // [n_uniq] the distinct envelope values, ascending
+    uint32_t  n_uniq;
 };
 
 // ---------------------------------------------------------------------------------------------
 // K-A: envelope, sequential block sum, block max.  One warp handles 32 consecutive blocks of one
-// stream: 32-sample slabs are loaded coalesced (4 lanes x 16 B per block row), turned into envelopes
-// by the loading lane, parked in a padded shared tile, and lane b then adds row b in sample order.
+// stream and lane b owns block b: its 512 envelopes must be added one after the other (bitfount.rs:48),
+// so the lane walks its own 1024 bytes.  The bytes reach it through shared memory: the warp copies
+// 64-byte slabs of its 32 block rows with cp.async (16 bytes per lane, 4 lanes per row: coalesced, no
+// registers, the next slab in flight while this one is summed) into rows of pitch 80 bytes, which lane b
+// then reads back with LDS.128 -- 5 x 16 bytes between lanes, so the eight lanes of a quarter-warp phase
+// hit eight different bank groups.  No envelope is ever written back to shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int KA_WARPS = 16;
-constexpr int KA_SLAB = 32;                  // samples per block row per slab
-constexpr int KA_LPR = KA_SLAB * 2 / 16;     // lanes (16-byte loads) per block row
-constexpr int KA_RPI = 32 / KA_LPR;          // block rows per load iteration
-constexpr int KA_LD = KA_SLAB + 1;           // padded row length (floats)
-
-constexpr int KA_SMEM_BYTES = OOK_LUT_BYTES + KA_WARPS * 32 * KA_LD * 4;
+constexpr int KA_SLAB = 32;                          // samples per block row per slab (64 bytes)
+constexpr int KA_PITCH = KA_SLAB * 2 + 16;           // bytes between block rows in the staging tile
+constexpr int KA_STAGE_BYTES = 32 * KA_PITCH;
+constexpr int KA_STAGES = 2;
+constexpr int KA_SMEM_BYTES = OOK_LUT_BYTES + KA_WARPS * KA_STAGES * KA_STAGE_BYTES;
 
 __global__ void __launch_bounds__(KA_WARPS * 32, 1)
 ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
@@ -106,57 +118,55 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
     float *lut = ka_smem;
     lut_load(lut, g_lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *env = ka_smem + OOK_LUT_N + warp * (32 * KA_LD);
+    uint8_t *stg = reinterpret_cast<uint8_t *>(ka_smem + OOK_LUT_N) + warp * (KA_STAGES * KA_STAGE_BYTES);
+    const uint32_t stg_s = smem_u32(stg);
     const size_t groups_per_stream = (n_blocks + 31) / 32;
     const size_t n_groups = groups_per_stream * n_streams;
     const size_t warps_total = (size_t)gridDim.x * KA_WARPS;
+    constexpr int N_SLABS = OOK_BLOCK / KA_SLAB;
     for (size_t grp = (size_t)blockIdx.x * KA_WARPS + warp; grp < n_groups; grp += warps_total) {
         const size_t st = grp / groups_per_stream, b0 = (grp % groups_per_stream) * 32;
         const int nb = (int)((n_blocks - b0) < 32 ? (n_blocks - b0) : 32);
         const uint8_t *base = iq + st * stream_stride + b0 * (size_t)(OOK_BLOCK * 2);
-        float s = 0.0f, mx = 0.0f;
-        // slab loads are software-pipelined: slab i+1 is in flight while slab i is converted and summed
-        constexpr int NIT = 32 / KA_RPI;
-        uint4 nxt[NIT];
-        auto load_slab = [&](int slab) {
+        auto issue = [&](int slab) {
+            const uint32_t dst0 = stg_s + (slab & 1) * KA_STAGE_BYTES;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int row = it * KA_RPI + lane / KA_LPR, col = lane % KA_LPR;
-                nxt[it] = row < nb ? ldg_stream_u4(reinterpret_cast<const uint4 *>(
-                                         base + (size_t)row * (OOK_BLOCK * 2) + slab * (KA_SLAB * 2) + col * 16))
-                                   : make_uint4(0u, 0u, 0u, 0u);
+            for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + (lane >> 2), col = lane & 3;
+                if (row < nb)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                 :: "r"(dst0 + row * KA_PITCH + col * 16),
+                                    "l"(base + (size_t)row * (OOK_BLOCK * 2) + slab * (KA_SLAB * 2) + col * 16) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        load_slab(0);
-        for (int slab = 0; slab < OOK_BLOCK / KA_SLAB; ++slab) {
-            uint4 cur[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) cur[it] = nxt[it];
-            if (slab + 1 < OOK_BLOCK / KA_SLAB) load_slab(slab + 1);
-            // 32 rows x 64 B: 4 iterations of (8 rows x 4 lanes x 16 B); the padded tile makes both the
-            // envelope stores here and the row-wise reads below bank-conflict free
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int row = it * KA_RPI + lane / KA_LPR, col = lane % KA_LPR;
-                const uint32_t w[4] = {cur[it].x, cur[it].y, cur[it].z, cur[it].w};
-                float *dst = env + row * KA_LD + col * 8;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    dst[2 * k]     = lut_envelope(lut, w[k] & 0xffu, (w[k] >> 8) & 0xffu);
-                    dst[2 * k + 1] = lut_envelope(lut, (w[k] >> 16) & 0xffu, w[k] >> 24);
-                }
+        float s = 0.0f, mx = 0.0f;
+        issue(0);
+        for (int slab = 0; slab < N_SLABS; ++slab) {
+            if (slab + 1 < N_SLABS) {
+                issue(slab + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
-            __syncwarp();
+            __syncwarp();                                   // every lane's copies of this slab have landed
             if (lane < nb) {
-                const float *r = env + lane * KA_LD;
+                const uint4 *r = reinterpret_cast<const uint4 *>(stg + (slab & 1) * KA_STAGE_BYTES + lane * KA_PITCH);
 #pragma unroll
-                for (int j = 0; j < KA_SLAB; ++j) {
-                    const float e = r[j];
-                    s = __fadd_rn(s, e);                 // samples.iter().sum(): left to right from 0.0
-                    mx = fmaxf(mx, e);
+                for (int q = 0; q < KA_SLAB * 2 / 16; ++q) {
+                    const uint4 v = r[q];
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float e0 = lut_envelope(lut, w[k] & 0xffu, (w[k] >> 8) & 0xffu);
+                        const float e1 = lut_envelope(lut, (w[k] >> 16) & 0xffu, w[k] >> 24);
+                        s = __fadd_rn(s, e0);                // samples.iter().sum(): left to right from 0.0
+                        s = __fadd_rn(s, e1);
+                        mx = fmaxf(mx, fmaxf(e0, e1));
+                    }
                 }
             }
-            __syncwarp();
+            __syncwarp();                                   // the stage is rewritten two slabs from now
         }
         if (lane < nb) {
             d_sum[st * n_blocks + b0 + lane] = s;
@@ -168,14 +178,26 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
 // ---------------------------------------------------------------------------------------------
 // K-B: trigger state machine, one thread per stream (bitfount.rs:41-81, statement by statement)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int KB_THREADS = 64;                // streams per CTA (static shared memory stays under 48 KB)
+constexpr int KB_TILE = 32;                   // blocks per staged tile
+constexpr int KB_LD = KB_TILE + 1;
+
+__global__ void __launch_bounds__(KB_THREADS)
 ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_max, size_t n_streams,
                    size_t n_blocks, size_t max_bursts, int32_t *__restrict__ d_tag, float *__restrict__ d_half,
                    uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
 {
-    const size_t st = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (st >= n_streams) return;
-    const float *sum = d_sum + st * n_blocks, *bmax = d_max + st * n_blocks;
+    // The state machine is sequential per stream (one thread each); its inputs are not: the CTA stages
+    // tiles of [128 streams][32 blocks] sums and maxima through shared memory with coalesced row reads
+    // (a warp reads 32 consecutive floats of one stream), double-buffered so the next tile is in flight
+    // while this one is walked, and the tags leave the same way.
+    __shared__ float s_sum[2][KB_THREADS * KB_LD];
+    __shared__ float s_max[2][KB_THREADS * KB_LD];
+    __shared__ int32_t s_tag[KB_THREADS * KB_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t st0 = (size_t)blockIdx.x * KB_THREADS;
+    const size_t st = st0 + tid;
+    const bool live = st < n_streams;
     int32_t *tag = d_tag + st * n_blocks;
     float *half = d_half + st * max_bursts;
     uint8_t *flags = d_bflags + st * max_bursts;
@@ -187,62 +209,85 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     uint32_t burst = 0;                       // index of the burst being collected
     size_t burst_first_block = 0;
     bool burst_has_blocks = false;
-    // blocks are walked four at a time; the next four sums/maxima are already in flight (the state machine
-    // itself is sequential, the loads are not)
-    const bool vec = (n_blocks % 4 == 0);
-    auto load4 = [&](size_t b, float *s4, float *m4) {
-        if (vec && b + 4 <= n_blocks) {
-            const float4 a = *reinterpret_cast<const float4 *>(sum + b), c = *reinterpret_cast<const float4 *>(bmax + b);
-            s4[0] = a.x; s4[1] = a.y; s4[2] = a.z; s4[3] = a.w;
-            m4[0] = c.x; m4[1] = c.y; m4[2] = c.z; m4[3] = c.w;
-        } else {
-            for (int u = 0; u < 4; ++u) {
-                s4[u] = (b + u < n_blocks) ? sum[b + u] : 0.0f;
-                m4[u] = (b + u < n_blocks) ? bmax[b + u] : 0.0f;
+    const size_t n_tiles = (n_blocks + KB_TILE - 1) / KB_TILE;
+    // cp.async (LDGSTS) writes the staged tile straight into shared memory: the loads of tile t+1 are in
+    // flight while the state machine walks tile t, and nothing waits on a register
+    auto stage = [&](size_t tile, int buf) {
+        const size_t b = tile * KB_TILE + lane;
+#pragma unroll 4
+        for (int r = warp; r < KB_THREADS; r += KB_THREADS / 32) {
+            const size_t s = st0 + r;
+            float *ds = &s_sum[buf][r * KB_LD + lane], *dm = &s_max[buf][r * KB_LD + lane];
+            if (s < n_streams && b < n_blocks) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(ds)), "l"(d_sum + s * n_blocks + b) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dm)), "l"(d_max + s * n_blocks + b) : "memory");
+            } else {
+                *ds = 0.0f; *dm = 0.0f;
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    float ns[4], nm[4];
-    load4(0, ns, nm);
-    for (size_t b4 = 0; b4 < n_blocks; b4 += 4) {
-        float cs[4], cm[4];
-        for (int u = 0; u < 4; ++u) { cs[u] = ns[u]; cm[u] = nm[u]; }
-        if (b4 + 4 < n_blocks) load4(b4 + 4, ns, nm);
-        for (int u = 0; u < 4 && b4 + u < n_blocks; ++u) {
-            const size_t b = b4 + u;
-            trigger -= 1;                                                       // :46
-            const float s = cs[u];                                             // :48
-            if (buf_len > 1000ull * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
-                if (burst_has_blocks)
-                    for (size_t k = burst_first_block; k < b; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
-                buf_len = 1; lead0 = true; cur_max = 0.0f; burst_has_blocks = false;
-            }
-            if (threshold == 0.0f) threshold = s;                               // :57-59
-            if (trigger < 0) {                                                  // :62-65
-                threshold = __fadd_rn(threshold, __fdiv_rn(s, 1000.0f));
-                threshold = __fsub_rn(threshold, __fmul_rn(threshold, 0.002f));
-            }
-            if (s > __fmul_rn(threshold, 4.0f)) trigger = OOK_TRIGGER_DURATION; // :68-70
-            int32_t tg = -1;
-            if (trigger > 1) {                                                  // :73-75 push_all
-                if (burst < max_bursts) {
-                    tg = (int32_t)burst;
-                    if (!burst_has_blocks) { burst_first_block = b; burst_has_blocks = true; }
+    stage(0, 0);
+    for (size_t tile = 0; tile < n_tiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                                   // tile `tile` is in shared memory for every thread
+        if (tile + 1 < n_tiles) stage(tile + 1, buf ^ 1);  // buffer buf^1 was last read two barriers ago
+        const size_t b0 = tile * KB_TILE;
+        const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
+        if (live) {
+            for (int u = 0; u < nb; ++u) {
+                const size_t b = b0 + u;
+                trigger -= 1;                                                       // :46
+                const float s = s_sum[buf][tid * KB_LD + u];                       // :48
+                const float s_over_1000 = __fdiv_rn(s, 1000.0f);                    // off the threshold's dependency chain
+                if (buf_len > 1000ull * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
+                    if (burst_has_blocks) {
+                        // blocks of this burst tagged in earlier tiles are already in global memory
+                        for (size_t k = burst_first_block; k < b0; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
+                        for (int k = 0; k < u; ++k) if (s_tag[tid * KB_LD + k] == (int32_t)burst) s_tag[tid * KB_LD + k] = -1;
+                    }
+                    buf_len = 1; lead0 = true; cur_max = 0.0f; burst_has_blocks = false;
                 }
-                buf_len += OOK_BLOCK;
-                cur_max = fmaxf(cur_max, cm[u]);
-            }
-            tag[b] = tg;
-            if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
-                if (burst < max_bursts) {
-                    half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
-                    flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                if (threshold == 0.0f) threshold = s;                               // :57-59
+                if (trigger < 0) {                                                  // :62-65
+                    threshold = __fadd_rn(threshold, s_over_1000);
+                    threshold = __fsub_rn(threshold, __fmul_rn(threshold, 0.002f));
                 }
-                burst += 1;
-                buf_len = 0; lead0 = false; cur_max = 0.0f; burst_has_blocks = false;
+                if (s > __fmul_rn(threshold, 4.0f)) trigger = OOK_TRIGGER_DURATION; // :68-70
+                int32_t tg = -1;
+                if (trigger > 1) {                                                  // :73-75 push_all
+                    if (burst < max_bursts) {
+                        tg = (int32_t)burst;
+                        if (!burst_has_blocks) { burst_first_block = b; burst_has_blocks = true; }
+                    }
+                    buf_len += OOK_BLOCK;
+                    cur_max = fmaxf(cur_max, s_max[buf][tid * KB_LD + u]);
+                }
+                s_tag[tid * KB_LD + u] = tg;
+                if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
+                    if (burst < max_bursts) {
+                        const float h = __fdiv_rn(cur_max, 2.0f);                   // discretize :90-91 max/2f32
+                        half[burst] = h;
+                        flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                    }
+                    burst += 1;
+                    buf_len = 0; lead0 = false; cur_max = 0.0f; burst_has_blocks = false;
+                }
             }
         }
+        __syncthreads();
+        // tags of this tile out, coalesced
+        {
+            const size_t b = b0 + lane;
+            for (int r = warp; r < KB_THREADS; r += KB_THREADS / 32) {
+                const size_t s = st0 + r;
+                if (s < n_streams && b < n_blocks) d_tag[s * n_blocks + b] = s_tag[r * KB_LD + lane];
+            }
+        }
+        __syncthreads();
     }
+    if (!live) return;
     // a burst still open when the capture ends is never sent: un-tag its blocks
     if (burst_has_blocks)
         for (size_t k = burst_first_block; k < n_blocks; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
@@ -253,17 +298,50 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
 // K-C: discretize + rle as bit masks, one warp per stream.  Lane l owns samples [16 l, 16 l + 16) of a
 // collected block (32 contiguous bytes).  The positions (in the flattened bit stream) where the value
 // changes are appended to the stream's transition list in order.
+//
+// The slicer `x > max/2` (bitfount.rs:91) never needs the envelope VALUE here, only its order against the
+// threshold: the plan holds rank[b0 | b1 << 8] = index of the pair's envelope among the 32 k distinct
+// envelope values in ascending order (a 128 KB u16 table indexed by the raw byte pair -- no max/min, no
+// triangular index); a burst's max/2 becomes the rank threshold #{values <= max/2} by a warp-wide 32-ary
+// search of the sorted values when the walk enters the burst; then x > max/2  <=>  rank(x) >= threshold,
+// exactly, for every byte pair.  Neighbouring byte pairs (a noise floor sits within a few codes of 127/127)
+// would all fall into the banks of byte0 >> 1, so the table is stored XOR-swizzled: entry (b0, b1) lives at
+// (b0 ^ ((b1 & 7) << 3)) | b1 << 8, which spreads an 8 x 8 neighbourhood over all 32 banks.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+constexpr int OOK_RANK_BYTES = 65536 * 2;
+__host__ __device__ __forceinline__ uint32_t ook_rank_slot(uint32_t pair) { return pair ^ ((pair >> 5) & 0x38u); }
+
+// #{i : uniq[i] <= h} for ascending uniq[0..n): every lane probes one position per round
+__device__ __forceinline__ uint32_t warp_upper_bound(const float *__restrict__ uniq, uint32_t n, float h, int lane)
+{
+    uint32_t lo = 0, hi = n;          // the answer is in [lo, hi]: uniq[i] <= h for i < lo, uniq[i] > h for i >= hi
+    while (lo < hi) {
+        const uint32_t step = (hi - lo + 31) / 32;
+        const uint32_t p = lo + (lane + 1) * step - 1;
+        const bool le = p < hi ? (__ldg(uniq + p) <= h) : false;
+        const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));
+        const uint32_t nlo = lo + c * step;
+        const uint32_t cap = lo + (c + 1) * step - 1;
+        hi = cap < hi ? cap : hi;
+        lo = nlo;
+    }
+    return lo;
+}
+
+constexpr int KC_THREADS = 1024;             // 32 streams per CTA, one CTA per SM: 4736 warps cover 4096 streams in ONE wave
+
+__global__ void __launch_bounds__(KC_THREADS, 1)
 ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
-               size_t max_bursts, size_t max_runs, const float *__restrict__ g_lut,
+               size_t max_bursts, size_t max_runs, const uint16_t *__restrict__ g_rank,
                const int32_t *__restrict__ d_tag,
-               const float *__restrict__ d_half, const uint8_t *__restrict__ d_bflags,
+               const float *__restrict__ d_half, const float *__restrict__ uniq, uint32_t n_uniq,
+               const uint8_t *__restrict__ d_bflags,
                uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans, uint32_t *__restrict__ d_nbits)
 {
-    extern __shared__ __align__(16) float kc_lut[];
-    lut_load(kc_lut, g_lut);
-    const float *lut = kc_lut;
+    extern __shared__ __align__(16) uint16_t kc_rank[];
+    for (int i = threadIdx.x; i < OOK_RANK_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(kc_rank)[i] = __ldg(reinterpret_cast<const uint4 *>(g_rank) + i);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (st >= n_streams) return;
@@ -276,70 +354,83 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
     uint32_t ntr = 0;            // transitions so far
     uint32_t prev = 0;           // value of the last bit (meaningful once pos > 0)
     int32_t cur_burst = -1;
-    float h = 0.0f;
-    for (size_t b0 = 0; b0 < n_blocks; b0 += 32) {
-        // fetch 32 tags at once; skip quickly over untriggered stretches
-        const size_t bi = b0 + lane;
-        const int32_t tg_l = bi < n_blocks ? tag[bi] : -1;
-        unsigned live = __ballot_sync(0xffffffffu, tg_l >= 0);
-        uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
-        if (live) {                                     // first live block of this group
-            const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + __ffs(live) - 1) * (size_t)(OOK_BLOCK * 2) + lane * 32);
-            n0 = ldg_stream_u4(p); n1 = ldg_stream_u4(p + 1);
-        }
-        while (live) {
-            const int k = __ffs(live) - 1;
-            live &= live - 1;
-            const int32_t tg = __shfl_sync(0xffffffffu, tg_l, k);
-            const size_t b = b0 + k;
-            const uint4 q0 = n0, q1 = n1;
-            if (live) {                                 // the next live block is already on its way
-                const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + __ffs(live) - 1) * (size_t)(OOK_BLOCK * 2) + lane * 32);
-                n0 = ldg_stream_u4(p); n1 = ldg_stream_u4(p + 1);
+    uint32_t h = 0;              // rank threshold of the current burst
+    // one collected block: 16 samples per lane -> bit mask -> transitions appended in order
+    auto process = [&](int32_t tg, const uint4 &q0, const uint4 &q1) {
+        if (tg != cur_burst) {
+            cur_burst = tg;
+            h = warp_upper_bound(uniq, n_uniq, half[tg], lane);
+            if (flags[tg] & 2u) {
+                // the burst starts with the literal 0.0 of vec!(0.0): 0.0 > max/2 is false -> bit 0
+                if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }
+                prev = 0u; pos += 1;
             }
-            if (tg != cur_burst) {
-                cur_burst = tg;
-                h = half[tg];
-                if (flags[tg] & 2u) {
-                    // the burst starts with the literal 0.0 of vec!(0.0): 0.0 > max/2 is false -> bit 0
-                    if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }
-                    prev = 0u; pos += 1;
+        }
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t r0 = kc_rank[ook_rank_slot(w[i] & 0xffffu)], r1 = kc_rank[ook_rank_slot(w[i] >> 16)];
+            m |= (r0 >= h ? 1u : 0u) << (2 * i);                             // (x > max/2f32) as usize  :91
+            m |= (r1 >= h ? 1u : 0u) << (2 * i + 1);
+        }
+        // previous bit of this lane's first sample
+        uint32_t pb = __shfl_up_sync(0xffffffffu, m >> 15, 1) & 1u;
+        const bool has_prev = (lane > 0) || (pos > 0);
+        if (lane == 0) pb = prev;
+        uint32_t tm = (m ^ ((m << 1) | pb)) & 0xffffu;                       // bit i set: sample i differs from i-1
+        if (!has_prev) tm &= ~1u;                                            // very first bit of the stream
+        const uint32_t cnt = __popc(tm);
+        uint32_t off = cnt;                                                  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
+            if (lane >= d) off += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
+        uint32_t o = ntr + off - cnt;
+        while (tm) {
+            const int i = __ffs(tm) - 1;
+            tm &= tm - 1;
+            if (o < max_runs) trans[o] = pos + lane * 16 + i;
+            ++o;
+        }
+        ntr += total;
+        prev = __shfl_sync(0xffffffffu, m >> 15, 31) & 1u;
+        pos += OOK_BLOCK;
+    };
+    // collected blocks are fetched PF at a time, one batch ahead of the one being sliced: a warp keeps
+    // 2 x PF KB in flight instead of one block (the walk along a stream is sequential)
+    constexpr int PF = 2;
+    int32_t tg_next = lane < (int)n_blocks ? tag[lane] : -1;
+    for (size_t b0 = 0; b0 < n_blocks; b0 += 32) {
+        const int32_t tg_l = tg_next;
+        {
+            const size_t bn = b0 + 32 + lane;                                 // the next group's tags are on their way
+            tg_next = bn < n_blocks ? tag[bn] : -1;
+        }
+        unsigned rem = __ballot_sync(0xffffffffu, tg_l >= 0);
+        int kA[PF], kB[PF];
+        uint4 dA[PF][2], dB[PF][2];
+        auto take = [&](int (&ks)[PF], uint4 (&d)[PF][2]) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                ks[i] = rem ? __ffs(rem) - 1 : -1;
+                if (rem) rem &= rem - 1;
+                if (ks[i] >= 0) {
+                    const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + ks[i]) * (size_t)(OOK_BLOCK * 2) + lane * 32);
+                    d[i][0] = ldg_stream_u4(p); d[i][1] = ldg_stream_u4(p + 1);
                 }
             }
-            (void)b;
-            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t m = 0;
+        };
+        take(kA, dA);
+        while (kA[0] >= 0) {
+            take(kB, dB);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float e0 = lut_envelope(lut, w[i] & 0xffu, (w[i] >> 8) & 0xffu);
-                const float e1 = lut_envelope(lut, (w[i] >> 16) & 0xffu, w[i] >> 24);
-                m |= (e0 > h ? 1u : 0u) << (2 * i);                          // (x > max/2f32) as usize  :91
-                m |= (e1 > h ? 1u : 0u) << (2 * i + 1);
-            }
-            // previous bit of this lane's first sample
-            uint32_t pb = __shfl_up_sync(0xffffffffu, m >> 15, 1) & 1u;
-            const bool has_prev = (lane > 0) || (pos > 0);
-            if (lane == 0) pb = prev;
-            uint32_t tm = (m ^ ((m << 1) | pb)) & 0xffffu;                   // bit i set: sample i differs from i-1
-            if (!has_prev) tm &= ~1u;                                        // very first bit of the stream
-            const uint32_t cnt = __popc(tm);
-            uint32_t off = cnt;                                              // inclusive warp scan
+            for (int i = 0; i < PF; ++i)
+                if (kA[i] >= 0) process(__shfl_sync(0xffffffffu, tg_l, kA[i]), dA[i][0], dA[i][1]);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
-                if (lane >= d) off += v;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
-            uint32_t o = ntr + off - cnt;
-            while (tm) {
-                const int i = __ffs(tm) - 1;
-                tm &= tm - 1;
-                if (o < max_runs) trans[o] = pos + lane * 16 + i;
-                ++o;
-            }
-            ntr += total;
-            prev = __shfl_sync(0xffffffffu, m >> 15, 31) & 1u;
-            pos += OOK_BLOCK;
+            for (int i = 0; i < PF; ++i) { kA[i] = kB[i]; dA[i][0] = dB[i][0]; dA[i][1] = dB[i][1]; }
         }
     }
     if (lane == 0) { d_ntrans[st] = ntr; d_nbits[st] = pos; }
@@ -365,45 +456,69 @@ struct Shaper {
     }
 };
 
-__global__ void __launch_bounds__(128)
+// one run at a time through the pulse-pair matchers of ratpak.rs:88-97 (looper bodies) and shaper_optional
+struct Matcher {
+    int proto; bool pending; float d; Shaper sh;
+    __device__ void feed(uint32_t v, float dur)
+    {
+        if (!pending) {
+            bool first;
+            if (proto == 0) first = (v == 1u) && in_rng(dur, 2e-4f, 6e-4f);                                         // ratpak.rs:91
+            else first = (v == 1u) && (in_rng(dur, 125e-6f, 250e-6f) || in_rng(dur, 500e-6f, 650e-6f));            // :96
+            if (!first) sh.feed(-1);
+            else { pending = true; d = dur; }
+            return;
+        }
+        pending = false;                                    // a.next().unwrap(): the following run is consumed
+        const float e = dur;
+        if (proto == 0) {
+            if (v == 0u && in_rng(e, 1.5e-3f, 2.5e-3f)) sh.feed(0);
+            else if (v == 0u && in_rng(e, 3.5e-3f, 4.5e-3f)) sh.feed(1);
+            else sh.feed(-1);
+        } else {
+            if (v == 0u && (in_rng(e, 500e-6f, 650e-6f) || in_rng(e, 125e-6f, 250e-6f))) sh.feed(d > e ? 1 : 0);
+            else sh.feed(-1);
+        }
+        // a pulse still pending when the runs end: the reference block dies in unwrap() with nothing sent
+    }
+};
+
+// One warp per stream.  Run lengths -> seconds (dle) is data-parallel: the lanes turn a chunk of 256
+// transitions into durations in shared memory with coalesced reads; the matchers are sequential, so lane 0
+// (proto A) and lane 1 (proto B) then walk the chunk from shared memory instead of chasing global loads.
+constexpr int KD_WARPS = 4, KD_CHUNK = 256;
+
+__global__ void __launch_bounds__(KD_WARPS * 32)
 ook_match_kernel(const uint32_t *__restrict__ d_trans, const uint32_t *__restrict__ d_ntrans, size_t n_streams,
                  size_t max_runs, size_t max_packets, float s_rate_f, unsigned long long *__restrict__ d_packets,
                  uint32_t *__restrict__ d_npackets, uint32_t *__restrict__ d_runs_dbg)
 {
-    const size_t st = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_dur[KD_WARPS][KD_CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t st = (size_t)blockIdx.x * KD_WARPS + warp;
     if (st >= n_streams) return;
     const uint32_t *tr = d_trans + st * max_runs;
     uint32_t nr = d_ntrans[st];
     if (nr > max_runs) nr = (uint32_t)max_runs;           // overflow is reported by fetch
     // run k: value = k & 1 (the stream starts with the 0 bit of vec!(0.0)), length = tr[k] - tr[k-1]
     uint32_t *dbg = d_runs_dbg + st * max_runs;
-    for (uint32_t k = 0; k < nr; ++k) dbg[k] = ((k & 1u) << 31) | (tr[k] - (k ? tr[k - 1] : 0u));
-    for (int proto = 0; proto < 2; ++proto) {
-        Shaper sh{0ull, 0u, proto == 0 ? 36u : 24u, 0u, d_packets + (st * 2 + proto) * max_packets, max_packets};
-        uint32_t k = 0;
-        while (k < nr) {
-            const uint32_t v = k & 1u;
-            const float d = __fdiv_rn((float)(tr[k] - (k ? tr[k - 1] : 0u)), s_rate_f);   // dle kpn.rs:35
-            ++k;
-            bool first;
-            if (proto == 0) first = (v == 1u) && in_rng(d, 2e-4f, 6e-4f);                                  // ratpak.rs:91
-            else first = (v == 1u) && (in_rng(d, 125e-6f, 250e-6f) || in_rng(d, 500e-6f, 650e-6f));          // :96
-            if (!first) { sh.feed(-1); continue; }
-            if (k >= nr) break;                                // a.next().unwrap() on a drained port: the block dies
-            const uint32_t v2 = k & 1u;
-            const float e = __fdiv_rn((float)(tr[k] - tr[k - 1]), s_rate_f);
-            ++k;
-            if (proto == 0) {
-                if (v2 == 0u && in_rng(e, 1.5e-3f, 2.5e-3f)) sh.feed(0);
-                else if (v2 == 0u && in_rng(e, 3.5e-3f, 4.5e-3f)) sh.feed(1);
-                else sh.feed(-1);
-            } else {
-                if (v2 == 0u && (in_rng(e, 500e-6f, 650e-6f) || in_rng(e, 125e-6f, 250e-6f))) sh.feed(d > e ? 1 : 0);
-                else sh.feed(-1);
-            }
+    Matcher mt{lane, false, 0.0f,
+               Shaper{0ull, 0u, lane == 0 ? 36u : 24u, 0u, d_packets + (st * 2 + (lane & 1)) * max_packets, max_packets}};
+    float *dur = s_dur[warp];
+    for (uint32_t k0 = 0; k0 < nr; k0 += KD_CHUNK) {
+        const uint32_t nk = nr - k0 < (uint32_t)KD_CHUNK ? nr - k0 : (uint32_t)KD_CHUNK;
+        for (uint32_t i = lane; i < nk; i += 32) {
+            const uint32_t k = k0 + i;
+            const uint32_t len = tr[k] - (k ? tr[k - 1] : 0u);
+            dbg[k] = ((k & 1u) << 31) | len;
+            dur[i] = __fdiv_rn((float)len, s_rate_f);                                   // dle kpn.rs:35
         }
-        d_npackets[st * 2 + proto] = sh.count;
+        __syncwarp();
+        if (lane < 2)
+            for (uint32_t i = 0; i < nk; ++i) mt.feed((k0 + i) & 1u, dur[i]);
+        __syncwarp();
     }
+    if (lane < 2) d_npackets[st * 2 + lane] = mt.sh.count;
 }
 
 __global__ void ook_envelope_table_kernel(float *__restrict__ table)
@@ -438,13 +553,36 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
     OOK_ALLOC(d_runs_dbg, n_streams * o->max_runs);
     OOK_ALLOC(d_lut, (size_t)OOK_LUT_N);
+    OOK_ALLOC(d_rank, (size_t)65536); OOK_ALLOC(d_uniq, (size_t)65536);
 #undef OOK_ALLOC
     if (e == cudaSuccess) {
+        e = cudaMemsetAsync(o->d_lut, 0, OOK_LUT_BYTES, ctx->stream);           // the row padding is never read
         ook_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(o->d_lut);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_LUT_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_RANK_BYTES);
+    }
+    if (e == cudaSuccess) {
+        // rank table for the slicer: the envelope of every byte pair, computed ON THE DEVICE by the routine the
+        // block-sum kernel uses, ordered on the host (a plain sort of 65536 floats, no arithmetic)
+        ook_envelope_table_kernel<<<256, 256, 0, ctx->stream>>>(o->d_uniq);          // d_uniq as scratch: index b0*256 + b1
+        e = cudaGetLastError();
+        std::vector<float> tab(65536);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(tab.data(), o->d_uniq, 65536 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) {
+            std::vector<float> uq(tab);
+            std::sort(uq.begin(), uq.end());
+            uq.erase(std::unique(uq.begin(), uq.end()), uq.end());
+            std::vector<uint16_t> rank(65536);
+            // kernel index = byte0 | byte1 << 8 (memory order); the table is symmetric in the two bytes
+            for (uint32_t i = 0; i < 65536; ++i)
+                rank[ook_rank_slot(i)] = (uint16_t)(std::lower_bound(uq.begin(), uq.end(), tab[i]) - uq.begin());
+            o->n_uniq = (uint32_t)uq.size();
+            e = cudaMemcpy(o->d_uniq, uq.data(), uq.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(o->d_rank, rank.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice);
+        }
     }
     if (e != cudaSuccess) {
         lrc_set_error("lrc_ook_create: %s", cudaGetErrorString(e));
@@ -462,6 +600,7 @@ extern "C" int lrc_ook_destroy(lrc_ook *o)
     cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags);
     cudaFree(o->d_nbursts); cudaFree(o->d_trans); cudaFree(o->d_ntrans); cudaFree(o->d_nbits);
     cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut);
+    cudaFree(o->d_rank); cudaFree(o->d_uniq);
     delete o;
     return LRC_OK;
 }
@@ -482,14 +621,14 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     ook_block_kernel<<<(unsigned)blocks, KA_WARPS * 32, KA_SMEM_BYTES, s>>>(d_iq, stream_stride_bytes, o->n_streams,
                                                                            o->n_blocks, o->d_lut, o->d_sum, o->d_max);
     LRC_CUDA(cudaGetLastError());
-    ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, 128), 128, 0, s>>>(
+    ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_THREADS), KB_THREADS, 0, s>>>(
         o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
     LRC_CUDA(cudaGetLastError());
-    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams * 32, 512), 512, OOK_LUT_BYTES, s>>>(
-        d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_lut, o->d_tag, o->d_half,
-        o->d_bflags, o->d_trans, o->d_ntrans, o->d_nbits);
+    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams * 32, (size_t)KC_THREADS), KC_THREADS, OOK_RANK_BYTES, s>>>(
+        d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
+        o->d_uniq, o->n_uniq, o->d_bflags, o->d_trans, o->d_ntrans, o->d_nbits);
     LRC_CUDA(cudaGetLastError());
-    ook_match_kernel<<<(unsigned)ceil_div(o->n_streams, 128), 128, 0, s>>>(
+    ook_match_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KD_WARPS), KD_WARPS * 32, 0, s>>>(
         o->d_trans, o->d_ntrans, o->n_streams, o->max_runs, o->max_packets, (float)o->sample_rate, o->d_packets,
         o->d_npackets, o->d_runs_dbg);
     LRC_CUDA(cudaGetLastError());

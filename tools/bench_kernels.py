@@ -35,6 +35,23 @@ def timeit(fn, iters=10, warm=3):
     return float(np.median(ts)), float(np.min(ts))
 
 
+
+
+def cpu_rate(fn, samples_per_call, seconds=2.0):
+    """Reference CPU path timed beside the GPU number: `fn` (an oracle/ call; ctypes releases the
+    GIL) on every host core for ~`seconds`; returns {"cpu_Msamples/s", "cpu_cores", "cpu_kind"}."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter(); fn(); per = time.perf_counter() - t0
+    calls = max(1, int(seconds / max(per, 1e-6)))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(lambda _: [fn() for _ in range(calls)], range(cores)))
+    dt = time.perf_counter() - t0
+    return {"cpu_Msamples/s": cores * calls * samples_per_call / dt / 1e6, "cpu_cores": cores}
+
+
 def report(name, samples, alg_bytes, ms, extra=None):
     gbs = alg_bytes / (ms * 1e-3) / 1e9
     line = {"kernel": name, "Msamples/s": samples / (ms * 1e-3) / 1e6, "ms": ms, "GB/s": gbs, "frac_hbm": gbs / PEAK,
@@ -48,7 +65,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--cpu", action="store_true", help="time the reference's CPU path (oracle/) beside each config")
     a = ap.parse_args()
+    if a.cpu:
+        import oracle
     q = 4 if a.quick else 1
     ctx = blocks.Context(0)
     dev = ctx.tdev
@@ -64,7 +84,12 @@ def main():
         def f():
             capi.check(ctx.lib.lrc_unpack_u8_cf32(ctx.h, C.c_void_p(iq.data_ptr()), n, C.c_void_p(out.data_ptr()), blocks._stream()), "unpack")
         ms, _ = timeit(f)
-        report("unpack u8->cf32 (K1)", n // 2, n + n * 4, ms)
+        extra = None
+        if a.cpu:
+            hb = np.random.default_rng(0).integers(0, 256, 1 << 22, dtype=np.uint8)
+            extra = cpu_rate(lambda: oracle.data_to_samples(hb), hb.size // 2)
+            extra["cpu_what"] = "restated rtlsdr::data_to_samples (rtlsdr.rs:159-162), strict f32 C"
+        report("unpack u8->cf32 (K1)", n // 2, n + n * 4, ms, extra)
         del iq, out
 
     if want("fir"):
@@ -73,7 +98,14 @@ def main():
         x = torch.view_as_complex(torch.randn(n_ch, n, 2, device=dev, generator=g))
         fir = blocks.Fir(ctx, taps, 10)
         ms, _ = timeit(lambda: fir.run(x))
-        report("FIR64/10 cf32 (K2 tile)", n_ch * n, n_ch * n * 8.8, ms, {"n_ch": n_ch})
+        extra = {"n_ch": n_ch}
+        if a.cpu:
+            hx = synth.cf32_noise_tones(240_000, seed=1)
+            extra.update(cpu_rate(lambda: oracle.fir_decimate(hx, taps, 10), hx.size))
+            extra["cpu_what"] = "restated dsputils::convolve (dsputils.rs:30-32) on kept outputs only, strict f32 C"
+            full = cpu_rate(lambda: oracle.fir_decimate(hx[:60_000], taps, 10, full=True), 60_000, 1.0)
+            extra["cpu_Msamples/s_faithful_all_outputs"] = full["cpu_Msamples/s"]
+        report("FIR64/10 cf32 (K2 tile)", n_ch * n, n_ch * n * 8.8, ms, extra)
         iq = torch.randint(0, 256, (n_ch, 2 * n), dtype=torch.uint8, device=dev, generator=g)
         ms, _ = timeit(lambda: fir.run_u8(iq))
         report("unpack+FIR64/10 u8 fused (K1+K2)", n_ch * n, n_ch * n * 2.8, ms,
@@ -91,7 +123,13 @@ def main():
         def run():
             capi.check(ctx.lib.lrc_fft_run(f.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), n // 1024, blocks._stream()), "fft")
         ms, _ = timeit(run)
-        report("FFT1024 batched out-of-place (K3)", n, n * 16, ms)
+        extra = None
+        if a.cpu and oracle.have_ref():
+            hx = synth.cf32_noise_tones(1024 * 256, seed=2).reshape(256, 1024)
+            extra = cpu_rate(lambda: oracle.ref_kissfft(hx), hx.size)
+            extra["cpu_what"] = "vendored kiss_fft.c, reference build flags (libkissfft/Makefile:4, no -O)"
+            extra["cpu_Msamples/s_O3"] = cpu_rate(lambda: oracle.ref_kissfft(hx, opt=True), hx.size, 1.0)["cpu_Msamples/s"]
+        report("FFT1024 batched out-of-place (K3)", n, n * 16, ms, extra)
         p = blocks.Psd(ctx, 1024)
         ms, _ = timeit(lambda: p.run(x, 64))
         report("Hann+FFT1024+|X|^2 avg K=64 (config 2, K3 fused)", n, n * 8, ms,
@@ -120,8 +158,12 @@ def main():
         ff = blocks.FastFir(ctx, h, 0)
         out = torch.empty(ff.out_len(n) + 1, dtype=torch.complex64, device=dev)
         ms, _ = timeit(lambda: ff.run(x, out=out), iters=5)
-        report("overlap-save FIR 4096 taps nfft 8192 (config 5, K4)", n, n * 16, ms,
-               {"flop_per_sample": 272, "TFLOP/s": n * 272 / (ms * 1e-3) / 1e12})
+        extra = {"flop_per_sample": 272, "TFLOP/s": n * 272 / (ms * 1e-3) / 1e12}
+        if a.cpu and oracle.have_ref():
+            hx = synth.cf32_noise_tones(1 << 20, seed=5)
+            extra.update(cpu_rate(lambda: oracle.ref_fastfir(h, hx), hx.size))
+            extra["cpu_what"] = "vendored tools/kiss_fastfir.c (-O3, tools/Makefile:43), 2^20-sample buffers"
+        report("overlap-save FIR 4096 taps nfft 8192 (config 5, K4)", n, n * 16, ms, extra)
         del x, out
         ff.close()
 
@@ -132,7 +174,11 @@ def main():
         ook = blocks.Ook(ctx, n_streams, n_blocks, 256000, 4096, 64)
         ms, _ = timeit(lambda: ook.decode(iq), iters=5)
         ns = n_streams * n_blocks * 512
-        report("OOK chain 4 kernels (config 4, K7)", ns, ns * 2, ms, {"packets": len(ook.packets())})
+        extra = {"packets": len(ook.packets())}
+        if a.cpu:
+            extra.update(cpu_rate(lambda: oracle.ook_decode(caps[0]), n_blocks * 512))
+            extra["cpu_what"] = "restated ratpak.rs:60-111 chain (envelope..shaper_optional), strict f32 C, one stream per core"
+        report("OOK chain 4 kernels (config 4, K7)", ns, ns * 2, ms, extra)
         ook.close()
     ctx.close()
 
