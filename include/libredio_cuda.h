@@ -158,6 +158,10 @@ int    lrc_chain_run(lrc_chain *chain, const float *d_in, size_t n_in, size_t k_
  * kernel through a double-buffered device ring, rows copied back; synchronous. */
 int    lrc_chain_run_host(lrc_chain *chain, const float *h_in, size_t n_in, size_t k_avg, float *h_rows,
                           size_t *n_rows);
+/* same with the rtlsdr wire format as host input: n_in samples of interleaved u8 I,Q (2 bytes per sample over
+ * PCIe instead of 8); rtlsdr::data_to_samples (rtlsdr.rs:160-162) runs on the device in front of the chain. */
+int    lrc_chain_run_host_u8(lrc_chain *chain, const uint8_t *h_iq, size_t n_in, size_t k_avg, float *h_rows,
+                             size_t *n_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * long FIR by FFT overlap-save.   Replaces kiss_fastfir_alloc / kiss_fastfir

@@ -272,6 +272,18 @@ class Chain:
         check(self.ctx.lib.lrc_chain_run_host(self.h, _p(x), n, k_avg, _p(out), C.byref(nr)), "lrc_chain_run_host")
         return out
 
+    def run_host_u8(self, iq, k_avg: int, out=None):
+        """iq: pinned CPU uint8 tensor (or numpy array) of interleaved I,Q bytes -- the rtlsdr wire format;
+        2 bytes per sample cross PCIe and data_to_samples runs on the device in front of the chain."""
+        n = (iq.numel() if isinstance(iq, torch.Tensor) else iq.size) // 2
+        rows = self.frames(n) // k_avg
+        if out is None:
+            out = (torch.empty((rows, self.nfft), dtype=torch.float32, pin_memory=True)
+                   if isinstance(iq, torch.Tensor) else np.empty((rows, self.nfft), dtype=np.float32))
+        nr = C.c_size_t()
+        check(self.ctx.lib.lrc_chain_run_host_u8(self.h, _p(iq), n, k_avg, _p(out), C.byref(nr)), "lrc_chain_run_host_u8")
+        return out
+
     def close(self):
         if self.h:
             self.ctx.lib.lrc_chain_destroy(self.h)

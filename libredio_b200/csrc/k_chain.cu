@@ -41,6 +41,7 @@ struct lrc_chain {
     float   *d_tmp; size_t tmp_cap;            // decimated signal (floats)
     // host ring (lrc_chain_run_host)
     float   *d_ring[2]; size_t ring_cap;       // samples per slot
+    uint8_t *d_ring_u8[2]; size_t ring_u8_cap; // samples per slot (u8 IQ staging of lrc_chain_run_host_u8)
     cudaEvent_t ev_ready[2], ev_free[2];
     float   *d_rows; size_t rows_cap;          // floats
 };
@@ -202,6 +203,7 @@ extern "C" int lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, in
     c->d_tw = nullptr; c->d_win = nullptr; c->d_partial = nullptr; c->partial_cap = 0;
     c->fir = nullptr; c->psd = nullptr; c->d_tmp = nullptr; c->tmp_cap = 0;
     c->d_ring[0] = c->d_ring[1] = nullptr; c->ring_cap = 0; c->d_rows = nullptr; c->rows_cap = 0;
+    c->d_ring_u8[0] = c->d_ring_u8[1] = nullptr; c->ring_u8_cap = 0;
     c->ev_ready[0] = c->ev_ready[1] = c->ev_free[0] = c->ev_free[1] = nullptr;
     int rc = lrc_fir_create(ctx, h_taps, ntaps, decim, &c->fir);       // also validates the taps
     if (!rc) rc = lrc_psd_create(ctx, nfft, window, &c->psd);
@@ -229,6 +231,7 @@ extern "C" int lrc_chain_destroy(lrc_chain *c)
     lrc_fir_destroy(c->fir); lrc_psd_destroy(c->psd);
     cudaFree(c->d_tw); cudaFree(c->d_win); cudaFree(c->d_partial); cudaFree(c->d_tmp);
     cudaFree(c->d_ring[0]); cudaFree(c->d_ring[1]); cudaFree(c->d_rows);
+    cudaFree(c->d_ring_u8[0]); cudaFree(c->d_ring_u8[1]);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -303,9 +306,11 @@ extern "C" int lrc_chain_run(lrc_chain *c, const float *d_in, size_t n_in, size_
     return chain_launch(c, d_in, rows, k_avg, d_rows, 1.0f / (float)k_avg, 0, lrc_stream(c->ctx, stream));
 }
 
-extern "C" int lrc_chain_run_host(lrc_chain *c, const float *h_in, size_t n_in, size_t k_avg, float *h_rows,
-                                  size_t *n_rows)
+static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_u8, size_t n_in, size_t k_avg,
+                               float *h_rows, size_t *n_rows)
 {
+    const float *h_in = (const float *)h_in_any;
+    const uint8_t *h_in_u8 = (const uint8_t *)h_in_any;
     LRC_REQUIRE(c != nullptr, LRC_ERR_INVALID, "null plan");
     LRC_BIND(c->ctx);
     LRC_REQUIRE(k_avg >= 1, LRC_ERR_INVALID, "lrc_chain_run_host: k_avg must be >= 1");
@@ -324,6 +329,12 @@ extern "C" int lrc_chain_run_host(lrc_chain *c, const float *h_in, size_t n_in, 
         c->ring_cap = 0;
         for (int i = 0; i < 2; ++i) LRC_CUDA(cudaMalloc(&c->d_ring[i], slot_samples * sizeof(float2)));
         c->ring_cap = slot_samples;
+    }
+    if (input_is_u8 && c->ring_u8_cap < slot_samples) {
+        for (int i = 0; i < 2; ++i) { cudaFree(c->d_ring_u8[i]); c->d_ring_u8[i] = nullptr; }
+        c->ring_u8_cap = 0;
+        for (int i = 0; i < 2; ++i) LRC_CUDA(cudaMalloc(&c->d_ring_u8[i], slot_samples * 2));
+        c->ring_u8_cap = slot_samples;
     }
     if (c->rows_cap < rows * (size_t)c->nfft) {
         cudaFree(c->d_rows); c->d_rows = nullptr; c->rows_cap = 0;
@@ -348,9 +359,16 @@ extern "C" int lrc_chain_run_host(lrc_chain *c, const float *h_in, size_t n_in, 
         const int b = (int)(seg & 1);
         const size_t ns = nfr * adv + tail;
         if (seg >= 2) LRC_CUDA(cudaStreamWaitEvent(cs, c->ev_free[b], 0));
-        LRC_CUDA(cudaMemcpyAsync(c->d_ring[b], h_in + 2 * f * adv, ns * sizeof(float2), cudaMemcpyHostToDevice, cs));
+        if (input_is_u8)      // 2 bytes per sample over PCIe; rtlsdr::data_to_samples runs on the device
+            LRC_CUDA(cudaMemcpyAsync(c->d_ring_u8[b], h_in_u8 + 2 * f * adv, ns * 2, cudaMemcpyHostToDevice, cs));
+        else
+            LRC_CUDA(cudaMemcpyAsync(c->d_ring[b], h_in + 2 * f * adv, ns * sizeof(float2), cudaMemcpyHostToDevice, cs));
         LRC_CUDA(cudaEventRecord(c->ev_ready[b], cs));
         LRC_CUDA(cudaStreamWaitEvent(ks, c->ev_ready[b], 0));
+        if (input_is_u8) {
+            const int urc = lrc_unpack_u8_cf32(c->ctx, c->d_ring_u8[b], ns * 2, c->d_ring[b], ks);
+            if (urc) return urc;
+        }
         int rc;
         if (slice_rows) {
             const size_t row = f / k_avg;
@@ -365,4 +383,16 @@ extern "C" int lrc_chain_run_host(lrc_chain *c, const float *h_in, size_t n_in, 
     LRC_CUDA(cudaMemcpyAsync(h_rows, c->d_rows, rows * (size_t)c->nfft * sizeof(float), cudaMemcpyDeviceToHost, ks));
     LRC_CUDA(cudaStreamSynchronize(ks));
     return LRC_OK;
+}
+
+extern "C" int lrc_chain_run_host(lrc_chain *c, const float *h_in, size_t n_in, size_t k_avg, float *h_rows,
+                                  size_t *n_rows)
+{
+    return chain_run_host_impl(c, h_in, 0, n_in, k_avg, h_rows, n_rows);
+}
+
+extern "C" int lrc_chain_run_host_u8(lrc_chain *c, const uint8_t *h_iq, size_t n_in, size_t k_avg, float *h_rows,
+                                     size_t *n_rows)
+{
+    return chain_run_host_impl(c, h_iq, 1, n_in, k_avg, h_rows, n_rows);
 }

@@ -201,9 +201,9 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     int32_t *tag = d_tag + st * n_blocks;
     float *half = d_half + st * max_bursts;
     uint8_t *flags = d_bflags + st * max_bursts;
-    long long trigger = 0;                    // :41
+    int trigger = 0;                          // :41 (isize there; |trigger| <= n_blocks here)
     float threshold = 0.0f;                   // :44
-    unsigned long long buf_len = 1;           // :43 sample_buffer = vec!(0.0)
+    uint32_t buf_len = 1;                     // :43 sample_buffer = vec!(0.0); capped at 25.6 M + 512 by the guard below
     bool lead0 = true;                        // the buffer currently starts with that 0.0
     float cur_max = 0.0f;
     uint32_t burst = 0;                       // index of the burst being collected
@@ -236,12 +236,17 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
         const size_t b0 = tile * KB_TILE;
         const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
         if (live) {
+            // s / 1000 (:63) for the whole tile first: 32 independent IEEE divisions pipeline, inside the
+            // state machine each would sit on the threshold's dependency chain.  s_tag doubles as the buffer.
+            float *s_q = reinterpret_cast<float *>(s_tag) + tid * KB_LD;
+#pragma unroll 8
+            for (int u = 0; u < KB_TILE; ++u) s_q[u] = __fdiv_rn(s_sum[buf][tid * KB_LD + u], 1000.0f);
             for (int u = 0; u < nb; ++u) {
                 const size_t b = b0 + u;
                 trigger -= 1;                                                       // :46
                 const float s = s_sum[buf][tid * KB_LD + u];                       // :48
-                const float s_over_1000 = __fdiv_rn(s, 1000.0f);                    // off the threshold's dependency chain
-                if (buf_len > 1000ull * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
+                const float s_over_1000 = s_q[u];
+                if (buf_len > 1000u * OOK_TRIGGER_DURATION * OOK_BLOCK) {         // :52-54 OOM guard
                     if (burst_has_blocks) {
                         // blocks of this burst tagged in earlier tiles are already in global memory
                         for (size_t k = burst_first_block; k < b0; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;

@@ -449,3 +449,20 @@ def test_chain_host_ring_matches_device_path(ctx, frames, k):
     # rows that span several ring segments are summed in a different order: float rounding only
     assert (a - b).abs().max().item() <= 1e-5 * a.pow(2).mean().sqrt().item()
     ch.close()
+
+
+def test_chain_host_ring_u8_input_matches_unpack_then_chain(ctx):
+    """lrc_chain_run_host_u8: rtlsdr bytes in host memory -> (device) data_to_samples -> chain; equals the cf32
+    host path fed with the oracle's unpack of the same bytes, bit for bit (the unpack is bit-exact)."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    frames, k = 300, 20
+    iq = synth.iq_tone_noise_u8(frames * 10240 + 54, seed=21)
+    ch = blocks.Chain(ctx, taps, 10, 1024, capi.WINDOW_HANN)
+    got = ch.run_host_u8(iq, k)
+    ref = ch.run_host(oracle.data_to_samples(iq), k)
+    assert got.shape == ref.shape == (frames // k, 1024)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    pref = D.psd_rows(oracle.fir_decimate(oracle.data_to_samples(iq), taps, 10), 1024, k, D.hann_periodic(1024))
+    assert_close_rms(got, pref)
+    ch.close()
