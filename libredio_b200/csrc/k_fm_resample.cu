@@ -144,8 +144,8 @@ struct lrc_resampler {
     size_t   n_ch, max_chunk, tpp, ntaps, cap;   // cap: floats per staging row
     std::vector<double> h;                       // prototype (f64)
     float   *d_hp;                               // [L][tpp] polyphase rows, f32
-    float   *d_buf;                              // [n_ch][cap]: tpp-1 history + chunk
-    float   *d_carry;                            // [n_ch][tpp]
+    float   *d_carry[2];                         // [n_ch][tpp] x2: the tpp-1 samples before the next chunk (ping-pong)
+    int      cur;                                // which carry buffer is current
     float   *d_hin, *d_hout; size_t hin_cap, hout_cap;   // staging for the host entry point (floats)
     unsigned long long n_total, m_next;          // inputs consumed / next output index (same for all channels)
 };
@@ -185,9 +185,21 @@ static bool rational(double x, int max_den, int *num, int *den)
     return true;
 }
 
+// The stream a kernel sees is the virtual row [carry (tpp-1 samples of history) | chunk]: no staging copy of
+// the chunk is ever made, the first window of a channel simply starts inside the carry buffer.
+struct RsRow {
+    const float *carry; size_t hist;          // carry + c*tpp, tpp - 1
+    const float *in; size_t n_in;             // in + c*in_stride
+    __device__ __forceinline__ float at(size_t v) const
+    {
+        return v < hist ? carry[v] : (v - hist < n_in ? __ldg(in + (v - hist)) : 0.f);
+    }
+};
+
 template <int UNROLL>
 __global__ void __launch_bounds__(256)
-resample_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, const float *__restrict__ hp, int L, int M,
+resample_kernel(const float *__restrict__ carry, const float *__restrict__ in, size_t n_in, size_t in_stride,
+                size_t n_ch, const float *__restrict__ hp, int L, int M,
                 int tpp, unsigned long long n_total, unsigned long long m_next, size_t n_out,
                 float *__restrict__ out, size_t out_stride)
 {
@@ -197,22 +209,46 @@ resample_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, const fl
         const unsigned long long t = (m_next + k) * (unsigned long long)M;
         const unsigned long long base = t / (unsigned long long)L;
         const int phase = (int)(t % (unsigned long long)L);
-        // buffer index of x[base]: the row starts at global input index n_total - (tpp - 1)
-        const float *x = buf + c * cap + (size_t)(base - n_total) + (size_t)(tpp - 1);
+        // virtual index of x[base]: the row starts at global input index n_total - (tpp - 1)
+        const RsRow row{carry + c * (size_t)tpp, (size_t)(tpp - 1), in + c * in_stride, n_in};
+        const size_t v0 = (size_t)(base - n_total) + (size_t)(tpp - 1);
         const float *h = hp + (size_t)phase * tpp;
         float acc[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) acc[u] = 0.f;
         int j = 0;
-        for (; j + UNROLL <= tpp; j += UNROLL) {
+        if (v0 >= (size_t)(tpp - 1) + row.hist) {
+            // whole window inside the chunk (every output but the first few of a call): plain pointer walk
+            const float *x = row.in + (v0 - row.hist);
+            for (; j + UNROLL <= tpp; j += UNROLL) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) acc[u] = fmaf(__ldg(h + j + u), x[-(j + u)], acc[u]);
+                for (int u = 0; u < UNROLL; ++u) acc[u] = fmaf(__ldg(h + j + u), x[-(j + u)], acc[u]);
+            }
+            for (; j < tpp; ++j) acc[0] = fmaf(__ldg(h + j), x[-j], acc[0]);
+        } else {
+            for (; j + UNROLL <= tpp; j += UNROLL) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) acc[u] = fmaf(__ldg(h + j + u), row.at(v0 - (size_t)(j + u)), acc[u]);
+            }
+            for (; j < tpp; ++j) acc[0] = fmaf(__ldg(h + j), row.at(v0 - (size_t)j), acc[0]);
         }
-        for (; j < tpp; ++j) acc[0] = fmaf(__ldg(h + j), x[-j], acc[0]);
         float s = 0.f;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) s += acc[u];
         out[c * out_stride + k] = s;
+    }
+}
+
+// next history = the last tpp-1 samples of [carry | chunk], written to the other carry buffer
+__global__ void rs_carry_kernel(const float *__restrict__ carry, float *__restrict__ next, const float *__restrict__ in,
+                                size_t n_in, size_t in_stride, size_t n_ch, int tpp)
+{
+    const size_t hist = (size_t)(tpp - 1);
+    const size_t total = n_ch * hist;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / hist, k = i % hist;
+        const RsRow row{carry + c * (size_t)tpp, hist, in + c * in_stride, n_in};
+        next[c * (size_t)tpp + k] = row.at(n_in + k);
     }
 }
 
@@ -240,7 +276,8 @@ struct RsDecCfg {
 
 template <int M, int R, int NT>
 __global__ void __launch_bounds__(NT)
-resample_dec_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, size_t valid, size_t s0, size_t n_out,
+resample_dec_kernel(const float *__restrict__ carry, const float *__restrict__ in, size_t n_in, size_t in_stride,
+                    size_t n_ch, size_t s0, size_t n_out,
                     float *__restrict__ out, size_t out_stride, const __grid_constant__ RsTaps<2 * RS_ZERO_CROSSINGS * M + 1> taps)
 {
     using Cfg = RsDecCfg<M, R, NT>;
@@ -250,10 +287,15 @@ resample_dec_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, size
     const size_t n_tiles = tiles_per_ch * n_ch;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t c = tile / tiles_per_ch, o0 = (tile % tiles_per_ch) * Cfg::TILE_OUT;
-        const size_t first = s0 + o0 * M;                                   // window of output o0 starts here
-        const float *src = buf + c * cap + first;
-        const size_t avail = valid - first;                                 // floats of this row that exist
-        for (int i = t; i < Cfg::TILE_IN; i += NT) rs_tile[i] = (size_t)i < avail ? src[i] : 0.f;
+        const size_t first = s0 + o0 * M;                                   // window of output o0 starts here (virtual row)
+        const RsRow row{carry + c * (size_t)Cfg::TPP, (size_t)(Cfg::TPP - 1), in + c * in_stride, n_in};
+        if (first >= row.hist) {                                            // every tile but a channel's first
+            const float *src = row.in + (first - row.hist);
+            const size_t avail = n_in - (first - row.hist);
+            for (int i = t; i < Cfg::TILE_IN; i += NT) rs_tile[i] = (size_t)i < avail ? __ldg(src + i) : 0.f;
+        } else {
+            for (int i = t; i < Cfg::TILE_IN; i += NT) rs_tile[i] = row.at(first + (size_t)i);
+        }
         __syncthreads();
         float acc[R];
 #pragma unroll
@@ -281,7 +323,8 @@ resample_dec_kernel(const float *__restrict__ buf, size_t cap, size_t n_ch, size
 }
 
 template <int M, int R>
-static int launch_resample_dec(lrc_resampler *r, size_t n_in, size_t no, float *d_out, size_t out_stride, cudaStream_t s)
+static int launch_resample_dec(lrc_resampler *r, const float *d_in, size_t n_in, size_t in_stride, size_t no, float *d_out,
+                               size_t out_stride, cudaStream_t s)
 {
     constexpr int NT = 128;
     using Cfg = RsDecCfg<M, R, NT>;
@@ -297,8 +340,7 @@ static int launch_resample_dec(lrc_resampler *r, size_t n_in, size_t no, float *
     for (int i = 0; i < Cfg::TPP; ++i) taps.g[i] = (float)r->h[Cfg::TPP - 1 - i];      // reversed: correlation form
     // buffer index of x[m_next*M - (TPP-1)]: the row starts at global input index n_total - (TPP-1)
     const size_t s0 = (size_t)(r->m_next * (unsigned long long)M - r->n_total);
-    const size_t valid = (r->tpp - 1) + n_in;
-    kern<<<(unsigned)blocks, NT, Cfg::SMEM_BYTES, s>>>(r->d_buf, r->cap, r->n_ch, valid, s0, no, d_out, out_stride, taps);
+    kern<<<(unsigned)blocks, NT, Cfg::SMEM_BYTES, s>>>(r->d_carry[r->cur], d_in, n_in, in_stride, r->n_ch, s0, no, d_out, out_stride, taps);
     LRC_CUDA(cudaGetLastError());
     return LRC_OK;
 }
@@ -340,12 +382,12 @@ extern "C" int lrc_resampler_create(lrc_ctx *ctx, double ratio, size_t n_ch, siz
             if (idx < r->ntaps) hp[(size_t)p * r->tpp + j] = (float)r->h[idx];
         }
     r->cap = (r->tpp + max_chunk + 3) / 4 * 4;
-    r->d_hp = r->d_buf = r->d_carry = nullptr;
+    r->d_hp = r->d_carry[0] = r->d_carry[1] = nullptr; r->cur = 0;
     r->d_hin = r->d_hout = nullptr; r->hin_cap = r->hout_cap = 0;
     r->n_total = 0; r->m_next = 0;
     if (cudaMalloc(&r->d_hp, hp.size() * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&r->d_buf, n_ch * r->cap * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&r->d_carry, n_ch * r->tpp * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&r->d_carry[0], n_ch * r->tpp * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&r->d_carry[1], n_ch * r->tpp * sizeof(float)) != cudaSuccess ||
         cudaMemcpy(r->d_hp, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
         lrc_set_error("lrc_resampler_create: %s", cudaGetErrorString(cudaGetLastError()));
         lrc_resampler_destroy(r);
@@ -359,7 +401,7 @@ extern "C" int lrc_resampler_destroy(lrc_resampler *r)
 {
     if (!r) return LRC_OK;
     cudaSetDevice(r->ctx->device);
-    cudaFree(r->d_hp); cudaFree(r->d_buf); cudaFree(r->d_carry); cudaFree(r->d_hin); cudaFree(r->d_hout);
+    cudaFree(r->d_hp); cudaFree(r->d_carry[0]); cudaFree(r->d_carry[1]); cudaFree(r->d_hin); cudaFree(r->d_hout);
     delete r;
     return LRC_OK;
 }
@@ -369,7 +411,8 @@ extern "C" int lrc_resampler_reset(lrc_resampler *r)
     LRC_REQUIRE(r != nullptr, LRC_ERR_INVALID, "null plan");
     LRC_BIND(r->ctx);
     r->n_total = 0; r->m_next = 0;
-    LRC_CUDA(cudaMemsetAsync(r->d_buf, 0, r->n_ch * r->cap * sizeof(float), r->ctx->stream));   // x[<0] = 0
+    r->cur = 0;
+    LRC_CUDA(cudaMemsetAsync(r->d_carry[0], 0, r->n_ch * r->tpp * sizeof(float), r->ctx->stream));   // x[<0] = 0
     LRC_CUDA(cudaStreamSynchronize(r->ctx->stream));
     return LRC_OK;
 }
@@ -406,9 +449,7 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
     LRC_REQUIRE(n_in <= r->max_chunk, LRC_ERR_CAPACITY, "lrc_resampler_process: chunk longer than max_chunk");
     LRC_REQUIRE(d_in && in_stride >= n_in, LRC_ERR_INVALID, "lrc_resampler_process: bad input");
     cudaStream_t s = lrc_stream(r->ctx, stream);
-    const size_t hist = r->tpp - 1, row = r->cap * sizeof(float);
-    LRC_CUDA(cudaMemcpy2DAsync(r->d_buf + hist, row, d_in, in_stride * sizeof(float), n_in * sizeof(float), r->n_ch,
-                               cudaMemcpyDeviceToDevice, s));
+    const size_t hist = r->tpp - 1;
     const size_t no = lrc_resampler_next_out_len(r, n_in);
     if (no) {
         LRC_REQUIRE(d_out && out_stride >= no, LRC_ERR_CAPACITY, "lrc_resampler_process: output too small "
@@ -416,11 +457,11 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
         int rc = -1;
         if (r->L == 1) {                       // decimators with a register-blocked tile instance
             switch (r->M) {
-                case 2: rc = launch_resample_dec<2, 6>(r, n_in, no, d_out, out_stride, s); break;
-                case 3: rc = launch_resample_dec<3, 4>(r, n_in, no, d_out, out_stride, s); break;
-                case 4: rc = launch_resample_dec<4, 5>(r, n_in, no, d_out, out_stride, s); break;
-                case 5: rc = launch_resample_dec<5, 4>(r, n_in, no, d_out, out_stride, s); break;
-                case 6: rc = launch_resample_dec<6, 6>(r, n_in, no, d_out, out_stride, s); break;
+                case 2: rc = launch_resample_dec<2, 6>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 3: rc = launch_resample_dec<3, 4>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 4: rc = launch_resample_dec<4, 5>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 5: rc = launch_resample_dec<5, 4>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 6: rc = launch_resample_dec<6, 6>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
                 default: break;
             }
         }
@@ -429,18 +470,19 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
             size_t blocks = ceil_div(r->n_ch * no, 256);
             const size_t cap = (size_t)r->ctx->n_sm * 16;
             if (blocks > cap) blocks = cap;
-            resample_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(r->d_buf, r->cap, r->n_ch, r->d_hp, r->L, r->M, (int)r->tpp,
-                                                               r->n_total, r->m_next, no, d_out, out_stride);
+            resample_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(r->d_carry[r->cur], d_in, n_in, in_stride, r->n_ch, r->d_hp, r->L,
+                                                               r->M, (int)r->tpp, r->n_total, r->m_next, no, d_out, out_stride);
             LRC_CUDA(cudaGetLastError());
         }
     }
-    // new history = the last tpp-1 floats of [history | chunk]
+    // new history = the last tpp-1 samples of [history | chunk], into the other carry buffer
     if (hist) {
-        const size_t crow = r->tpp * sizeof(float);
-        LRC_CUDA(cudaMemcpy2DAsync(r->d_carry, crow, r->d_buf + n_in, row, hist * sizeof(float), r->n_ch,
-                                   cudaMemcpyDeviceToDevice, s));
-        LRC_CUDA(cudaMemcpy2DAsync(r->d_buf, row, r->d_carry, crow, hist * sizeof(float), r->n_ch,
-                                   cudaMemcpyDeviceToDevice, s));
+        size_t blocks = ceil_div(r->n_ch * hist, 256);
+        if (blocks > 4096) blocks = 4096;
+        rs_carry_kernel<<<(unsigned)blocks, 256, 0, s>>>(r->d_carry[r->cur], r->d_carry[r->cur ^ 1], d_in, n_in, in_stride, r->n_ch,
+                                                        (int)r->tpp);
+        LRC_CUDA(cudaGetLastError());
+        r->cur ^= 1;
     }
     r->n_total += n_in;
     r->m_next += no;
