@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         L.orc_b2d.restype = sz
         L.orc_b2d.argtypes = [vp, sz]
         L.orc_eat.argtypes = [vp, vp, sz, vp]
+        L.orc_kissfft_batch.restype = sz
+        L.orc_kissfft_batch.argtypes = [vp, vp, C.c_int, C.c_int, sz, vp, vp]
         L.orc_chain_psd.restype = sz
         L.orc_chain_psd.argtypes = [vp, sz, vp, sz, sz, C.c_int, vp, vp, vp, vp]
         _lib = L
@@ -329,6 +331,18 @@ def chain_psd_cpu(x: np.ndarray, taps: np.ndarray, d: int, nfft: int, win: np.nd
         a, f = C.c_void_p(None), C.c_void_p(None)
     nfr = lib().orc_chain_psd(_ptr(x), x.size, _ptr(taps), taps.size, d, nfft, _ptr(win), _ptr(psd), a, f)
     return psd, int(nfr)
+
+
+def kissfft_batch_cpu(x: np.ndarray, inverse: bool = False, opt: bool = False) -> np.ndarray:
+    """(batch, nfft) frames through the vendored kiss_fft (or the restatement) in one C loop -- for timing."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    out = np.empty_like(x)
+    if have_ref():
+        a, f = ref_kiss_fn_ptrs(opt)
+    else:
+        a, f = C.c_void_p(None), C.c_void_p(None)
+    lib().orc_kissfft_batch(_ptr(x), _ptr(out), x.shape[-1], int(inverse), x.size // x.shape[-1], a, f)
+    return out
 
 
 def psdpng_rows(pcm: np.ndarray, nfft: int = 1024, navg: int = 20, remove_dc: bool = False, stereo: bool = False,

@@ -530,3 +530,17 @@ size_t orc_chain_psd(const orc_cpx *x, size_t n, const float *taps, size_t m, si
     free(frame); free(spec); free(cfg);
     return nframes;
 }
+
+/* batch of frames through the vendored kiss_fft in a C loop (CPU baseline timing only: a Python loop over
+ * kiss_fft() calls measures the interpreter, not the library) */
+size_t orc_kissfft_batch(const orc_cpx *x, orc_cpx *y, int nfft, int inverse, size_t batch,
+                         orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn)
+{
+    void *cfg = alloc_fn ? alloc_fn(nfft, inverse, NULL, NULL) : NULL;
+    for (size_t f = 0; f < batch; ++f) {
+        if (fft_fn) fft_fn(cfg, x + f * (size_t)nfft, y + f * (size_t)nfft);
+        else orc_fft(nfft, inverse, x + f * (size_t)nfft, y + f * (size_t)nfft);
+    }
+    free(cfg);
+    return batch;
+}

@@ -115,4 +115,7 @@ size_t orc_chain_psd(const orc_cpx *x, size_t n, const float *taps, size_t m, si
 #ifdef __cplusplus
 }
 #endif
+size_t orc_kissfft_batch(const orc_cpx *x, orc_cpx *y, int nfft, int inverse, size_t batch,
+                         orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn);
+
 #endif

@@ -15,7 +15,7 @@ pub const LRC_WINDOW_NONE: c_int = 0;
 pub const LRC_WINDOW_HANN: c_int = 1;
 
 macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
-opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_ook);
+opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_rfft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_ook);
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -57,6 +57,14 @@ extern "C" {
     pub fn lrc_fft_destroy(fft: *mut lrc_fft) -> c_int;
     pub fn lrc_fft_run(fft: *mut lrc_fft, d_in: *const c_float, d_out: *mut c_float, batch: size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_fft_run_host(fft: *mut lrc_fft, h_in: *const c_float, h_out: *mut c_float, n_samples: size_t) -> c_int;
+    // kiss_fftr / kiss_fftri (libkissfft/tools/kiss_fftr.c:67-159)
+    pub fn lrc_rfft_create(ctx: *mut lrc_ctx, nfft: c_int, inverse: c_int, rfft: *mut *mut lrc_rfft) -> c_int;
+    pub fn lrc_rfft_destroy(rfft: *mut lrc_rfft) -> c_int;
+    pub fn lrc_rfft_run(rfft: *mut lrc_rfft, d_in: *const c_float, d_out: *mut c_float, batch: size_t, stream: *mut c_void) -> c_int;
+    pub fn lrc_rfft_run_host(rfft: *mut lrc_rfft, h_in: *const c_float, h_out: *mut c_float, batch: size_t) -> c_int;
+    // tools/psdpng.c:120-185 spectrogram rows
+    pub fn lrc_psdpng_rows(ctx: *mut lrc_ctx, d_pcm: *const i16, n_samples: size_t, nfft: c_int, navg: c_int, remove_dc: c_int,
+                           stereo: c_int, d_rows: *mut c_float, n_rows: *mut size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_psd_create(ctx: *mut lrc_ctx, nfft: c_int, window: c_int, psd: *mut *mut lrc_psd) -> c_int;
     pub fn lrc_psd_set_window(psd: *mut lrc_psd, h_window: *const c_float) -> c_int;
     pub fn lrc_psd_destroy(psd: *mut lrc_psd) -> c_int;
@@ -70,6 +78,8 @@ extern "C" {
                          n_rows: *mut size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_chain_run_host(chain: *mut lrc_chain, h_in: *const c_float, n_in: size_t, k_avg: size_t, h_rows: *mut c_float,
                               n_rows: *mut size_t) -> c_int;
+    pub fn lrc_chain_run_host_u8(chain: *mut lrc_chain, h_iq: *const u8, n_in: size_t, k_avg: size_t, h_rows: *mut c_float,
+                                 n_rows: *mut size_t) -> c_int;
 
     pub fn lrc_fastfir_create(ctx: *mut lrc_ctx, h_taps_cpx: *const c_float, nh: size_t, nfft: size_t, ff: *mut *mut lrc_fastfir) -> c_int;
     pub fn lrc_fastfir_destroy(ff: *mut lrc_fastfir) -> c_int;

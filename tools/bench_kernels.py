@@ -126,9 +126,9 @@ def main():
         extra = None
         if a.cpu and oracle.have_ref():
             hx = synth.cf32_noise_tones(1024 * 256, seed=2).reshape(256, 1024)
-            extra = cpu_rate(lambda: oracle.ref_kissfft(hx), hx.size)
+            extra = cpu_rate(lambda: oracle.kissfft_batch_cpu(hx), hx.size)
             extra["cpu_what"] = "vendored kiss_fft.c, reference build flags (libkissfft/Makefile:4, no -O)"
-            extra["cpu_Msamples/s_O3"] = cpu_rate(lambda: oracle.ref_kissfft(hx, opt=True), hx.size, 1.0)["cpu_Msamples/s"]
+            extra["cpu_Msamples/s_O3"] = cpu_rate(lambda: oracle.kissfft_batch_cpu(hx, opt=True), hx.size, 1.0)["cpu_Msamples/s"]
         report("FFT1024 batched out-of-place (K3)", n, n * 16, ms, extra)
         p = blocks.Psd(ctx, 1024)
         ms, _ = timeit(lambda: p.run(x, 64))
