@@ -58,6 +58,21 @@ __device__ __forceinline__ float lut_envelope(const float *lut, uint32_t b0, uin
     return lut[lut_index(max(b0, b1), min(b0, b1))];
 }
 
+// The block-sum kernel is bound by the ALU pipe (byte extraction, max/min, index and address arithmetic run
+// there at half the FMA pipe's rate), so its lookup is written to keep that pipe short: one PRMT per byte,
+// max, min, and the byte address  lut + 4 (hi (hi + 17) / 2 + lo)  =  lut + hi (2 hi + 34) + 4 lo  as two
+// integer multiply-adds (FMA pipe) and one scaled add.
+__device__ __forceinline__ float lut_envelope_s(uint32_t lut_s, uint32_t b0, uint32_t b1)
+{
+    const uint32_t hi = max(b0, b1), lo = min(b0, b1);
+    uint32_t a, b;
+    asm("mad.lo.u32 %0, %1, 2, 34;" : "=r"(a) : "r"(hi));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(b) : "r"(hi), "r"(a), "r"(lut_s));
+    float e;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(b + 4u * lo));
+    return e;
+}
+
 __device__ __forceinline__ void lut_load(float *s_lut, const float *__restrict__ g_lut)
 {
     for (int i = threadIdx.x; i < OOK_LUT_N / 4; i += blockDim.x)
@@ -120,6 +135,7 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stg = reinterpret_cast<uint8_t *>(ka_smem + OOK_LUT_N) + warp * (KA_STAGES * KA_STAGE_BYTES);
     const uint32_t stg_s = smem_u32(stg);
+    const uint32_t lut_s = smem_u32(lut);
     const size_t groups_per_stream = (n_blocks + 31) / 32;
     const size_t n_groups = groups_per_stream * n_streams;
     const size_t warps_total = (size_t)gridDim.x * KA_WARPS;
@@ -158,8 +174,8 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float e0 = lut_envelope(lut, w[k] & 0xffu, (w[k] >> 8) & 0xffu);
-                        const float e1 = lut_envelope(lut, (w[k] >> 16) & 0xffu, w[k] >> 24);
+                        const float e0 = lut_envelope_s(lut_s, __byte_perm(w[k], 0, 0x4440), __byte_perm(w[k], 0, 0x4441));
+                        const float e1 = lut_envelope_s(lut_s, __byte_perm(w[k], 0, 0x4442), __byte_perm(w[k], 0, 0x4443));
                         s = __fadd_rn(s, e0);                // samples.iter().sum(): left to right from 0.0
                         s = __fadd_rn(s, e1);
                         mx = fmaxf(mx, fmaxf(e0, e1));
@@ -310,11 +326,17 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
 // triangular index); a burst's max/2 becomes the rank threshold #{values <= max/2} by a warp-wide 32-ary
 // search of the sorted values when the walk enters the burst; then x > max/2  <=>  rank(x) >= threshold,
 // exactly, for every byte pair.  Neighbouring byte pairs (a noise floor sits within a few codes of 127/127)
-// would all fall into the banks of byte0 >> 1, so the table is stored XOR-swizzled: entry (b0, b1) lives at
-// (b0 ^ ((b1 & 7) << 3)) | b1 << 8, which spreads an 8 x 8 neighbourhood over all 32 banks.
+// would all fall into the banks of byte0 >> 1 with a pitch of 256 entries, so a byte1 row is 264 entries long:
+// 132 words = 4 banks further per row, which spreads an 8 x 8 neighbourhood over all 32 banks.  Like the
+// block-sum kernel this one is ALU-pipe bound, so the per-sample work is kept to two PRMT, one integer
+// multiply-add (FMA pipe) and one scaled add for the address, one subtraction and one funnel shift that
+// moves the comparison's sign bit into the mask (bits arrive reversed; one BREV per 16 samples).
 // ---------------------------------------------------------------------------------------------
-constexpr int OOK_RANK_BYTES = 65536 * 2;
-__host__ __device__ __forceinline__ uint32_t ook_rank_slot(uint32_t pair) { return pair ^ ((pair >> 5) & 0x38u); }
+constexpr int OOK_RANK_PITCH = 264;                           // u16 entries per byte1 row (256 used)
+constexpr int OOK_RANK_N = 256 * OOK_RANK_PITCH;
+constexpr int OOK_RANK_BYTES = OOK_RANK_N * 2;                // 135 168
+static_assert(OOK_RANK_BYTES % 16 == 0, "table is copied as uint4");
+__host__ __device__ __forceinline__ uint32_t ook_rank_slot(uint32_t b0, uint32_t b1) { return b0 + OOK_RANK_PITCH * b1; }
 
 // #{i : uniq[i] <= h} for ascending uniq[0..n): every lane probes one position per round
 __device__ __forceinline__ uint32_t warp_upper_bound(const float *__restrict__ uniq, uint32_t n, float h, int lane)
@@ -348,6 +370,7 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         reinterpret_cast<uint4 *>(kc_rank)[i] = __ldg(reinterpret_cast<const uint4 *>(g_rank) + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const uint32_t rank_s = smem_u32(kc_rank);
     const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (st >= n_streams) return;
     const int32_t *tag = d_tag + st * n_blocks;
@@ -373,12 +396,19 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         }
         const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         uint32_t m = 0;
+        const uint32_t hm1 = h - 1u;                                         // rank >= h  <=>  (h - 1) - rank < 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const uint32_t r0 = kc_rank[ook_rank_slot(w[i] & 0xffffu)], r1 = kc_rank[ook_rank_slot(w[i] >> 16)];
-            m |= (r0 >= h ? 1u : 0u) << (2 * i);                             // (x > max/2f32) as usize  :91
-            m |= (r1 >= h ? 1u : 0u) << (2 * i + 1);
+            uint32_t a0, a1;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a0) : "r"(__byte_perm(w[i], 0, 0x4441)), "r"(2u * OOK_RANK_PITCH), "r"(rank_s));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(__byte_perm(w[i], 0, 0x4443)), "r"(2u * OOK_RANK_PITCH), "r"(rank_s));
+            unsigned short r0, r1;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r0) : "r"(a0 + 2u * __byte_perm(w[i], 0, 0x4440)));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r1) : "r"(a1 + 2u * __byte_perm(w[i], 0, 0x4442)));
+            m = __funnelshift_l(hm1 - (uint32_t)r0, m, 1);                   // (x > max/2f32) as usize  :91
+            m = __funnelshift_l(hm1 - (uint32_t)r1, m, 1);
         }
+        m = __brev(m) >> 16;                                                 // sample i -> bit i
         // previous bit of this lane's first sample
         uint32_t pb = __shfl_up_sync(0xffffffffu, m >> 15, 1) & 1u;
         const bool has_prev = (lane > 0) || (pos > 0);
@@ -558,7 +588,7 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
     OOK_ALLOC(d_runs_dbg, n_streams * o->max_runs);
     OOK_ALLOC(d_lut, (size_t)OOK_LUT_N);
-    OOK_ALLOC(d_rank, (size_t)65536); OOK_ALLOC(d_uniq, (size_t)65536);
+    OOK_ALLOC(d_rank, (size_t)OOK_RANK_N); OOK_ALLOC(d_uniq, (size_t)65536);
 #undef OOK_ALLOC
     if (e == cudaSuccess) {
         e = cudaMemsetAsync(o->d_lut, 0, OOK_LUT_BYTES, ctx->stream);           // the row padding is never read
@@ -580,13 +610,13 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
             std::vector<float> uq(tab);
             std::sort(uq.begin(), uq.end());
             uq.erase(std::unique(uq.begin(), uq.end()), uq.end());
-            std::vector<uint16_t> rank(65536);
-            // kernel index = byte0 | byte1 << 8 (memory order); the table is symmetric in the two bytes
+            std::vector<uint16_t> rank(OOK_RANK_N, 0);
+            // tab index = b0 * 256 + b1; the table is symmetric in the two bytes
             for (uint32_t i = 0; i < 65536; ++i)
-                rank[ook_rank_slot(i)] = (uint16_t)(std::lower_bound(uq.begin(), uq.end(), tab[i]) - uq.begin());
+                rank[ook_rank_slot(i >> 8, i & 0xffu)] = (uint16_t)(std::lower_bound(uq.begin(), uq.end(), tab[i]) - uq.begin());
             o->n_uniq = (uint32_t)uq.size();
             e = cudaMemcpy(o->d_uniq, uq.data(), uq.size() * sizeof(float), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(o->d_rank, rank.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(o->d_rank, rank.data(), rank.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
         }
     }
     if (e != cudaSuccess) {
