@@ -11,10 +11,12 @@
 
 namespace lrfft {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add/sub as ONE packed instruction each (FADD2, see common.cuh)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
 
-// forward: a * (-j);  inverse: a * (+j)
+// forward: a * (-j);  inverse: a * (+j).  Pure lane swap + one negation: ptxas folds it into the operand
+// modifier of the consuming packed instruction.
 template <bool INV>
 __device__ __forceinline__ float2 rot90(float2 a)
 {
@@ -29,7 +31,7 @@ __device__ __forceinline__ void bfly2(float2 &a, float2 &b)
     b = csub(t, b);
 }
 
-// natural-order 4-point DFT in place
+// natural-order 4-point DFT in place: 8 packed adds
 template <bool INV>
 __device__ __forceinline__ void bfly4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
@@ -41,7 +43,8 @@ __device__ __forceinline__ void bfly4(float2 &a0, float2 &a1, float2 &a2, float2
     a3 = csub(d02, d13);
 }
 
-// a * W16^k, W16 = exp(-+ 2 pi j / 16); k is a compile-time constant after unrolling
+// a * W16^k, W16 = exp(-+ 2 pi j / 16); k is a compile-time constant after unrolling.  Two packed
+// instructions (FMUL2 + FFMA2) for the non-trivial k.
 template <bool INV>
 __device__ __forceinline__ float2 mul_w16(float2 a, int k)
 {
@@ -69,8 +72,8 @@ __device__ __forceinline__ float2 mul_w16(float2 a, int k)
         default: c = C1;  s = -S1; break;   // 15
     }
     if (INV) s = -s;
-    // (a.x + j a.y)(c - j s)
-    return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+    // (a.x + j a.y)(c - j s) = (a.x c + a.y s, a.y c - a.x s)
+    return fma2(a, make_float2(c, c), mul2(make_float2(a.y, a.x), make_float2(s, -s)));
 }
 
 // natural-order R-point DFT of v[0..R) held in registers, R in {1, 2, 4, 8, 16}

@@ -316,7 +316,7 @@ psd_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const f
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 float2 x = __ldcs(src + e * T);
-                v[e] = make_float2(x.x * w[e], x.y * w[e]);
+                v[e] = mul2(x, make_float2(w[e], w[e]));
             }
             if constexpr (T >= 32) {
                 F::run_twreg(v, sm, twr, t, SyncNamed{1 + g, T});
@@ -350,7 +350,7 @@ struct PsdTmaCfg {
     static constexpr int SMEM_BYTES = G * GROUP_BYTES;
 };
 
-template <int LOG2N, int PSD_STAGES, int MINB>
+template <int LOG2N, int PSD_STAGES, int MINB, bool PACKACC>
 __global__ void __launch_bounds__(PsdTmaCfg<LOG2N, PSD_STAGES>::THREADS, MINB)
 psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
                float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
@@ -407,9 +407,11 @@ psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, con
     if (t == 0)
         for (int i = 0; i < PSD_STAGES - 1 && ahead.item < n_items; ++i) request();
 
-    float acc[E];
+    // PACKACC: (sum re^2, sum im^2) kept apart, one FFMA2 per bin per frame (fewer issue slots, 16 more
+    // registers); otherwise one float per bin, two FFMA (same FP32-pipe cycles)
+    float2 acc[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    for (int e = 0; e < E; ++e) acc[e] = make_float2(0.f, 0.f);
     for (int i = 0; cur.item < n_items; ++i) {
         const int stage = i % PSD_STAGES;
         // the stage being refilled now was read (into registers) one iteration ago, and every thread has
@@ -421,15 +423,18 @@ psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, con
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const float2 x = src[e * T];
-            v[e] = make_float2(x.x * w[e], x.y * w[e]);
+            v[e] = mul2(x, make_float2(w[e], w[e]));
         }
         F::run_twreg(v, sm, twr, t, SyncNamed{1 + g, T});
 #pragma unroll
-        for (int e = 0; e < E; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));
+        for (int e = 0; e < E; ++e) {
+            if constexpr (PACKACC) acc[e] = fma2(v[e], v[e], acc[e]);
+            else acc[e].x = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e].x));
+        }
         if (cur.f + 1 == cur.f1) {                        // last frame of the item: hand the partial spectrum out
             float *dst = partial + cur.item * N + t;
 #pragma unroll
-            for (int e = 0; e < E; ++e) { dst[e * T] = acc[e]; acc[e] = 0.f; }
+            for (int e = 0; e < E; ++e) { dst[e * T] = PACKACC ? acc[e].x + acc[e].y : acc[e].x; acc[e] = make_float2(0.f, 0.f); }
         }
         advance(cur);
     }
@@ -457,9 +462,8 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
     if constexpr (T >= 32 && T <= 128) {            // N = 512 .. 2048: the ring fits several CTAs per SM
         if (((uintptr_t)in & 15) == 0) {
             static const int variant = getenv("LRC_PSD_VARIANT") ? atoi(getenv("LRC_PSD_VARIANT")) : 0;
-            if (variant == 1) {
-                using Cfg = PsdTmaCfg<LOG2N, 2>;
-                auto kern = psd_tma_kernel<LOG2N, 2, 4>;
+            auto go = [&](auto kern, auto cfg) -> int {
+                using Cfg = decltype(cfg);
                 LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
                 int occ = 1;
                 LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
@@ -470,19 +474,13 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
                 kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
                 LRC_CUDA(cudaGetLastError());
                 return LRC_OK;
+            };
+            switch (variant) {      // tuning variants (tools/bench_kernels.py); 0 is the shipped one
+                case 1: return go(psd_tma_kernel<LOG2N, 2, 4, false>, PsdTmaCfg<LOG2N, 2>{});
+                case 2: return go(psd_tma_kernel<LOG2N, 3, 2, true>, PsdTmaCfg<LOG2N, 3>{});
+                case 3: return go(psd_tma_kernel<LOG2N, 2, 3, false>, PsdTmaCfg<LOG2N, 2>{});
+                default: return go(psd_tma_kernel<LOG2N, 3, 3, false>, PsdTmaCfg<LOG2N, 3>{});
             }
-            using Cfg = PsdTmaCfg<LOG2N, 3>;
-            auto kern = psd_tma_kernel<LOG2N, 3, 1>;
-            LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-            int occ = 1;
-            LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
-            if (occ < 1) occ = 1;
-            size_t blocks = ceil_div(n_items, (size_t)Cfg::G);
-            const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
-            if (blocks > max_blocks) blocks = max_blocks;
-            kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
-            LRC_CUDA(cudaGetLastError());
-            return LRC_OK;
         }
     }
     const int threads = T > 128 ? T : 128;
