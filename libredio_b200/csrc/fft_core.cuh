@@ -76,10 +76,29 @@ __device__ __forceinline__ float2 mul_w16(float2 a, int k)
     return fma2(a, make_float2(c, c), mul2(make_float2(a.y, a.x), make_float2(s, -s)));
 }
 
-// natural-order R-point DFT of v[0..R) held in registers, R in {1, 2, 4, 8, 16}
+// a * W32^k, W32 = exp(-+ 2 pi j / 32); even k is a W16 power, odd k takes cos/sin from a literal table
+// (k is a compile-time constant after unrolling, so the lookups fold to immediates)
+template <bool INV>
+__device__ __forceinline__ float2 mul_w32(float2 a, int k)
+{
+    k &= 31;
+    if ((k & 1) == 0) return mul_w16<INV>(a, k >> 1);
+    constexpr float C1 = 0.98078528040323043f, C3 = 0.83146961230254524f;   // cos(pi/16), cos(3 pi/16)
+    constexpr float C5 = 0.55557023301960229f, C7 = 0.19509032201612833f;   // cos(5 pi/16), cos(7 pi/16)
+    const float cq[4] = {C1, C3, C5, C7}, sq[4] = {C7, C5, C3, C1};        // first quadrant, odd k = 1, 3, 5, 7
+    const int q = k >> 3, i = (k & 7) >> 1;
+    float c = cq[i], s = sq[i];                                             // W = c - j s (forward)
+    if (q == 1) { const float t = c; c = -s; s = t; }                       // angle + pi/2
+    else if (q == 2) { c = -c; s = -s; }
+    else if (q == 3) { const float t = c; c = s; s = -t; }
+    if (INV) s = -s;
+    return fma2(a, make_float2(c, c), mul2(make_float2(a.y, a.x), make_float2(s, -s)));
+}
+
+// natural-order R-point DFT of v[0..R) held in registers, R in {1, 2, 4, 8, 16, 32}
 template <int R, bool INV>
 struct RegFFT {
-    static_assert(R == 8 || R == 16, "radix");
+    static_assert(R == 8 || R == 16 || R == 32, "radix");
     __device__ __forceinline__ static void run(float2 *v)
     {
         constexpr int R2 = R / 4;    // R = 4 * R2 ; input index s = R2*a + b, output index r = c + 4*d
@@ -88,7 +107,7 @@ struct RegFFT {
 #pragma unroll
         for (int c = 1; c < 4; ++c)
 #pragma unroll
-            for (int b = 1; b < R2; ++b) v[R2 * c + b] = mul_w16<INV>(v[R2 * c + b], b * c * (16 / R));
+            for (int b = 1; b < R2; ++b) v[R2 * c + b] = mul_w32<INV>(v[R2 * c + b], b * c * (32 / R));
 #pragma unroll
         for (int c = 0; c < 4; ++c) RegFFT<R2, INV>::run(v + R2 * c);
         float2 tmp[R];
@@ -242,6 +261,55 @@ struct CtaFFT {
     __device__ __forceinline__ static void run_twreg(float2 *v, float2 *sm, const float2 *twr, int t, const Sync &sync)
     {
         stage<1, true, Sync>(v, sm, nullptr, twr, t, sync);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// 1024-point transform by ONE warp (32 x 32): lane n2 holds x[n2 + 32 e], e < 32, in registers.
+//   pass 1: DFT-32 over e in registers            A[n2][k1]
+//   twiddle W1024^(n2 k1)                          (k1 = register index, n2 = lane)
+//   ONE exchange through a 33-padded [32][32] shared tile (both directions conflict-free), __syncwarp only
+//   pass 2: DFT-32 over n2 in registers            X[k1 + 32 k2], lane = k1, register = k2
+// Input and output both use the coalesced layout "lane t holds element t + 32 e".  Against the CTA-level
+// CtaFFT<10> (16 x 16 x 4, two exchanges, named barriers) this moves half the shared-memory bytes per point and
+// has no barrier between warps: the 1024-point kernels are bound by shared-memory bandwidth and barrier
+// stalls, not by FP32 issue.
+// The 31 per-lane twiddles W^(lane r) live in a [31][32] shared table (row r - 1, column lane: conflict-free
+// LDS.64) filled once per CTA -- 62 registers otherwise, or extra FP32 work if rebuilt from fewer stored powers,
+// and this kernel is FP32-pipe bound once the exchanges are halved.
+template <bool INV>
+struct WarpFFT1024 {
+    static constexpr int N = 1024;
+    static constexpr int SMEM_CPX = 32 * 33;           // per-warp exchange tile
+    static constexpr int TW_CPX = 31 * 32;             // per-CTA twiddle table
+
+    // all threads of the CTA; caller synchronises afterwards
+    __device__ __forceinline__ static void fill_twiddles(const float2 *__restrict__ tw, float2 *tws)
+    {
+        for (int i = threadIdx.x; i < TW_CPX; i += blockDim.x) {
+            const int r = i / 32 + 1, lane = i % 32;
+            float2 w = __ldg(&tw[r * lane]);             // 31 * 31 < 1024
+            if (INV) w.y = -w.y;
+            tws[i] = w;
+        }
+    }
+
+    // v[e] = x[lane + 32 e] on entry, X[lane + 32 e] on exit.  xb: this warp's SMEM_CPX float2 tile.
+    __device__ __forceinline__ static void run(float2 *v, float2 *xb, const float2 *tws, int lane)
+    {
+        RegFFT<32, INV>::run(v);
+        const float2 *twl = tws + lane;
+#pragma unroll
+        for (int r = 1; r < 32; ++r) v[r] = cmulf(v[r], twl[32 * (r - 1)]);
+        float2 *wp = xb + 33 * lane;                       // row n2 = lane, column k1 = r
+        __syncwarp();                                      // previous frame's reads are done
+#pragma unroll
+        for (int r = 0; r < 32; ++r) wp[r] = v[r];
+        __syncwarp();
+        const float2 *rp = xb + lane;                      // column k1 = lane, rows n2 = e
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = rp[33 * e];
+        RegFFT<32, INV>::run(v);
     }
 };
 

@@ -146,11 +146,61 @@ fft_tma_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, size_t b
     }
 }
 
+// N = 1024, one warp per transform (WarpFFT1024): global -> registers -> one exchange -> registers -> global.
+// In-place calls are safe: a warp has its whole frame in registers before it stores anything.
+constexpr int FFTW_WARPS = 4;
+constexpr int FFTW_SMEM_BYTES = (FFTW_WARPS * WarpFFT1024<false>::SMEM_CPX + WarpFFT1024<false>::TW_CPX) * 8;
+
+template <bool INV>
+__global__ void __launch_bounds__(FFTW_WARPS * 32, 4)
+fft1024_warp_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, size_t batch, const float2 *__restrict__ tw)
+{
+    using F = WarpFFT1024<INV>;
+    extern __shared__ __align__(16) float2 fftw_sm[];
+    float2 *tws = fftw_sm + FFTW_WARPS * F::SMEM_CPX;
+    F::fill_twiddles(tw, tws);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *xb = fftw_sm + warp * F::SMEM_CPX;
+    const size_t stride = (size_t)gridDim.x * FFTW_WARPS;
+    for (size_t f = (size_t)blockIdx.x * FFTW_WARPS + warp; f < batch; f += stride) {
+        float2 v[32];
+        const float2 *src = in + f * 1024 + lane;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __ldcs(src + 32 * e);
+        if (f + stride < batch) {
+            const char *nx = reinterpret_cast<const char *>(in + (f + stride) * 1024) + lane * 256;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 128));
+        }
+        F::run(v, xb, tws, lane);
+        float2 *dst = out + f * 1024 + lane;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) __stcs(dst + 32 * e, v[e]);
+    }
+}
+
 template <int LOG2N, bool INV>
 static int launch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t batch, cudaStream_t s)
 {
     using F = CtaFFT<LOG2N, INV>;
     constexpr int T = F::T;
+    if constexpr (LOG2N == 10) {
+        static const int variant = getenv("LRC_FFT_VARIANT") ? atoi(getenv("LRC_FFT_VARIANT")) : 0;
+        if (variant == 0) {
+            auto kern = fft1024_warp_kernel<INV>;
+            LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FFTW_SMEM_BYTES));
+            int occ = 1;
+            LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FFTW_WARPS * 32, FFTW_SMEM_BYTES));
+            if (occ < 1) occ = 1;
+            size_t blocks = ceil_div(batch, (size_t)FFTW_WARPS);
+            const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+            if (blocks > max_blocks) blocks = max_blocks;
+            kern<<<(unsigned)blocks, FFTW_WARPS * 32, FFTW_SMEM_BYTES, s>>>(in, out, batch, p->d_tw);
+            LRC_CUDA(cudaGetLastError());
+            return LRC_OK;
+        }
+    }
     if constexpr (T >= 32 && T <= 128) {
         // in-place calls are safe here too: a frame is fully in shared memory before its slot is written
         if (((uintptr_t)in & 15) == 0 && batch >= 64) {
@@ -440,6 +490,84 @@ psd_tma_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, con
     }
 }
 
+// N = 1024, one WARP per transform (WarpFFT1024): frames go straight from global memory into registers (the
+// next frame is prefetched into L2 while this one is transformed), one shared-memory exchange per frame, no
+// barrier between warps.  Shared-memory traffic per point: 16 B exchange + 4 B window, against 48 B for the
+// TMA-staged CTA-level kernel above, which is bound by exactly that.
+constexpr int PSDW_WARPS = 4;
+constexpr int PSDW_SMEM_BYTES = (PSDW_WARPS * WarpFFT1024<false>::SMEM_CPX + WarpFFT1024<false>::TW_CPX) * 8 + 1024 * 4;
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+template <int MINB, int PF>
+__global__ void __launch_bounds__(PSDW_WARPS * 32, MINB)
+psd1024_warp_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
+                    float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
+{
+    using F = WarpFFT1024<false>;
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) float2 psdw_sm[];
+    float2 *tws = psdw_sm + PSDW_WARPS * F::SMEM_CPX;
+    float *wsm = reinterpret_cast<float *>(tws + F::TW_CPX);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[i] = win[i];
+    F::fill_twiddles(tw, tws);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *xb = psdw_sm + warp * F::SMEM_CPX;
+    const float *wl = wsm + lane;
+
+    const size_t stride = (size_t)gridDim.x * PSDW_WARPS;
+    for (size_t item = (size_t)blockIdx.x * PSDW_WARPS + warp; item < n_items; item += stride) {
+        const size_t row = item / ipr, c = item % ipr;
+        const size_t f0 = row * k_avg + c * fpi;
+        size_t f1 = f0 + fpi;
+        if (f1 > (row + 1) * k_avg) f1 = (row + 1) * k_avg;
+        // first frame of this warp's next item, for the prefetch issued during the last frame of this one
+        size_t fnext_item = 0;
+        const bool has_next = item + stride < n_items;
+        if (has_next) {
+            const size_t it2 = item + stride;
+            fnext_item = (it2 / ipr) * k_avg + (it2 % ipr) * fpi;
+        }
+        float acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+        for (size_t f = f0; f < f1; ++f) {
+            float2 v[32];
+            const float2 *src = in + f * N + lane;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __ldcs(src + 32 * e);
+            {   // next frame -> L2: 8 KB = 64 lines of 128 B, two per lane
+                const bool more = f + 1 < f1;
+                if (more || has_next) {
+                    const char *nx = reinterpret_cast<const char *>(in + (more ? f + 1 : fnext_item) * N) + lane * 256;
+                    if (PF == 1) { prefetch_l2(nx); prefetch_l2(nx + 128); }
+                    if (PF == 2) { prefetch_l1(nx); prefetch_l1(nx + 128); }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float w = wl[32 * e];
+                v[e] = mul2(v[e], make_float2(w, w));
+            }
+            F::run(v, xb, tws, lane);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));
+        }
+        float *dst = partial + item * N + lane;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dst[32 * e] = acc[e];
+    }
+}
+
 __global__ void psd_reduce_kernel(const float *__restrict__ partial, float *__restrict__ rows, int nfft,
                                   size_t ipr, size_t n_rows, float scale, int accumulate)
 {
@@ -475,11 +603,34 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
                 LRC_CUDA(cudaGetLastError());
                 return LRC_OK;
             };
+            if constexpr (LOG2N == 10) {
+                if (variant == 0 || variant >= 10) {
+                    auto launch_w = [&](auto kern) -> int {
+                        LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSDW_SMEM_BYTES));
+                        int occ = 1;
+                        LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PSDW_WARPS * 32, PSDW_SMEM_BYTES));
+                        if (occ < 1) occ = 1;
+                        size_t blocks = ceil_div(n_items, (size_t)PSDW_WARPS);
+                        const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+                        if (blocks > max_blocks) blocks = max_blocks;
+                        kern<<<(unsigned)blocks, PSDW_WARPS * 32, PSDW_SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
+                        LRC_CUDA(cudaGetLastError());
+                        return LRC_OK;
+                    };
+                    switch (variant) {
+                        case 10: return launch_w(psd1024_warp_kernel<3, 0>);
+                        case 11: return launch_w(psd1024_warp_kernel<4, 1>);
+                        case 12: return launch_w(psd1024_warp_kernel<3, 2>);
+                        case 13: return launch_w(psd1024_warp_kernel<4, 2>);
+                        default: return launch_w(psd1024_warp_kernel<3, 1>);
+                    }
+                }
+            }
             switch (variant) {      // tuning variants (tools/bench_kernels.py); 0 is the shipped one
                 case 1: return go(psd_tma_kernel<LOG2N, 2, 4, false>, PsdTmaCfg<LOG2N, 2>{});
                 case 2: return go(psd_tma_kernel<LOG2N, 3, 2, true>, PsdTmaCfg<LOG2N, 3>{});
                 case 3: return go(psd_tma_kernel<LOG2N, 2, 3, false>, PsdTmaCfg<LOG2N, 2>{});
-                default: return go(psd_tma_kernel<LOG2N, 3, 3, false>, PsdTmaCfg<LOG2N, 3>{});
+                default: return go(psd_tma_kernel<LOG2N, 3, 3, false>, PsdTmaCfg<LOG2N, 3>{});   // also variant 4
             }
         }
     }
@@ -573,7 +724,10 @@ extern "C" int lrc_psd_run(lrc_psd *p, const float *d_in, size_t n_frames, size_
     LRC_REQUIRE(d_in && d_rows, LRC_ERR_INVALID, "lrc_psd_run: null buffer");
     LRC_REQUIRE(((uintptr_t)d_in & 7) == 0, LRC_ERR_INVALID, "lrc_psd_run: input must be 8-byte aligned");
     cudaStream_t s = lrc_stream(p->ctx, stream);
-    const size_t fpi = lrc_psd_frames_per_item(k_avg);
+    size_t fpi = lrc_psd_frames_per_item(k_avg);
+    // the grouping of frames into items is a function of k_avg alone, so results do not depend on the launch
+    // or on how a stream is sharded (finer items were measured slower: 16 -> 8 costs 2 %, -> 4 costs 9 %)
+    if (const char *e = getenv("LRC_PSD_FPI")) { const size_t v = (size_t)atoi(e); if (v >= 1 && v <= k_avg) fpi = v; }
     const size_t ipr = ceil_div(k_avg, fpi);
     const size_t n_items = n_rows * ipr;
     int rc = lrc_psd_ensure_partial(&p->d_partial, &p->partial_cap, n_items * (size_t)p->nfft);
