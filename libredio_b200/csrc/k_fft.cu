@@ -568,6 +568,83 @@ psd1024_warp_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw
     }
 }
 
+// Same transform, frames double-buffered in REGISTERS: the 32 loads of the warp's next frame are issued before
+// the current frame is transformed, so a full frame of arithmetic (~760 issue slots) covers the HBM latency and
+// no warp ever sits in a pure load phase.  Costs 64 more registers (2 CTAs of 4 warps per SM instead of 3).
+// The frame loop is unrolled by two so the buffers ping-pong without register moves.
+template <int MINB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+psd1024_warp_db_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
+                       float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
+{
+    using F = WarpFFT1024<false>;
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) float2 psdw_sm[];
+    float2 *tws = psdw_sm + WARPS * F::SMEM_CPX;
+    float *wsm = reinterpret_cast<float *>(tws + F::TW_CPX);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[i] = win[i];
+    F::fill_twiddles(tw, tws);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *xb = psdw_sm + warp * F::SMEM_CPX;
+    const float *wl = wsm + lane;
+    const size_t stride = (size_t)gridDim.x * WARPS;
+
+    struct Cur { size_t item, f, f1; bool valid; };
+    auto setup = [&](size_t item) -> Cur {
+        Cur c;
+        c.item = item;
+        c.valid = item < n_items;
+        const size_t row = item / ipr, col = item % ipr;
+        c.f = row * k_avg + col * fpi;
+        c.f1 = c.f + fpi;
+        if (c.f1 > (row + 1) * k_avg) c.f1 = (row + 1) * k_avg;
+        return c;
+    };
+    auto next_of = [&](const Cur &c) -> Cur {
+        if (c.f + 1 < c.f1) { Cur n = c; n.f = c.f + 1; return n; }
+        return setup(c.item + stride);
+    };
+    auto load = [&](float2 *b, const Cur &c) {
+        if (c.valid) {
+            const float2 *src = in + c.f * N + lane;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) b[e] = __ldcs(src + 32 * e);
+        }
+    };
+    float acc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+    auto compute = [&](float2 *v, const Cur &c) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const float w = wl[32 * e];
+            v[e] = mul2(v[e], make_float2(w, w));
+        }
+        F::run(v, xb, tws, lane);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, acc[e]));
+        if (c.f + 1 == c.f1) {
+            float *dst = partial + c.item * N + lane;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { dst[32 * e] = acc[e]; acc[e] = 0.f; }
+        }
+    };
+
+    float2 a[32], b[32];
+    Cur cur = setup((size_t)blockIdx.x * WARPS + warp);
+    load(a, cur);
+    while (cur.valid) {
+        const Cur nxt = next_of(cur);
+        load(b, nxt);
+        compute(a, cur);
+        if (!nxt.valid) break;
+        cur = next_of(nxt);
+        load(a, cur);
+        compute(b, nxt);
+    }
+}
+
 __global__ void psd_reduce_kernel(const float *__restrict__ partial, float *__restrict__ rows, int nfft,
                                   size_t ipr, size_t n_rows, float scale, int accumulate)
 {
@@ -605,15 +682,16 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
             };
             if constexpr (LOG2N == 10) {
                 if (variant == 0 || variant >= 10) {
-                    auto launch_w = [&](auto kern) -> int {
-                        LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSDW_SMEM_BYTES));
+                    auto launch_w = [&](auto kern, int warps = PSDW_WARPS) -> int {
+                        const int smem = (warps * WarpFFT1024<false>::SMEM_CPX + WarpFFT1024<false>::TW_CPX) * 8 + 1024 * 4;
+                        LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                         int occ = 1;
-                        LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PSDW_WARPS * 32, PSDW_SMEM_BYTES));
+                        LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
                         if (occ < 1) occ = 1;
-                        size_t blocks = ceil_div(n_items, (size_t)PSDW_WARPS);
+                        size_t blocks = ceil_div(n_items, (size_t)warps);
                         const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
                         if (blocks > max_blocks) blocks = max_blocks;
-                        kern<<<(unsigned)blocks, PSDW_WARPS * 32, PSDW_SMEM_BYTES, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
+                        kern<<<(unsigned)blocks, warps * 32, smem, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
                         LRC_CUDA(cudaGetLastError());
                         return LRC_OK;
                     };
@@ -622,6 +700,9 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
                         case 11: return launch_w(psd1024_warp_kernel<4, 1>);
                         case 12: return launch_w(psd1024_warp_kernel<3, 2>);
                         case 13: return launch_w(psd1024_warp_kernel<4, 2>);
+                        case 14: return launch_w(psd1024_warp_db_kernel<2, 4>, 4);
+                        case 15: return launch_w(psd1024_warp_db_kernel<1, 8>, 8);
+                        case 16: return launch_w(psd1024_warp_db_kernel<3, 4>, 4);
                         default: return launch_w(psd1024_warp_kernel<3, 1>);
                     }
                 }

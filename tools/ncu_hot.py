@@ -16,7 +16,12 @@ def main():
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    body = []
+    for r in rows[hi + 1:]:                    # first kernel of the report only
+        if r and r[0] in ("Kernel Name", "Address"):
+            break
+        if len(r) == len(hdr):
+            body.append(r)
     tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
     agg = {}
     for r in body:
