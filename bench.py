@@ -7,8 +7,9 @@ step   : one pass of the fused chain kernel over one batch of synthetic cf32 sam
          65536 frames = 2^26 decimated samples into the FFT (configs[1]) = 671 088 694 input samples (5.4 GB),
          much larger than the 126 MB L2, so no L2 flush is needed between steps.
 N > 1  : one process per GPU (torchrun); each rank owns an independent stream of the same size (weak
-         scaling, channels sharded across GPUs); the only exchange is an NCCL all-gather of the 4 MB of
-         output rows per rank over NVLink, inside the timed region.
+         scaling, channels sharded across GPUs); the only exchange is the gather of the 4 MB of output rows
+         per rank over NVLink, inside the timed region: lrc_gather (copy-engine P2P pushes, no SMs) by
+         default, NCCL all-gather with --gather nccl or when CUDA IPC is unavailable.
 e2e    : the same step through the host-buffer entry point lrc_chain_run_host (pinned host input, chunked
          H2D overlapped with the kernel through the double-buffered device ring, rows copied back).
 --impl reference : the reference's own CPU path (oracle/: strict-f32 restatement of dsputils::convolve +
@@ -254,21 +255,49 @@ def run_ours(args):
     rows = frames // K_AVG
     # two output slots: the NVLink gather of step i (NCCL's stream) overlaps the kernel of step i+1
     outs = [torch.empty((rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
-    gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
     pending = [None, None]
+    # the only exchange: every rank's output rows go to every peer.  Default: lrc_gather (copy engines over NVLink,
+    # zero SMs, overlaps the next step's persistent kernel); fallback / --gather nccl: NCCL all-gather, whose kernel
+    # cannot start while the chain kernel fills every SM and therefore serialises with it.
+    gather, gather_kind, gath = None, "none (1 GPU)", None
+    if world > 1:
+        ok = torch.zeros(1, device=dev)
+        if args.gather == "ce":
+            try:
+                gather = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
+                ok += 1
+            except Exception as e:                         # e.g. CUDA IPC not permitted in this container
+                print(f"bench.py rank {rank}: lrc_gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+                gather = None
+        dist.all_reduce(ok)                                # all ranks must agree on the mechanism
+        if int(ok.item()) != world:
+            if gather is not None:
+                gather.close()
+            gather = None
+        if gather is None:
+            gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
+            gather_kind = "NCCL all_gather_into_tensor of output rows (async, 2 slots)"
+        else:
+            gather_kind = "lrc_gather: copy-engine P2P push of output rows into every peer's slot (CUDA IPC, 2 slots)"
 
     def step(i):
         b = i & 1
-        if pending[b] is not None:
+        if gather is not None:
+            gather.wait_sent(b)                            # slot reuse: the previous push must have read outs[b]
+        elif pending[b] is not None:
             pending[b].wait()                              # slot reuse: its previous gather must be done
             pending[b] = None
         chain.run(x, K_AVG, outs[b])
-        if world > 1:                                      # the only exchange: all-gather of the output rows
+        if gather is not None:
+            gather.push(b, outs[b])
+        elif world > 1:
             pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
 
     def drain():
         for b in range(2):
-            if pending[b] is not None:
+            if gather is not None:
+                gather.wait(b)                             # every peer's rows for this slot have ARRIVED here
+            elif pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
 
@@ -292,13 +321,17 @@ def run_ours(args):
     ev[0].record()
     for i in range(args.steps):
         b = i & 1
-        if pending[b] is not None:
+        if gather is not None:
+            gather.wait_sent(b)
+        elif pending[b] is not None:
             pending[b].wait()
             pending[b] = None
         kev[i][0].record()
         chain.run(x, K_AVG, outs[b])
         kev[i][1].record()
-        if world > 1:
+        if gather is not None:
+            gather.push(b, outs[b])
+        elif world > 1:
             pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
         if i == args.steps - 1:
             drain()                                        # the last gathers are inside the timed region
@@ -306,6 +339,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if gather is not None:
+        # the gathered rows must be what an NCCL all-gather of the same outputs gives (every step computes the same
+        # rows from the same resident input, so both slots hold the final result of every rank)
+        torch.cuda.synchronize()
+        for b in range(2):
+            want = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(want, outs[b])
+            got = gather.buffer(b).reshape(world * rows, NFFT)
+            if not torch.equal(got, want):
+                raise SystemExit(f"bench.py rank {rank}: lrc_gather slot {b} differs from the NCCL all-gather")
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     clocks = None
@@ -406,7 +449,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(frames), "ntaps": NTAPS, "decim": DECIM, "nfft": NFFT, "k_avg": K_AVG,
                        "window": "hann", "l2": "input 5.4 GB per step >> 126 MB L2, no flush needed",
-                       "sharding": f"{world} independent streams, one per GPU; all-gather of output rows only",
+                       "sharding": f"{world} independent streams, one per GPU; gather of output rows only",
+                       "gather": gather_kind,
                        "e2e_workload": workload_name(e2e_frames) + f", {e2e_steps} steps through lrc_chain_run_host"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "chain_kernel<64,10,10,7> (+ psd_reduce)",
@@ -424,6 +468,10 @@ def run_ours(args):
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    if gather is not None:
+        gather.close()
     chain.close()
     ctx.close()
     if world > 1:
@@ -442,6 +490,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1.5, dest="cpu_seconds",
                     help="per-thread seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
+                    help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -246,6 +246,37 @@ int lrc_eat(const uint8_t *bits, size_t nbits, const size_t *widths, size_t n_wi
  * OOK kernels use (exhaustive parity hook); d_table is 65536 f32, index b0*256 + b1 */
 int lrc_ook_envelope_table(lrc_ctx *ctx, float *d_table, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (e) Output gather across GPUs over NVLink.  The reference moves results between blocks by
+ *     sending the Vec down an mpsc channel (src/kpn/src/kpn.rs:127-131, e.g. `v.send(x).unwrap()` kpn.rs:27);
+ *     when the producer blocks are sharded over several GPUs this is that send: every rank pushes its
+ *     output block into block `rank` of every peer's receive buffer with the copy engines (no SMs, no
+ *     collective, overlaps the next kernel).  One process per GPU: exchange lrc_gather_export() blobs
+ *     (any host transport, e.g. torch.distributed all_gather_object) and lrc_gather_connect(); several
+ *     contexts in ONE process (kpn thread-per-block graphs): lrc_gather_connect_local().
+ *     Receive buffer of a slot: `world` blocks, block r at  *d_ptr + r * *block_stride  (lrc_gather_buffer).
+ *     SPMD contract: every rank pushes a given slot the same number of times; before a slot is pushed again
+ *     its readers must be done with it (the application's flow control -- `slots` steps of slack or a
+ *     consumer-side handshake; the kpn wrapper uses one slot per in-flight batch).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lrc_gather lrc_gather;
+int    lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, lrc_gather **g);
+int    lrc_gather_destroy(lrc_gather *g);
+size_t lrc_gather_handle_bytes(void);
+int    lrc_gather_export(lrc_gather *g, void *h_handle, size_t cap);
+/* h_handles: `world` handles of lrc_gather_handle_bytes() each, ordered by rank (own entry ignored) */
+int    lrc_gather_connect(lrc_gather *g, const void *h_handles);
+int    lrc_gather_connect_local(lrc_gather *g, lrc_gather *const *all /* world objects, all[r]->rank == r */);
+/* after the work queued on `stream` (the producer of d_src) completes, copy bytes_per_rank bytes from d_src to
+ * every rank's receive slot and raise their arrival flags; asynchronous */
+int    lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void *stream);
+/* order `stream` behind this rank's previous push from `slot` having READ its source buffer (so the buffer
+ * may be overwritten by work queued on `stream` afterwards) */
+int    lrc_gather_wait_sent(lrc_gather *g, int slot, void *stream);
+/* order `stream` behind the ARRIVAL of every rank's latest push into this rank's `slot` */
+int    lrc_gather_wait(lrc_gather *g, int slot, void *stream);
+int    lrc_gather_buffer(lrc_gather *g, int slot, void **d_ptr, size_t *block_stride);
+
 #ifdef __cplusplus
 }
 #endif

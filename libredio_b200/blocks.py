@@ -442,3 +442,71 @@ def ook_envelope_table(ctx: Context) -> torch.Tensor:
     t = torch.empty(65536, dtype=torch.float32, device=ctx.tdev)
     check(ctx.lib.lrc_ook_envelope_table(ctx.h, _p(t), _stream()), "lrc_ook_envelope_table")
     return t.reshape(256, 256)
+
+
+# ---- (e) output gather over NVLink ---------------------------------------------------------------
+class Gather:
+    """Copy-engine gather of equally sized per-rank output blocks (include/libredio_cuda.h "(e)"): the multi-GPU
+    form of the reference's `v.send(x)` between blocks (src/kpn/src/kpn.rs:127-131).  One process per GPU:
+    `Gather(ctx, rank, world, nbytes, slots).connect_distributed()`; several contexts in one process:
+    `Gather.connect_local([g0, g1, ...])`."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, bytes_per_rank: int, slots: int = 2):
+        self.ctx, self.rank, self.world, self.bytes_per_rank, self.slots = ctx, rank, world, bytes_per_rank, slots
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_gather_create(ctx.h, rank, world, bytes_per_rank, slots, C.byref(self.h)), "lrc_gather_create")
+
+    def export(self) -> bytes:
+        n = self.ctx.lib.lrc_gather_handle_bytes()
+        buf = C.create_string_buffer(n)
+        check(self.ctx.lib.lrc_gather_export(self.h, buf, n), "lrc_gather_export")
+        return buf.raw
+
+    def connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        check(self.ctx.lib.lrc_gather_connect(self.h, C.c_char_p(blob)), "lrc_gather_connect")
+
+    def connect_distributed(self, group=None):
+        """Exchange the IPC handles through torch.distributed (host objects) and map every peer."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return self
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.export(), group=group)
+        self.connect(handles)
+        dist.barrier(group=group)              # nobody pushes before everybody has mapped everybody
+        return self
+
+    @staticmethod
+    def connect_local(gathers: list["Gather"]):
+        arr = (C.c_void_p * len(gathers))(*[g.h for g in gathers])
+        for g in gathers:
+            check(g.ctx.lib.lrc_gather_connect_local(g.h, arr), "lrc_gather_connect_local")
+
+    def push(self, slot: int, src: torch.Tensor):
+        assert src.is_cuda and src.is_contiguous() and src.numel() * src.element_size() == self.bytes_per_rank
+        check(self.ctx.lib.lrc_gather_push(self.h, slot, _p(src), _stream()), "lrc_gather_push")
+
+    def wait_sent(self, slot: int):
+        check(self.ctx.lib.lrc_gather_wait_sent(self.h, slot, _stream()), "lrc_gather_wait_sent")
+
+    def wait(self, slot: int):
+        check(self.ctx.lib.lrc_gather_wait(self.h, slot, _stream()), "lrc_gather_wait")
+
+    def buffer(self, slot: int, dtype=torch.float32) -> torch.Tensor:
+        """The slot's receive buffer as a [world, elems_per_rank] tensor view (no copy)."""
+        ptr, stride = C.c_void_p(), C.c_size_t()
+        check(self.ctx.lib.lrc_gather_buffer(self.h, slot, C.byref(ptr), C.byref(stride)), "lrc_gather_buffer")
+        es = torch.empty(0, dtype=dtype).element_size()
+        assert stride.value % es == 0 and self.bytes_per_rank % es == 0
+        iface = {"shape": (self.world, stride.value // es), "typestr": np.dtype(torch.empty(0, dtype=dtype).numpy().dtype).str,
+                 "data": (ptr.value, False), "version": 3}
+        holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
+        t = torch.as_tensor(holder, device=self.ctx.tdev)
+        self._keep = holder
+        return t[:, : self.bytes_per_rank // es]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lrc_gather_destroy(self.h)
+            self.h = C.c_void_p()

@@ -90,6 +90,16 @@ SIGNATURES = {
     "lrc_ook_debug_ptrs": (_i, [_vp, _pp, _pp, _pp, _pp]),
     "lrc_eat": (_i, [_vp, _sz, _vp, _sz, _vp]),
     "lrc_ook_envelope_table": (_i, [_vp, _fp, _vp]),
+    "lrc_gather_create": (_i, [_vp, _i, _i, _sz, _i, _pp]),
+    "lrc_gather_destroy": (_i, [_vp]),
+    "lrc_gather_handle_bytes": (_sz, []),
+    "lrc_gather_export": (_i, [_vp, _vp, _sz]),
+    "lrc_gather_connect": (_i, [_vp, _vp]),
+    "lrc_gather_connect_local": (_i, [_vp, _pp]),
+    "lrc_gather_push": (_i, [_vp, _i, _vp, _vp]),
+    "lrc_gather_wait_sent": (_i, [_vp, _i, _vp]),
+    "lrc_gather_wait": (_i, [_vp, _i, _vp]),
+    "lrc_gather_buffer": (_i, [_vp, _i, _pp, _szp]),
 }
 
 _lib = None

@@ -1,0 +1,229 @@
+// k_gather.cu -- output gather over NVLink with the copy engines (the path shards into independent
+// units; the ONLY inter-GPU traffic is moving each rank's output block to its peers).
+//
+// The reference has no multi-GPU story at all (threads + mpsc channels, kpn.rs:127-131); this is the piece that
+// replaces "send the result Vec down the channel" when the producer blocks live on different GPUs.
+//
+// Why not ncclAllGather: the compute kernels are persistent and fill every SM (2 CTAs/SM of the chain kernel), so an
+// NCCL kernel launched beside them only starts once they drain -- the gather serialises with the compute and costs
+// 8 % of a step at 2 GPUs.  Here every rank owns a receive buffer [slot][src_rank][bytes_per_rank] that its peers
+// map through CUDA IPC (one process per GPU) or plain peer access (several contexts in one process), and a push is
+// `world` cudaMemcpyAsync D2D copies on a dedicated stream: copy engines over NVLink 5 / NVSwitch, zero SMs, fully
+// overlapped with the next step's kernel.  Arrival is signalled by a 32-bit sequence number written into the
+// receiver's flag word by the same stream (cuStreamWriteValue32, ordered after the data copy); consumers order a
+// stream behind it with cuStreamWaitValue32 -- no host round trip, no collective.
+#include "common.cuh"
+#include <cuda.h>
+
+constexpr int GATHER_MAX_WORLD = 64;
+constexpr size_t GATHER_ALIGN = 256;
+
+typedef CUresult (*write32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+struct lrc_gather {
+    lrc_ctx     *ctx;
+    int          rank, world, slots;
+    size_t       bytes_per_rank, block_stride, slot_stride, flags_off, total_bytes;
+    uint8_t     *base;                          // this rank's receive buffer (+ flag words)
+    uint8_t     *peer[GATHER_MAX_WORLD];        // peers' receive buffers mapped into this process
+    bool         opened[GATHER_MAX_WORLD];      // mapped with cudaIpcOpenMemHandle (must be closed)
+    bool         connected;
+    cudaStream_t push_stream;
+    cudaEvent_t  ev_src;                        // producer stream -> push stream
+    cudaEvent_t *ev_sent;                       // per slot: this rank's pushes have left the source buffer
+    uint32_t    *seq;                           // per slot: pushes issued so far
+    write32_fn   write32;
+    wait32_fn    wait32;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static uint8_t *slot_block(const lrc_gather *g, uint8_t *base, int slot, int src)
+{
+    return base + (size_t)slot * g->slot_stride + (size_t)src * g->block_stride;
+}
+static uint8_t *flag_word(const lrc_gather *g, uint8_t *base, int slot, int src)
+{
+    return base + g->flags_off + ((size_t)slot * g->world + src) * sizeof(uint32_t);
+}
+
+extern "C" int lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, lrc_gather **out)
+{
+    LRC_BIND(ctx);
+    LRC_REQUIRE(out != nullptr, LRC_ERR_INVALID, "lrc_gather_create: null out");
+    LRC_REQUIRE(world >= 1 && world <= GATHER_MAX_WORLD && rank >= 0 && rank < world, LRC_ERR_INVALID,
+                "lrc_gather_create: need 0 <= rank < world <= 64");
+    LRC_REQUIRE(slots >= 1 && slots <= 64 && bytes_per_rank > 0, LRC_ERR_INVALID,
+                "lrc_gather_create: need 1 <= slots <= 64 and bytes_per_rank > 0");
+    lrc_gather *g = new (std::nothrow) lrc_gather();
+    LRC_REQUIRE(g != nullptr, LRC_ERR_NOMEM, "out of host memory");
+    g->ctx = ctx; g->rank = rank; g->world = world; g->slots = slots;
+    g->bytes_per_rank = bytes_per_rank;
+    g->block_stride = align_up(bytes_per_rank, GATHER_ALIGN);
+    g->slot_stride = g->block_stride * world;
+    g->flags_off = g->slot_stride * slots;
+    g->total_bytes = g->flags_off + align_up((size_t)slots * world * sizeof(uint32_t), GATHER_ALIGN);
+    g->connected = false;
+    for (int i = 0; i < GATHER_MAX_WORLD; ++i) { g->peer[i] = nullptr; g->opened[i] = false; }
+    void *fw = nullptr, *fq = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &fw, cudaEnableDefault, &qr);
+    if (e == cudaSuccess) e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fq, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || !fw || !fq) {
+        delete g;
+        lrc_set_error("lrc_gather_create: the driver does not export cuStreamWriteValue32/cuStreamWaitValue32");
+        return LRC_ERR_UNSUPPORTED;
+    }
+    g->write32 = reinterpret_cast<write32_fn>(fw);
+    g->wait32 = reinterpret_cast<wait32_fn>(fq);
+    // plain cudaMalloc: IPC handles cannot be taken from pool / virtual-memory allocations
+    e = cudaMalloc(reinterpret_cast<void **>(&g->base), g->total_bytes);
+    if (e != cudaSuccess) {
+        delete g;
+        lrc_set_error("lrc_gather_create: cudaMalloc(%zu) -> %s", g->total_bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? LRC_ERR_NOMEM : LRC_ERR_CUDA;
+    }
+    LRC_CUDA(cudaMemset(g->base, 0, g->total_bytes));
+    LRC_CUDA(cudaStreamCreateWithFlags(&g->push_stream, cudaStreamNonBlocking));
+    LRC_CUDA(cudaEventCreateWithFlags(&g->ev_src, cudaEventDisableTiming));
+    g->ev_sent = new cudaEvent_t[slots];
+    g->seq = new uint32_t[slots]();
+    for (int s = 0; s < slots; ++s) LRC_CUDA(cudaEventCreateWithFlags(&g->ev_sent[s], cudaEventDisableTiming));
+    g->peer[rank] = g->base;
+    if (world == 1) g->connected = true;
+    *out = g;
+    return LRC_OK;
+}
+
+extern "C" int lrc_gather_destroy(lrc_gather *g)
+{
+    if (!g) return LRC_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->push_stream);
+    for (int p = 0; p < g->world; ++p)
+        if (g->opened[p]) cudaIpcCloseMemHandle(g->peer[p]);
+    for (int s = 0; s < g->slots; ++s) cudaEventDestroy(g->ev_sent[s]);
+    cudaEventDestroy(g->ev_src);
+    cudaStreamDestroy(g->push_stream);
+    cudaFree(g->base);
+    delete[] g->ev_sent;
+    delete[] g->seq;
+    delete g;
+    return LRC_OK;
+}
+
+extern "C" size_t lrc_gather_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int lrc_gather_export(lrc_gather *g, void *h_handle, size_t cap)
+{
+    LRC_REQUIRE(g && h_handle, LRC_ERR_INVALID, "lrc_gather_export: null argument");
+    LRC_BIND(g->ctx);
+    LRC_REQUIRE(cap >= sizeof(cudaIpcMemHandle_t), LRC_ERR_CAPACITY, "lrc_gather_export: handle buffer too small");
+    cudaIpcMemHandle_t h;
+    LRC_CUDA(cudaIpcGetMemHandle(&h, g->base));
+    memcpy(h_handle, &h, sizeof(h));
+    return LRC_OK;
+}
+
+extern "C" int lrc_gather_connect(lrc_gather *g, const void *h_handles)
+{
+    LRC_REQUIRE(g && (h_handles || g->world == 1), LRC_ERR_INVALID, "lrc_gather_connect: null argument");
+    LRC_BIND(g->ctx);
+    LRC_REQUIRE(!g->connected || g->world == 1, LRC_ERR_INVALID, "lrc_gather_connect: already connected");
+    const uint8_t *hb = static_cast<const uint8_t *>(h_handles);
+    for (int p = 0; p < g->world; ++p) {
+        if (p == g->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hb + (size_t)p * sizeof(h), sizeof(h));
+        void *ptr = nullptr;
+        LRC_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        g->peer[p] = static_cast<uint8_t *>(ptr);
+        g->opened[p] = true;
+    }
+    g->connected = true;
+    return LRC_OK;
+}
+
+extern "C" int lrc_gather_connect_local(lrc_gather *g, lrc_gather *const *all)
+{
+    LRC_REQUIRE(g && all, LRC_ERR_INVALID, "lrc_gather_connect_local: null argument");
+    LRC_BIND(g->ctx);
+    for (int p = 0; p < g->world; ++p) {
+        const lrc_gather *o = all[p];
+        LRC_REQUIRE(o && o->world == g->world && o->rank == p && o->slots == g->slots &&
+                    o->bytes_per_rank == g->bytes_per_rank, LRC_ERR_INVALID,
+                    "lrc_gather_connect_local: peers must be created with the same geometry, all[p]->rank == p");
+        if (o->ctx->device != g->ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            LRC_CUDA(e);
+        }
+        g->peer[p] = o->base;
+    }
+    g->connected = true;
+    return LRC_OK;
+}
+
+// Order `stream` (the producer of the NEXT block that will live in the same source buffer) behind the copies of
+// this rank's previous push from `slot`: the source buffer may be overwritten afterwards.
+extern "C" int lrc_gather_wait_sent(lrc_gather *g, int slot, void *stream)
+{
+    LRC_REQUIRE(g && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_wait_sent: bad slot");
+    LRC_BIND(g->ctx);
+    if (g->seq[slot] == 0) return LRC_OK;
+    LRC_CUDA(cudaStreamWaitEvent(lrc_stream(g->ctx, stream), g->ev_sent[slot], 0));
+    return LRC_OK;
+}
+
+extern "C" int lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void *stream)
+{
+    LRC_REQUIRE(g && d_src && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_push: bad argument");
+    LRC_BIND(g->ctx);
+    LRC_REQUIRE(g->connected, LRC_ERR_INVALID, "lrc_gather_push: peers are not connected yet");
+    const uint32_t seq = ++g->seq[slot];
+    LRC_CUDA(cudaEventRecord(g->ev_src, lrc_stream(g->ctx, stream)));
+    LRC_CUDA(cudaStreamWaitEvent(g->push_stream, g->ev_src, 0));
+    for (int i = 0; i < g->world; ++i) {
+        const int p = (g->rank + 1 + i) % g->world;          // start at the right-hand neighbour: spreads the NVSwitch ports
+        LRC_CUDA(cudaMemcpyAsync(slot_block(g, g->peer[p], slot, g->rank), d_src, g->bytes_per_rank,
+                                 cudaMemcpyDeviceToDevice, g->push_stream));
+        const CUresult r = g->write32(reinterpret_cast<CUstream>(g->push_stream),
+                                      reinterpret_cast<CUdeviceptr>(flag_word(g, g->peer[p], slot, g->rank)), seq, 0);
+        if (r != CUDA_SUCCESS) {
+            lrc_set_error("lrc_gather_push: cuStreamWriteValue32 to rank %d -> CUresult %d", p, (int)r);
+            return LRC_ERR_CUDA;
+        }
+    }
+    LRC_CUDA(cudaEventRecord(g->ev_sent[slot], g->push_stream));
+    return LRC_OK;
+}
+
+// Order `stream` behind the arrival of every rank's most recent push into this rank's `slot` (SPMD use: every rank
+// pushes each slot the same number of times, so "most recent" is this rank's own push count for the slot).
+extern "C" int lrc_gather_wait(lrc_gather *g, int slot, void *stream)
+{
+    LRC_REQUIRE(g && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_wait: bad slot");
+    LRC_BIND(g->ctx);
+    const uint32_t seq = g->seq[slot];
+    if (seq == 0) return LRC_OK;
+    cudaStream_t s = lrc_stream(g->ctx, stream);
+    for (int p = 0; p < g->world; ++p) {
+        const CUresult r = g->wait32(reinterpret_cast<CUstream>(s),
+                                     reinterpret_cast<CUdeviceptr>(flag_word(g, g->base, slot, p)), seq,
+                                     CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) {
+            lrc_set_error("lrc_gather_wait: cuStreamWaitValue32 -> CUresult %d", (int)r);
+            return LRC_ERR_CUDA;
+        }
+    }
+    return LRC_OK;
+}
+
+extern "C" int lrc_gather_buffer(lrc_gather *g, int slot, void **d_ptr, size_t *block_stride)
+{
+    LRC_REQUIRE(g && d_ptr && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_buffer: bad argument");
+    *d_ptr = g->base + (size_t)slot * g->slot_stride;
+    if (block_stride) *block_stride = g->block_stride;
+    return LRC_OK;
+}
