@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         L.orc_kissfft_batch.argtypes = [vp, vp, C.c_int, C.c_int, sz, vp, vp]
         L.orc_chain_psd.restype = sz
         L.orc_chain_psd.argtypes = [vp, sz, vp, sz, sz, C.c_int, vp, vp, vp, vp]
+        L.orc_chain_psd_mode.restype = sz
+        L.orc_chain_psd_mode.argtypes = [vp, sz, vp, sz, sz, C.c_int, vp, vp, vp, vp, C.c_int]
         _lib = L
     return _lib
 
@@ -319,8 +321,9 @@ def ref_kiss_fn_ptrs(opt: bool = False):
 
 
 def chain_psd_cpu(x: np.ndarray, taps: np.ndarray, d: int, nfft: int, win: np.ndarray,
-                  use_ref: bool = True, opt: bool = False):
-    """CPU baseline of the headline chain; returns (psd_sum f64[nfft], n_frames)."""
+                  use_ref: bool = True, opt: bool = False, full: bool = False):
+    """CPU baseline of the headline chain; returns (psd_sum f64[nfft], n_frames).  ``full``: the FIR computes every
+    lag like dsputils::convolve (dsputils.rs:30-32) and then keeps every d-th output."""
     x = np.ascontiguousarray(x, dtype=np.complex64)
     taps = np.ascontiguousarray(taps, dtype=np.float32)
     win = np.ascontiguousarray(win, dtype=np.float32)
@@ -329,7 +332,7 @@ def chain_psd_cpu(x: np.ndarray, taps: np.ndarray, d: int, nfft: int, win: np.nd
         a, f = ref_kiss_fn_ptrs(opt)
     else:
         a, f = C.c_void_p(None), C.c_void_p(None)
-    nfr = lib().orc_chain_psd(_ptr(x), x.size, _ptr(taps), taps.size, d, nfft, _ptr(win), _ptr(psd), a, f)
+    nfr = lib().orc_chain_psd_mode(_ptr(x), x.size, _ptr(taps), taps.size, d, nfft, _ptr(win), _ptr(psd), a, f, int(full))
     return psd, int(nfr)
 
 

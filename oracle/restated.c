@@ -514,6 +514,15 @@ size_t orc_chain_psd(const orc_cpx *x, size_t n, const float *taps, size_t m, si
                      int nfft, const float *window, double *psd,
                      orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn)
 {
+    return orc_chain_psd_mode(x, n, taps, m, d, nfft, window, psd, alloc_fn, fft_fn, 0);
+}
+
+/* full = 1: the FIR is dsputils::convolve as written (dsputils.rs:30-32: EVERY lag is computed) followed by
+ * keeping every d-th output -- the composition a LibRedio user has today; full = 0 computes kept outputs only. */
+size_t orc_chain_psd_mode(const orc_cpx *x, size_t n, const float *taps, size_t m, size_t d,
+                          int nfft, const float *window, double *psd,
+                          orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn, int full)
+{
     if (n < m) return 0;
     size_t nz = (n - m) / d + 1;
     size_t nframes = nz / (size_t)nfft;
@@ -521,7 +530,7 @@ size_t orc_chain_psd(const orc_cpx *x, size_t n, const float *taps, size_t m, si
     orc_cpx *frame = (orc_cpx *)malloc(sizeof(orc_cpx) * (size_t)nfft);
     orc_cpx *spec = (orc_cpx *)malloc(sizeof(orc_cpx) * (size_t)nfft);
     for (size_t f = 0; f < nframes; ++f) {
-        orc_fir_decimate_cf32(x + f * (size_t)nfft * d, (size_t)(nfft - 1) * d + m, taps, m, d, frame, 0);
+        orc_fir_decimate_cf32(x + f * (size_t)nfft * d, (size_t)(nfft - 1) * d + m, taps, m, d, frame, full);
         for (int i = 0; i < nfft; ++i) { frame[i].r *= window[i]; frame[i].i *= window[i]; }
         if (fft_fn) fft_fn(cfg, frame, spec); else orc_fft(nfft, 0, frame, spec);
         for (int i = 0; i < nfft; ++i)            /* tools/psdpng.c:165-166 */

@@ -111,11 +111,17 @@ typedef void  (*orc_kiss_fft_fn)(void *, const orc_cpx *, orc_cpx *);
 size_t orc_chain_psd(const orc_cpx *x, size_t n, const float *taps, size_t m, size_t d,
                      int nfft, const float *window, double *psd,
                      orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn);
+size_t orc_chain_psd_mode(const orc_cpx *x, size_t n, const float *taps, size_t m, size_t d,
+                          int nfft, const float *window, double *psd,
+                          orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn, int full);
 
 #ifdef __cplusplus
 }
 #endif
 size_t orc_kissfft_batch(const orc_cpx *x, orc_cpx *y, int nfft, int inverse, size_t batch,
                          orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn);
+size_t orc_chain_psd_mode(const orc_cpx *x, size_t n, const float *taps, size_t m, size_t d,
+                          int nfft, const float *window, double *psd,
+                          orc_kiss_alloc_fn alloc_fn, orc_kiss_fft_fn fft_fn, int full);
 
 #endif
