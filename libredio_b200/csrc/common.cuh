@@ -182,6 +182,21 @@ __device__ __forceinline__ void tma_load_1d_evict_first(void *smem_dst, const vo
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+// Ampere-style asynchronous 4-byte global -> shared copy (LDGSTS); src_bytes = 0 zero-fills without reading
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// wait until at most N of this thread's committed groups are still in flight
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group()
+{
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
 // order generic-proxy smem accesses before subsequent async-proxy (TMA) writes to the same buffer
 __device__ __forceinline__ void fence_proxy_async()
 {

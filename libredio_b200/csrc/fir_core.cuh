@@ -49,29 +49,36 @@ struct FirTile {
     // u8 IQ window (2 bytes per sample), 4-byte aligned.  The unpack i2f(b) = b/127 - 1 is folded:
     // sum_j h_j (b_j/127 - 1) = sum_j (h_j/127) (b_j - 127), and b - 127 is exact in f32, so the
     // caller passes taps already divided by 127 (in double, on the host).
+    //
+    // This path is FP32-issue bound, not HBM bound (2 B in per sample): the scalar form spent 896 FFMA + 248 FADD
+    // + 248 PRMT + 62 LDS = 1454 issue slots per thread and tile.  Here the I and Q lanes of a sample go through
+    // ONE packed instruction (FFMA2 for the tap product, FADD2 for the bias), the tap broadcast to both lanes:
+    // 448 FFMA2 + 124 FADD2 + 248 PRMT + 62 LDS = 882 slots, which leaves the FMA pipe (1144 lane-cycles) as the
+    // bound.  Each lane still performs exactly fma(x, h, acc) in ascending tap order: results are bit-identical
+    // to the scalar form.
     __device__ __forceinline__ static void run_u8(const uint32_t *sw, const FirTaps<NTAPS> &taps127, float2 *acc)
     {
+        // taps live in registers: a packed instruction takes its broadcast operand from a register, not from
+        // the constant bank
+        float h[NTAPS];
+#pragma unroll
+        for (int k = 0; k < NTAPS; ++k) h[k] = taps127.h[k];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+        const float2 bias = make_float2(8388735.0f, 8388735.0f);
 #pragma unroll
         for (int j = 0; j < WIN; j += 2) {
             const uint32_t w = sw[j / 2];
             // 0x4B0000bb is the float 2^23 + bb; subtracting 2^23 + 127 gives bb - 127 exactly
-            const float i0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - 8388735.0f;
-            const float q0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388735.0f;
-            const float i1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - 8388735.0f;
-            const float q1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - 8388735.0f;
+            const float2 x0 = sub2(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)),
+                                               __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441))), bias);
+            const float2 x1 = sub2(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)),
+                                               __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443))), bias);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int k0 = j - r * DECIM, k1 = k0 + 1;
-                if (k0 >= 0 && k0 < NTAPS) {
-                    acc[r].x = fmaf(i0, taps127.h[k0], acc[r].x);
-                    acc[r].y = fmaf(q0, taps127.h[k0], acc[r].y);
-                }
-                if (k1 >= 0 && k1 < NTAPS) {
-                    acc[r].x = fmaf(i1, taps127.h[k1], acc[r].x);
-                    acc[r].y = fmaf(q1, taps127.h[k1], acc[r].y);
-                }
+                if (k0 >= 0 && k0 < NTAPS) acc[r] = fma2(x0, make_float2(h[k0], h[k0]), acc[r]);
+                if (k1 >= 0 && k1 < NTAPS) acc[r] = fma2(x1, make_float2(h[k1], h[k1]), acc[r]);
             }
         }
     }

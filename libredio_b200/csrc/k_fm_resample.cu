@@ -345,6 +345,183 @@ static int launch_resample_dec(lrc_resampler *r, const float *d_in, size_t n_in,
     return LRC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed variant of the decimator: the scalar kernel above is FP32-ISSUE bound (82 % issue-active, 73 % of the
+// instructions FFMA), not pipe bound.  Here a CTA works on TWO tiles at once (neighbouring work items: two tiles of a
+// channel, or the last tile of one channel and the first of the next), stored INTERLEAVED in shared memory as
+// {A[i], B[i]} pairs, so one LDS.128 yields two consecutive samples of both tiles and one FFMA2 (tap broadcast to
+// both lanes) advances an accumulator of tile A and the matching one of tile B: half the issue slots per FMA.
+// Every output is still the same ascending-tap fmaf chain, so results are bit-identical to the scalar kernel.
+// R is chosen so that the per-thread stride R*M*8 bytes is an odd multiple of 16 bytes (conflict-free LDS.128).
+// ---------------------------------------------------------------------------------------------
+template <int M, int R, int NT>
+struct RsDec2Cfg {
+    static constexpr int TPP = 2 * RS_ZERO_CROSSINGS * M + 1;
+    static constexpr int WIN = (R - 1) * M + TPP;
+    static constexpr int WIN2 = (WIN + 1) / 2 * 2;                         // whole LDS.128s (2 samples of 2 tiles)
+    static constexpr int STEP = R * M;
+    static constexpr int TILE_OUT = R * NT;
+    static constexpr int TILE_IN = (NT - 1) * STEP + WIN2;                 // float2 pairs a tile pair reads
+    static constexpr int SMEM_BYTES = TILE_IN * 8;
+    static_assert((STEP * 8) % 16 == 0, "thread windows must start 16-byte aligned");
+    static_assert(((STEP * 8) / 16) % 2 == 1, "thread stride must be an odd number of 16-byte bank groups");
+};
+
+// The window loop, unrolled by template recursion (a `#pragma unroll` over ~175 iterations of packed builtins is
+// not honoured by the compiler, and thousands of inline-asm statements in one block take minutes to compile):
+// step J loads samples J, J+1 of both tiles with one LDS.128 and feeds the accumulators they belong to.
+template <int M, int R, int TPP, int J, int JEND>
+struct RsDec2Steps {
+    template <class Taps>
+    __device__ __forceinline__ static void run(const float2 *sx, const Taps &taps, float2 *acc)
+    {
+        if constexpr (J < JEND) {
+            const float4 x = *reinterpret_cast<const float4 *>(sx + J);
+            const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k0 = J - r * M, k1 = k0 + 1;
+                if (k0 >= 0 && k0 < TPP) acc[r] = __ffma2_rn(x0, make_float2(taps.g[k0], taps.g[k0]), acc[r]);
+                if (k1 >= 0 && k1 < TPP) acc[r] = __ffma2_rn(x1, make_float2(taps.g[k1], taps.g[k1]), acc[r]);
+            }
+            RsDec2Steps<M, R, TPP, J + 2, JEND>::run(sx, taps, acc);
+        }
+    }
+};
+
+// one tile of one channel as a source of samples: i -> x[first + i] of the virtual row [carry | chunk].  addr() is
+// branch-free: it yields the address of sample i (inside the carry buffer or inside the chunk) and the number of
+// bytes an asynchronous copy may read there (4, or 0 = zero-fill: past the end of the row, or no such tile).
+struct RsTileSrc {
+    RsRow row; size_t first; bool active;
+    __device__ __forceinline__ const float *addr(int i, uint32_t *nbytes) const
+    {
+        const size_t v = first + (size_t)i;
+        const bool in_carry = v < row.hist;
+        const size_t k = v - row.hist;                       // index into the chunk when !in_carry
+        const bool ok = active && (in_carry || k < row.n_in);
+        *nbytes = ok ? 4u : 0u;
+        return ok ? (in_carry ? row.carry + v : row.in + k) : row.in;
+    }
+};
+
+template <int M, int R, int NT, int STAGES>
+__global__ void __launch_bounds__(NT)
+resample_dec2_kernel(const float *__restrict__ carry, const float *__restrict__ in, size_t n_in, size_t in_stride,
+                     size_t n_ch, size_t s0, size_t n_out,
+                     float *__restrict__ out, size_t out_stride, const __grid_constant__ RsTaps<2 * RS_ZERO_CROSSINGS * M + 1> taps)
+{
+    using Cfg = RsDec2Cfg<M, R, NT>;
+    extern __shared__ __align__(16) float2 rs_tile2[];           // STAGES buffers of TILE_IN pairs
+    const int t = threadIdx.x;
+    const size_t tiles_per_ch = (n_out + Cfg::TILE_OUT - 1) / Cfg::TILE_OUT;
+    const size_t n_tiles = tiles_per_ch * n_ch;
+    const size_t n_pairs = (n_tiles + 1) / 2;
+    auto tile_src = [&](size_t w, size_t *c, size_t *o0) {
+        RsTileSrc s;
+        s.active = w < n_tiles;
+        *c = s.active ? w / tiles_per_ch : 0;
+        *o0 = s.active ? (w % tiles_per_ch) * Cfg::TILE_OUT : 0;
+        s.first = s0 + *o0 * M;
+        s.row = RsRow{carry + *c * (size_t)Cfg::TPP, (size_t)(Cfg::TPP - 1), in + *c * in_stride, n_in};
+        return s;
+    };
+    // Fill one stage with the tile pair `pair`: asynchronous 4-byte copies (LDGSTS) straight into the interleaved
+    // tile, zero-filled past the end of a row, one commit group per fill.  All loads of a thread are in flight at
+    // once and nothing is staged in registers (a register-staged fill exposed one HBM round trip per 16 loads and
+    // took 27-60 % of the kernel).  Three paths, cheapest first: both windows inside their rows (no predicates),
+    // both windows past the carry (one compare each), anything else (a channel's first tile starts in the carry).
+    auto fill = [&](size_t pair, float2 *buf) {
+        size_t c_, o_;
+        const RsTileSrc A = tile_src(2 * pair, &c_, &o_), B = tile_src(2 * pair + 1, &c_, &o_);
+        const size_t h = A.row.hist;
+        if (A.first >= h && B.active && B.first >= h) {
+            const float *pa = A.row.in + (A.first - h), *pb = B.row.in + (B.first - h);
+            const size_t na = n_in - (A.first - h), nb = n_in - (B.first - h);
+            if (na >= (size_t)Cfg::TILE_IN && nb >= (size_t)Cfg::TILE_IN) {
+#pragma unroll 4
+                for (int i = t; i < Cfg::TILE_IN; i += NT) {
+                    cp_async4(&buf[i].x, pa + i, 4u);
+                    cp_async4(&buf[i].y, pb + i, 4u);
+                }
+            } else {
+                for (int i = t; i < Cfg::TILE_IN; i += NT) {
+                    const size_t k = (size_t)i;
+                    cp_async4(&buf[i].x, pa + (k < na ? k : 0), k < na ? 4u : 0u);
+                    cp_async4(&buf[i].y, pb + (k < nb ? k : 0), k < nb ? 4u : 0u);
+                }
+            }
+        } else {
+            for (int i = t; i < Cfg::TILE_IN; i += NT) {
+                uint32_t ba, bb;
+                const float *pa = A.addr(i, &ba), *pb = B.addr(i, &bb);
+                cp_async4(&buf[i].x, pa, ba);
+                cp_async4(&buf[i].y, pb, bb);
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (STAGES == 2 && blockIdx.x < n_pairs) fill(blockIdx.x, rs_tile2);
+    int k = 0;
+    for (size_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++k) {
+        float2 *buf = rs_tile2 + (STAGES == 2 ? (k & 1) * Cfg::TILE_IN : 0);
+        if (STAGES == 2) {
+            // the other stage was consumed one iteration ago (trailing barrier): refill it while this one is filtered
+            const size_t next = pair + gridDim.x;
+            if (next < n_pairs) { fill(next, rs_tile2 + ((k & 1) ^ 1) * Cfg::TILE_IN); cp_async_wait_group<1>(); }
+            else cp_async_wait_group<0>();
+        } else {
+            fill(pair, buf);
+            cp_async_wait_group<0>();
+        }
+        __syncthreads();
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+        const float2 *sx = buf + t * Cfg::STEP;
+        RsDec2Steps<M, R, Cfg::TPP, 0, Cfg::WIN2>::run(sx, taps, acc);
+        size_t cA, oA, cB, oB;
+        tile_src(2 * pair, &cA, &oA);
+        const bool activeB = tile_src(2 * pair + 1, &cB, &oB).active;
+        float *dA = out + cA * out_stride + oA + (size_t)t * R;
+        const size_t leftA = n_out - oA;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if ((size_t)(t * R + r) < leftA) dA[r] = acc[r].x;
+        if (activeB) {
+            float *dB = out + cB * out_stride + oB + (size_t)t * R;
+            const size_t leftB = n_out - oB;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((size_t)(t * R + r) < leftB) dB[r] = acc[r].y;
+        }
+        __syncthreads();                                       // stage consumed before it is refilled
+    }
+}
+
+template <int M, int R, int NT, int STAGES>
+static int launch_resample_dec2(lrc_resampler *r, const float *d_in, size_t n_in, size_t in_stride, size_t no, float *d_out,
+                                size_t out_stride, cudaStream_t s)
+{
+    using Cfg = RsDec2Cfg<M, R, NT>;
+    constexpr int SMEM = Cfg::SMEM_BYTES * STAGES;
+    auto kern = resample_dec2_kernel<M, R, NT, STAGES>;
+    LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int occ = 1;
+    LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, SMEM));
+    if (occ < 1) occ = 1;
+    const size_t n_pairs = (ceil_div(no, (size_t)Cfg::TILE_OUT) * r->n_ch + 1) / 2;
+    size_t blocks = (size_t)r->ctx->n_sm * occ;
+    if (blocks > n_pairs) blocks = n_pairs;
+    RsTaps<Cfg::TPP> taps;
+    for (int i = 0; i < Cfg::TPP; ++i) taps.g[i] = (float)r->h[Cfg::TPP - 1 - i];      // reversed: correlation form
+    const size_t s0 = (size_t)(r->m_next * (unsigned long long)M - r->n_total);
+    kern<<<(unsigned)blocks, NT, SMEM, s>>>(r->d_carry[r->cur], d_in, n_in, in_stride, r->n_ch, s0, no, d_out, out_stride, taps);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
+}
+
 extern "C" int lrc_resampler_create(lrc_ctx *ctx, double ratio, size_t n_ch, size_t max_chunk, lrc_resampler **out)
 {
     LRC_BIND(ctx);
@@ -455,7 +632,29 @@ extern "C" int lrc_resampler_process(lrc_resampler *r, const float *d_in, size_t
         LRC_REQUIRE(d_out && out_stride >= no, LRC_ERR_CAPACITY, "lrc_resampler_process: output too small "
                     "(the reference sizes it ratio*len + 1, samplerate.rs:64)");
         int rc = -1;
-        if (r->L == 1) {                       // decimators with a register-blocked tile instance
+        // LRC_RS_VARIANT=0 keeps the scalar one-tile kernel (tuning / A-B measurements); default: packed two-tile
+        static const int variant = getenv("LRC_RS_VARIANT") ? atoi(getenv("LRC_RS_VARIANT")) : 1;
+        if (r->L == 1 && variant == 1) {       // packed (FFMA2) two-tile decimators
+            switch (r->M) {
+                case 2: rc = launch_resample_dec2<2, 7, 128, 1>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 3: rc = launch_resample_dec2<3, 6, 128, 1>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                case 5: {
+                    // tuning configurations of the BASELINE shape (240 kHz -> 48 kHz), LRC_RS_CFG = threads*10 + stages.
+                    // Measured on 1024 channels x 240 k samples (profiles/r1_s8_rs_configs.txt): 64 threads x 1 stage
+                    // 387 Gsamples/s, 128 x 1: 380, 64 x 2: 359, 128 x 2: 351 (a second stage halves the resident CTAs and
+                    // loses more than the hidden fill gains), scalar one-tile kernel 333.
+                    static const int cfg = getenv("LRC_RS_CFG") ? atoi(getenv("LRC_RS_CFG")) : 641;
+                    if (cfg == 1282)      rc = launch_resample_dec2<5, 6, 128, 2>(r, d_in, n_in, in_stride, no, d_out, out_stride, s);
+                    else if (cfg == 1281) rc = launch_resample_dec2<5, 6, 128, 1>(r, d_in, n_in, in_stride, no, d_out, out_stride, s);
+                    else if (cfg == 642)  rc = launch_resample_dec2<5, 6, 64, 2>(r, d_in, n_in, in_stride, no, d_out, out_stride, s);
+                    else                  rc = launch_resample_dec2<5, 6, 64, 1>(r, d_in, n_in, in_stride, no, d_out, out_stride, s);
+                    break;
+                }
+                case 6: rc = launch_resample_dec2<6, 5, 128, 1>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
+                default: break;                // M = 4: no conflict-free R, the scalar tile kernel below
+            }
+        }
+        if (rc < 0 && r->L == 1) {             // decimators with a register-blocked tile instance
             switch (r->M) {
                 case 2: rc = launch_resample_dec<2, 6>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
                 case 3: rc = launch_resample_dec<3, 4>(r, d_in, n_in, in_stride, no, d_out, out_stride, s); break;
