@@ -265,7 +265,8 @@ static int chain_launch(lrc_chain *c, const float *d_in, size_t rows_local, size
         int occ = 1;
         LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::SMEM_BYTES));
         if (occ < 1) occ = 1;
-        size_t blocks = (size_t)c->ctx->n_sm * occ;
+        static const size_t gm = lrc_grid_mult("LRC_CHAIN_GRID", 1);
+        size_t blocks = (size_t)c->ctx->n_sm * occ * gm;
         if (blocks > n_items) blocks = n_items;
         FirTaps<64> taps;
         for (int i = 0; i < 64; ++i) taps.h[i] = c->taps[i];

@@ -194,7 +194,8 @@ static int launch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t ba
             LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FFTW_WARPS * 32, FFTW_SMEM_BYTES));
             if (occ < 1) occ = 1;
             size_t blocks = ceil_div(batch, (size_t)FFTW_WARPS);
-            const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+            static const size_t gm = lrc_grid_mult("LRC_FFT_GRID", 16);
+            const size_t max_blocks = (size_t)p->ctx->n_sm * occ * gm;
             if (blocks > max_blocks) blocks = max_blocks;
             kern<<<(unsigned)blocks, FFTW_WARPS * 32, FFTW_SMEM_BYTES, s>>>(in, out, batch, p->d_tw);
             LRC_CUDA(cudaGetLastError());
@@ -689,7 +690,8 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
                         LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
                         if (occ < 1) occ = 1;
                         size_t blocks = ceil_div(n_items, (size_t)warps);
-                        const size_t max_blocks = (size_t)p->ctx->n_sm * occ;
+                        static const size_t gm = lrc_grid_mult("LRC_PSD_GRID", 16);
+                        const size_t max_blocks = (size_t)p->ctx->n_sm * occ * gm;
                         if (blocks > max_blocks) blocks = max_blocks;
                         kern<<<(unsigned)blocks, warps * 32, smem, s>>>(in, p->d_tw, p->d_win, p->d_partial, k_avg, fpi, ipr, n_items);
                         LRC_CUDA(cudaGetLastError());

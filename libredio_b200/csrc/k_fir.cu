@@ -197,7 +197,8 @@ static int fir_launch(lrc_fir *f, const void *d_in, size_t n_ch, size_t n_in, si
         LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, Cfg::SMEM_BYTES));
         if (occ < 1) occ = 1;
         const size_t n_tiles = ceil_div(n_out, (size_t)Cfg::TILE_OUT) * n_ch;
-        size_t blocks = (size_t)f->ctx->n_sm * occ;
+        static const size_t gm = lrc_grid_mult(IS_U8 ? "LRC_FIRU8_GRID" : "LRC_FIR_GRID", IS_U8 ? 16 : 1024);
+        size_t blocks = (size_t)f->ctx->n_sm * occ * gm;
         if (blocks > n_tiles) blocks = n_tiles;
         // TMA needs 16-byte aligned sources: base, channel stride and (always true) tile stride
         const int use_tma = (((uintptr_t)d_in & 15) == 0) && ((in_stride * ES) % 16 == 0);

@@ -9,6 +9,7 @@
 //     y[m] = sum_j h[(mM mod L) + jL] * x[floor(mM/L) - j],  x[<0] = 0   (streaming-causal).
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------
@@ -114,7 +115,9 @@ extern "C" int lrc_fmdemod_run(lrc_ctx *ctx, const float *d_in, size_t n_ch, siz
     cudaStream_t s = lrc_stream(ctx, stream);
     LRC_REQUIRE(n_ch <= 65535, LRC_ERR_UNSUPPORTED, "lrc_fmdemod_run: more than 65535 channels per call");
     size_t bx = ceil_div(ceil_div(n, 8), 256);
-    const size_t cap = ceil_div((size_t)ctx->n_sm * 16, n_ch);
+    // many short CTAs: 0.89 -> 0.97 of the copy bandwidth against 16 CTAs per SM looping (profiles/r1_s8_grid_sweeps.txt)
+    static const size_t capf = lrc_grid_mult("LRC_FM_CAP", 128);
+    const size_t cap = ceil_div((size_t)ctx->n_sm * capf, n_ch);
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     // 128-bit loads and stores need every row start aligned
@@ -512,7 +515,8 @@ static int launch_resample_dec2(lrc_resampler *r, const float *d_in, size_t n_in
     LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, SMEM));
     if (occ < 1) occ = 1;
     const size_t n_pairs = (ceil_div(no, (size_t)Cfg::TILE_OUT) * r->n_ch + 1) / 2;
-    size_t blocks = (size_t)r->ctx->n_sm * occ;
+    static const size_t gm = lrc_grid_mult("LRC_RS_GRID", 1024);
+    size_t blocks = (size_t)r->ctx->n_sm * occ * gm;
     if (blocks > n_pairs) blocks = n_pairs;
     RsTaps<Cfg::TPP> taps;
     for (int i = 0; i < Cfg::TPP; ++i) taps.g[i] = (float)r->h[Cfg::TPP - 1 - i];      // reversed: correlation form
