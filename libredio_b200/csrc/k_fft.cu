@@ -194,7 +194,7 @@ static int launch_fft(const lrc_fft *p, const float2 *in, float2 *out, size_t ba
             LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FFTW_WARPS * 32, FFTW_SMEM_BYTES));
             if (occ < 1) occ = 1;
             size_t blocks = ceil_div(batch, (size_t)FFTW_WARPS);
-            static const size_t gm = lrc_grid_mult("LRC_FFT_GRID", 16);
+            static const size_t gm = lrc_grid_mult("LRC_FFT_GRID", 32);
             const size_t max_blocks = (size_t)p->ctx->n_sm * occ * gm;
             if (blocks > max_blocks) blocks = max_blocks;
             kern<<<(unsigned)blocks, FFTW_WARPS * 32, FFTW_SMEM_BYTES, s>>>(in, out, batch, p->d_tw);
