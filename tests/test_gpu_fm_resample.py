@@ -103,6 +103,61 @@ def test_resampler_streaming_is_chunk_independent(ctx):
     rs.close()
 
 
+@pytest.mark.parametrize("den,n_ch,n", [(2, 1, 3001), (2, 5, 9000), (3, 2, 7001), (4, 3, 5000), (5, 1, 4000), (5, 5, 23_994),
+                                        (6, 2, 12_345)])
+def test_resampler_integer_decimators_many_channels(ctx, den, n_ch, n):
+    """L = 1 decimators run the packed two-tile kernel (M = 2, 3, 5, 6) or the scalar tile kernel (M = 4): odd channel
+    counts (a tile pair whose second half is absent or belongs to the next channel), ragged last tiles, the first tile
+    of every channel starting inside the carried history; every channel against the f64 definition."""
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(100 * den + n_ch)
+    t = np.arange(n)
+    x = np.stack([(np.sin(2 * np.pi * (0.003 + 0.002 * c) * t) + 0.2 * rng.standard_normal(n)).astype(np.float32)
+                  for c in range(n_ch)])
+    rs = blocks.Resampler(ctx, 1.0 / den, n_ch, n)
+    assert (rs.L, rs.M) == (1, den)
+    first = rs.process(dev(x[:, : n // 3], ctx)).cpu().numpy()          # two pushes: the second starts in the carry
+    second = rs.process(dev(x[:, n // 3:], ctx)).cpu().numpy()
+    got = np.concatenate([first, second], axis=1)
+    assert got.shape == (n_ch, (n - 1) // den + 1)
+    for c in range(n_ch):
+        assert D.snr_db(D.resample(x[c], 1.0 / den), got[c]) >= MIN_SNR_DB
+    rs.close()
+
+
+def test_resampler_packed_kernel_is_bit_identical_to_scalar_kernel(tmp_path):
+    """The packed (FFMA2, two tiles per CTA) decimator must produce the same bits as the scalar one-tile kernel it
+    replaced: per output it is the same ascending-tap fma chain.  The kernel choice is read once per process
+    (LRC_RS_VARIANT), so each variant runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from libredio_b200 import blocks\n"
+        "ctx = blocks.Context(0)\n"
+        "rng = np.random.default_rng(11)\n"
+        "outs = []\n"
+        "for den, n_ch, n in ((5, 3, 20_011), (2, 2, 5000), (3, 1, 9001), (6, 4, 7000)):\n"
+        "    x = rng.standard_normal((n_ch, n)).astype(np.float32)\n"
+        "    rs = blocks.Resampler(ctx, 1.0 / den, n_ch, n)\n"
+        "    a = rs.process(torch.from_numpy(np.ascontiguousarray(x[:, :777])).to(ctx.tdev)).cpu().numpy()\n"
+        "    b = rs.process(torch.from_numpy(np.ascontiguousarray(x[:, 777:])).to(ctx.tdev)).cpu().numpy()\n"
+        "    outs.append(np.concatenate([a, b], axis=1).ravel())\n"
+        "    rs.close()\n"
+        "np.save(sys.argv[1], np.concatenate(outs))\n" % root)
+    res = {}
+    for variant in ("0", "1"):
+        path = str(tmp_path / f"rs_variant_{variant}.npy")
+        env = dict(os.environ, LRC_RS_VARIANT=variant)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[variant] = np.load(path)
+    assert res["0"].shape == res["1"].shape and res["0"].size > 10_000
+    assert np.array_equal(res["0"].view(np.uint32), res["1"].view(np.uint32))
+
+
 def test_resampler_unsupported_ratio_is_loud(ctx):
     from libredio_b200 import blocks
     with pytest.raises(capi.LrcError) as e:
