@@ -15,7 +15,7 @@ pub const LRC_WINDOW_NONE: c_int = 0;
 pub const LRC_WINDOW_HANN: c_int = 1;
 
 macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
-opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_rfft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_ook);
+opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_rfft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_ook, lrc_gather);
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -111,4 +111,18 @@ extern "C" {
                               d_runs: *mut *const u32, d_n_bits: *mut *const u32) -> c_int;
     pub fn lrc_eat(bits: *const u8, nbits: size_t, widths: *const size_t, n_widths: size_t, out: *mut size_t) -> c_int;
     pub fn lrc_ook_envelope_table(ctx: *mut lrc_ctx, d_table: *mut c_float, stream: *mut c_void) -> c_int;
+
+    // output gather between GPUs (copy engines over NVLink): the `v.send(x)` of kpn.rs:27 when the producer blocks
+    // are sharded over several devices
+    pub fn lrc_gather_create(ctx: *mut lrc_ctx, rank: c_int, world: c_int, bytes_per_rank: size_t, slots: c_int,
+                             g: *mut *mut lrc_gather) -> c_int;
+    pub fn lrc_gather_destroy(g: *mut lrc_gather) -> c_int;
+    pub fn lrc_gather_handle_bytes() -> size_t;
+    pub fn lrc_gather_export(g: *mut lrc_gather, h_handle: *mut c_void, cap: size_t) -> c_int;
+    pub fn lrc_gather_connect(g: *mut lrc_gather, h_handles: *const c_void) -> c_int;
+    pub fn lrc_gather_connect_local(g: *mut lrc_gather, all: *const *mut lrc_gather) -> c_int;
+    pub fn lrc_gather_push(g: *mut lrc_gather, slot: c_int, d_src: *const c_void, stream: *mut c_void) -> c_int;
+    pub fn lrc_gather_wait_sent(g: *mut lrc_gather, slot: c_int, stream: *mut c_void) -> c_int;
+    pub fn lrc_gather_wait(g: *mut lrc_gather, slot: c_int, stream: *mut c_void) -> c_int;
+    pub fn lrc_gather_buffer(g: *mut lrc_gather, slot: c_int, d_ptr: *mut *mut c_void, block_stride: *mut size_t) -> c_int;
 }

@@ -29,6 +29,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.lrc_version() == 100
 
 
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/libredio-cuda-sys is shipped as source only (no rustc in this image): keep its extern block in step with the
+    header so the reference-side binding a maintainer would build is complete."""
+    txt = open(os.path.join(ROOT, "rust", "libredio-cuda-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\bpub fn (lrc_[a-z0-9_]+)\s*\(", txt))
+    missing = [s for s in header_symbols() if s not in declared]
+    assert not missing, f"missing from the Rust -sys crate: {missing}"
+    stale = sorted(declared - set(header_symbols()))
+    assert not stale, f"declared in Rust but not in the header: {stale}"
+
+
 def test_status_strings_and_host_helper():
     from libredio_b200 import capi
     lib = capi.load()
