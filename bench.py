@@ -275,6 +275,28 @@ def run_ours(args):
             except Exception as e:                         # e.g. CUDA IPC not permitted in this container
                 print(f"bench.py rank {rank}: lrc_gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
                 gather = None
+        # bounded-time probe before the timed loop depends on it: one push + arrival wait per slot on a side stream,
+        # polled from the host.  A peer whose flag write never arrives would otherwise hang the bench inside a
+        # device-side wait.  The probing stream can never drain in that case, so the process cannot fall back: it
+        # fails fast with a message instead (rerun with --gather nccl).
+        if gather is not None:
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                for b in range(2):
+                    gather.push(b, outs[b])
+                    gather.wait(b)
+                pev = torch.cuda.Event()
+                pev.record()
+            t0, probe_stuck = time.perf_counter(), False
+            while not pev.query():
+                if time.perf_counter() - t0 > args.gather_probe_s:
+                    probe_stuck = True
+                    break
+                time.sleep(0.005)
+            if probe_stuck:
+                print(f"bench.py rank {rank}: lrc_gather probe did not complete in {args.gather_probe_s:.0f} s "
+                      "(a peer's arrival flag never came); rerun with --gather nccl", file=sys.stderr, flush=True)
+                os._exit(3)
         dist.all_reduce(ok)                                # all ranks must agree on the mechanism
         if int(ok.item()) != world:
             if gather is not None:
@@ -500,6 +522,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1.5, dest="cpu_seconds",
                     help="per-thread seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
+                    help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
                     help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()
