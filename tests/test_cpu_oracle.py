@@ -222,6 +222,72 @@ def test_ook_chain_decodes_constructed_packets():
 
 
 # ---- north-star-defined stages ---------------------------------------------------------------------------------
+def _same(a: dict, b: dict):
+    assert a["n_bursts"] == b["n_bursts"]
+    for k in ("block_sums", "bits", "run_val", "run_len", "a_packets", "b_packets"):
+        x, y = a[k], b[k]
+        assert x.shape == y.shape, k
+        if x.dtype == np.float32:
+            x, y = x.view(np.uint32), y.view(np.uint32)
+        assert np.array_equal(x, y), k
+
+
+@pytest.mark.parametrize("seed,n_blocks,n_packets", [(4, 420, 2), (7, 300, 1), (11, 520, 3), (23, 64, 0)])
+def test_ook_chain_two_independent_restatements_agree_bit_for_bit(seed, n_blocks, n_packets):
+    """The reference has no test or vector for the OOK chain, so the C restatement (the GPU's oracle) is checked
+    against a second restatement written independently from the same Rust as a network of generator blocks
+    (oracle/restated_py.py): block sums, bursts, bit stream, every run and the packets must be identical."""
+    from oracle import restated_py as P
+    from libredio_b200 import synth                     # synthetic input generator only (numpy, no device code)
+    iq, sent = synth.ook_capture_u8(n_blocks, seed=seed, n_packets=n_packets)
+    a, b = oracle.ook_decode(iq), P.ook_decode(iq)
+    _same(a, b)
+    if n_packets:       # rle never flushes its last run, so the final packet may stay inside the chain (kpn.rs:17-29)
+        assert len(sent) - 1 <= a["a_packets"].shape[0] + a["b_packets"].shape[0] <= len(sent)
+
+
+def test_ook_chain_restatements_agree_on_unstructured_input():
+    """not packets: amplitude steps and noise bursts that drive the threshold arithmetic (bitfount.rs:57-70) through
+    re-triggers, a burst still open at the end of the capture and runs spanning burst boundaries"""
+    from oracle import restated_py as P
+    rng = np.random.default_rng(99)
+    n_blocks = 520
+    n = n_blocks * 512
+    amp = np.zeros(n)
+    pos = 50 * 512
+    k = 0
+    while pos < n - 3000:
+        ln = int(rng.integers(40, 20_000))
+        amp[pos:pos + ln] = rng.uniform(0.05, 0.9)
+        # short gaps keep a burst open (re-trigger, bitfount.rs:68-70); every third gap is long enough (> 50 blocks)
+        # for the counter to run out so that the burst is sent
+        k += 1
+        pos += ln + (int(rng.integers(100, 9000)) if k % 3 else int(rng.integers(56, 70)) * 512)
+    amp[-20_000:] = 0.8                                        # open burst at the end: never sent (bitfount.rs:78-81)
+    ph = rng.uniform(0, 2 * np.pi, n)
+    i = 127 + 127 * amp * np.cos(ph) + 1.5 * rng.standard_normal(n)
+    q = 127 + 127 * amp * np.sin(ph) + 1.5 * rng.standard_normal(n)
+    iq = np.empty(2 * n)
+    iq[0::2], iq[1::2] = i, q
+    iq = np.clip(np.rint(iq), 0, 255).astype(np.uint8)
+    a, b = oracle.ook_decode(iq), P.ook_decode(iq)
+    assert a["n_bursts"] >= 2 and a["run_len"].size > 5
+    _same(a, b)
+
+
+def test_python_restatement_micro_cases():
+    from oracle import restated_py as P
+    assert [float(P.i2f(b)) for b in (0, 127, 254)] == [-1.0, 0.0, 1.0]
+    assert P.i2f(255).view(np.uint32) == oracle.i2f(255).view(np.uint32)
+    assert P.b2d([1, 0, 1]) == 5 and P.eat([1, 0, 1, 1, 1, 1], [3, 3]) == [5, 7]
+    assert list(P.rle(iter([1, 1, 0, 0, 0, 1]))) == [(1, 2), (0, 3)]           # the last run is never flushed
+    assert list(P.shaper_optional(iter([1, 0, None, 1, None, 1, 1, None]), 2)) == [[1, 0], [1, 1]]
+    # matcher A consumes the next run only after a matching pulse (ratpak.rs:91)
+    d = [(1, np.float32(3e-4)), (0, np.float32(2e-3)), (0, np.float32(2e-3)), (1, np.float32(3e-4)), (0, np.float32(4e-3)),
+         (1, np.float32(3e-4)), (0, np.float32(3e-3))]
+    assert list(P.matcher_a(iter(d))) == [0, None, 1, None]
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3
