@@ -288,6 +288,30 @@ def test_python_restatement_micro_cases():
     assert list(P.matcher_a(iter(d))) == [0, None, 1, None]
 
 
+@pytest.mark.parametrize("ratio", [0.2, 0.5, 2.0, 48000 / 44100, 3 / 7])
+def test_resampler_definition_is_plain_polyphase_and_in_sinc_medium_class(ratio):
+    """libsamplerate is absent (parity unpinned), so the f64 definition is checked two ways:
+    (1) it IS the textbook rational polyphase filter -- identical to scipy.signal.upfirdn with the same prototype;
+    (2) the prototype sits in the class of the converter the reference asks for (SRC_SINC_MEDIUM_QUALITY,
+    samplerate.rs:61: ~121 dB SNR, ~90 % bandwidth): >= 120 dB rejection from 1.1x the slower Nyquist on, -6 dB at
+    0.9x, < 0.01 dB ripple over the lower 80 %."""
+    import scipy.signal as ss
+    L, M = D.resampler_ratio(ratio)
+    h = D.resampler_taps(L, M)
+    x = np.random.default_rng(5).standard_normal(5000)
+    y = D.resample(x, ratio)
+    u = ss.upfirdn(h, x, up=L, down=M)[: y.size]
+    assert np.max(np.abs(y - u)) < 1e-12
+    nfft = 1 << 22 if h.size > (1 << 12) else 1 << 20
+    H = np.abs(np.fft.rfft(h, nfft)) / L
+    f = np.arange(H.size) / nfft                        # cycles per sample at the L-times-upsampled rate
+    fc = 0.5 / max(L, M)                                # Nyquist of the slower of the two rates
+    assert 20 * np.log10(H[f >= 1.1 * fc].max()) <= -120.0
+    pb = H[f <= 0.8 * fc]
+    assert 20 * np.log10(pb.max() / pb.min()) < 0.01
+    assert abs(20 * np.log10(H[np.searchsorted(f, 0.9 * fc)]) + 6.02) < 0.1
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3
