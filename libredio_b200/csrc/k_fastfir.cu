@@ -8,13 +8,20 @@
 // registers/shared memory (the forward output layout "thread t holds bin t + e*T" is exactly the
 // inverse input layout), so HBM sees nfft reads and ngood writes per block and nothing else.
 #include "fft_core.cuh"
+#include <cmath>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 using namespace lrfft;
 
 int lrc_make_twiddles(int nfft, float2 **d_tw);
 int lrc_log2_exact(int n);
+// k_fastfir16k.cu (staged nfft = 16384 kernel)
+void lrc_fastfir16k_permute_H(const float2 *H, float2 *Hp);
+int lrc_fastfir16k_prepare(void);
+int lrc_fastfir16k_launch(int n_sm, const float2 *in, size_t n_in, float2 *out, size_t full, size_t nblk, size_t ngood,
+                          size_t keep, const float2 *d_tw16k, const float2 *d_tw1k, const float2 *d_Hp, cudaStream_t s);
 
 struct lrc_fastfir {
     lrc_ctx *ctx;
@@ -22,8 +29,32 @@ struct lrc_fastfir {
     int      log2n;
     float2  *d_tw;
     float2  *d_H;
-    float2  *d_Hc;     // nfft == 8192: H in the order fastfir8k_kernel uses
+    float2  *d_Hc;     // nfft == 8192: H in the order fastfir8k_kernel uses; nfft == 16384: Hp[k1][k2] = H[k1 + 16 k2]
+    float2  *d_tw1k;   // nfft == 16384: W_1024^k for the warp-level sub-transforms
 };
+
+// host-side f64 radix-2 FFT (forward), used only to build H for block sizes our own FFT plans do not cover
+static void host_fft_f64(std::vector<double> &re, std::vector<double> &im)
+{
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    const double pi = 3.14159265358979323846264338327950288;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double a = -2.0 * pi * (double)k / (double)len, c = cos(a), s = sin(a);
+                const size_t u = i + k, v = i + k + len / 2;
+                const double tr = re[v] * c - im[v] * s, ti = re[v] * s + im[v] * c;
+                re[v] = re[u] - tr; im[v] = im[u] - ti;
+                re[u] += tr; im[u] += ti;
+            }
+    }
+}
 
 template <int LOG2N>
 __global__ void __launch_bounds__(CtaFFT<LOG2N, false>::T)
@@ -299,14 +330,44 @@ extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t 
         if (nfft < 1024) nfft = 1024;
     }
     const int l2 = lrc_log2_exact((int)nfft);
-    if (l2 < 1 || l2 > 13 || nfft > 8192) {
+    // nfft = 16384 (75 % useful outputs per block for 4096 taps instead of 50 %): the kernel in k_fastfir16k.cu is
+    // STAGED -- checked once on hardware (profiles/r1_s8_fastfir16k_check.json), its pytest cases not yet -- and only
+    // reachable on request.  The automatic size stays kiss_fastfir's (8192 for 4096 taps): it fixes the output length.
+    const bool staged16k = nfft == 16384 && getenv("LRC_FASTFIR_STAGED") && atoi(getenv("LRC_FASTFIR_STAGED")) == 1;
+    if ((l2 < 1 || l2 > 13 || nfft > 8192) && !staged16k) {
         lrc_set_error("lrc_fastfir_create: nfft=%zu: only powers of two in [2, 8192] (nh <= 4096 with the "
                       "automatic size)", nfft);
         return LRC_ERR_UNSUPPORTED;
     }
     LRC_REQUIRE(nfft >= nh, LRC_ERR_INVALID, "lrc_fastfir_create: nfft shorter than the impulse response");
-    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr, nullptr};
+    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr, nullptr, nullptr};
     LRC_REQUIRE(f != nullptr, LRC_ERR_NOMEM, "out of host memory");
+    if (staged16k) {
+        int rc16 = lrc_make_twiddles(16384, &f->d_tw);
+        if (!rc16) rc16 = lrc_make_twiddles(1024, &f->d_tw1k);
+        if (!rc16) rc16 = lrc_fastfir16k_prepare();
+        if (rc16) { lrc_fastfir_destroy(f); return rc16; }
+        // H = FFT(h rotated) / nfft in f64 on the host (:148-169), rounded once to f32
+        const float2 *h16 = reinterpret_cast<const float2 *>(h_taps_cpx);
+        std::vector<double> re(nfft, 0.0), im(nfft, 0.0);
+        re[0] = h16[nh - 1].x; im[0] = h16[nh - 1].y;
+        for (size_t i = 0; i + 1 < nh; ++i) { re[nfft - nh + 1 + i] = h16[i].x; im[nfft - nh + 1 + i] = h16[i].y; }
+        host_fft_f64(re, im);
+        std::vector<float2> H(nfft), Hp(nfft);
+        for (size_t i = 0; i < nfft; ++i) H[i] = make_float2((float)(re[i] / (double)nfft), (float)(im[i] / (double)nfft));
+        lrc_fastfir16k_permute_H(H.data(), Hp.data());
+        cudaError_t e16 = cudaMalloc(&f->d_H, nfft * sizeof(float2));
+        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_H, H.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e16 == cudaSuccess) e16 = cudaMalloc(&f->d_Hc, nfft * sizeof(float2));
+        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_Hc, Hp.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e16 != cudaSuccess) {
+            lrc_set_error("lrc_fastfir_create: %s", cudaGetErrorString(e16));
+            lrc_fastfir_destroy(f);
+            return LRC_ERR_CUDA;
+        }
+        *out = f;
+        return LRC_OK;
+    }
     int rc = lrc_make_twiddles((int)nfft, &f->d_tw);
     if (rc) { delete f; return rc; }
     // rotated impulse response (:148-154), transformed with our own FFT kernel, scaled by 1/nfft (:159-169)
@@ -348,7 +409,7 @@ extern "C" int lrc_fastfir_destroy(lrc_fastfir *f)
 {
     if (!f) return LRC_OK;
     cudaSetDevice(f->ctx->device);
-    cudaFree(f->d_tw); cudaFree(f->d_H); cudaFree(f->d_Hc);
+    cudaFree(f->d_tw); cudaFree(f->d_H); cudaFree(f->d_Hc); cudaFree(f->d_tw1k);
     delete f;
     return LRC_OK;
 }
@@ -407,6 +468,8 @@ extern "C" int lrc_fastfir_run(lrc_fastfir *f, const float *d_in, size_t n_in, f
     const float2 *in = (const float2 *)d_in;
     float2 *out = (float2 *)d_out;
     static const int variant = getenv("LRC_FASTFIR_VARIANT") ? atoi(getenv("LRC_FASTFIR_VARIANT")) : 1;
+    if (f->nfft == 16384)
+        return lrc_fastfir16k_launch(f->ctx->n_sm, in, n_in, out, full, nblk, f->ngood, keep, f->d_tw, f->d_tw1k, f->d_Hc, s);
     if (f->d_Hc && variant == 1) {
         size_t blocks = (size_t)f->ctx->n_sm * 2;
         if (blocks > nblk) blocks = nblk;

@@ -312,6 +312,25 @@ def test_resampler_definition_is_plain_polyphase_and_in_sinc_medium_class(ratio)
     assert abs(20 * np.log10(H[np.searchsorted(f, 0.9 * fc)]) + 6.02) < 0.1
 
 
+def test_fastfir16k_design_model_is_an_exact_overlap_save():
+    """tools/models/fastfir16k_model.py mirrors, index for index, the data flow of the staged nfft = 16384 kernel
+    (16 x 1024 split, padded rows, warp-level 32 x 32 sub-transforms through the row buffer, factorised P1 twiddles,
+    H stored as Hp[k1][k2]); it must reproduce the direct convolution to f64 accuracy."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models", "fastfir16k_model.py")
+    spec = importlib.util.spec_from_file_location("fastfir16k_model", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(3)
+    nh = 4096
+    h = (rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64
+    x = rng.standard_normal(m.N + 12289) + 1j * rng.standard_normal(m.N + 12289)
+    y = m.fastfir(h, x)
+    assert y.size == 2 * 12289
+    ref = np.convolve(x, h)[nh - 1: nh - 1 + y.size]
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.sqrt(np.mean(np.abs(ref) ** 2))
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3

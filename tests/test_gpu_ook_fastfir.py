@@ -3,6 +3,8 @@
 OOK: every intermediate that the reference computes in f32 (envelope, block sums) must be BIT-identical to
 the CPU restatement, and so must the run lengths and decoded packet bits.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -200,4 +202,49 @@ def test_fastfir_config5_shape_spot_windows(ctx):
         ref = np.array([np.dot(seg[k:k + nh], hr) for k in range(64)])
         got = y[s0:s0 + 64].cpu().numpy()
         assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+    ff.close()
+
+
+# ---- staged: nfft = 16384 blocks (k_fastfir16k.cu) ----------------------------------------------------------
+STAGED = os.environ.get("LRC_FASTFIR_STAGED") == "1"
+
+
+def test_fastfir_nfft_16384_is_refused_unless_staged(ctx):
+    """the 16384-point kernel is written against a verified numpy model (tools/models/fastfir16k_model.py) and was
+    checked once on a B200 (profiles/r1_s8_fastfir16k_check.json), but the cases below have not run on hardware yet:
+    without LRC_FASTFIR_STAGED=1 the plan must be refused loudly, never silently mis-served"""
+    from libredio_b200 import blocks
+    if STAGED:
+        pytest.skip("LRC_FASTFIR_STAGED=1: the staged kernel is enabled in this run")
+    h = np.ones(4096, dtype=np.complex64)
+    with pytest.raises(capi.LrcError) as e:
+        blocks.FastFir(ctx, h, 16384)
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
+@pytest.mark.skipif(not STAGED, reason="staged kernel: run with LRC_FASTFIR_STAGED=1 to validate it on a GPU")
+@pytest.mark.parametrize("nh,n", [(4096, 16384), (4096, 16384 + 12289 * 3 + 100), (4096, 20_000), (1000, 70_000),
+                                  (4096, 1 << 22)])
+def test_fastfir_staged_nfft_16384_vs_oracle(ctx, nh, n):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(nh + n)
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / np.sqrt(nh)).astype(np.complex64)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    ff = blocks.FastFir(ctx, h, 16384)
+    assert ff.nfft == 16384 and ff.ngood == 16384 - nh + 1
+    for flush in (False, True):
+        got = ff.run(dev(x, ctx), flush).cpu().numpy()
+        assert got.shape == (ff.out_len(n, flush),)
+        if n <= 100_000:
+            ref = oracle.fastfir(h, x, 16384, flush)
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+        # true convolution with the transient removed, on windows (incl. block seams)
+        hr = h[::-1].astype(np.complex128)
+        for s0 in [0, ff.ngood - 8, got.size - 64] + [int(v) for v in rng.integers(0, max(1, got.size - 64), 6)]:
+            if s0 < 0 or s0 + 64 > got.size:
+                continue
+            seg = x[s0: s0 + 64 + nh - 1].astype(np.complex128)
+            ref = np.array([np.dot(seg[k:k + nh], hr) for k in range(64)])
+            assert np.max(np.abs(got[s0:s0 + 64] - ref)) <= 1e-4 * rms(ref)
     ff.close()
