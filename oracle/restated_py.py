@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- a second, independent restatement of the bit-exact OOK chain, in plain Python.
+"""TEST INFRASTRUCTURE ONLY -- a second, independent restatement of the stages the reference has no test for (unpack,
+convolve, the bit-exact OOK chain), in plain Python.
 
 oracle/restated.c is the oracle the GPU is held to; the reference holds no test, fixture or golden vector for this
 chain, so the C restatement is pinned by hand-computed micro-cases only.  This module restates the same
@@ -10,6 +11,7 @@ the decoded packets.  Pure-Python loops: small captures only.
 
 Reference (paths relative to the LibRedio tree):
     i2f, data_to_samples      src/rtlsdr/src/rtlsdr.rs:159-162
+    convolve                  src/dsputils/src/dsputils.rs:30-32
     x.norm()                  src/ratpak.rs:64-68 (num 0.1.22 Complex::norm = hypot)
     trigger                   src/bitfount/src/bitfount.rs:36-85
     discretize                src/bitfount/src/bitfount.rs:87-96
@@ -31,6 +33,31 @@ BLOCK = 512                      # samples per message (bitfount.rs:17,24: 1024 
 def i2f(b: int) -> np.float32:
     """rtlsdr.rs:159: i as f32 / 127.0 - 1.0"""
     return F(F(F(b) / F(127.0)) - F(1.0))
+
+
+def data_to_samples(data) -> list:
+    """rtlsdr.rs:160-162: data.chunks(2).map(|i| Complex{re: i2f(i[0]), im: i2f(i[1])}); an odd length indexes
+    i[1] out of bounds and panics"""
+    out = []
+    for k in range(0, len(data), 2):
+        pair = data[k:k + 2]
+        if len(pair) < 2:
+            raise IndexError("index out of bounds: the len is 1 but the index is 1")      # the reference's panic
+        out.append((i2f(int(pair[0])), i2f(int(pair[1]))))
+    return out
+
+
+def convolve(u, v) -> list:
+    """dsputils.rs:30-32: u.windows(v.len()).map(|x| x.iter().zip(v.iter()).map(|(&x,&y)| x*y)
+    .fold(Float::zero(), |a, b| a + b)) -- valid-mode correlation (taps not reversed), every product rounded to f32,
+    summed left to right from 0.0 in f32"""
+    out = []
+    for i in range(len(u) - len(v) + 1):
+        acc = F(0.0)
+        for j in range(len(v)):
+            acc = F(acc + F(F(u[i + j]) * F(v[j])))
+        out.append(acc)
+    return out
 
 
 def rtl_source_cmplx(iq: np.ndarray):

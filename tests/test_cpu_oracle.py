@@ -275,6 +275,26 @@ def test_ook_chain_restatements_agree_on_unstructured_input():
     _same(a, b)
 
 
+def test_unpack_and_convolve_two_independent_restatements_agree_bit_for_bit():
+    """rtlsdr.rs:159-162 and dsputils.rs:30-32 have no test in the reference either: C restatement == Python restatement"""
+    from oracle import restated_py as P
+    rng = np.random.default_rng(17)
+    data = rng.integers(0, 256, 4096, dtype=np.uint8)
+    a = oracle.data_to_samples(data)
+    b = np.array([complex(float(re), float(im)) for re, im in P.data_to_samples(data)], dtype=np.complex64)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    with pytest.raises(IndexError):
+        P.data_to_samples(data[:7])                                # odd length: the reference panics (rtlsdr.rs:161)
+    u = (rng.standard_normal(700) * 3).astype(np.float32)
+    for m in (1, 2, 64, 699, 700):
+        v = rng.standard_normal(m).astype(np.float32)
+        c = oracle.convolve(u, v)
+        p = np.array(P.convolve(u, v), dtype=np.float32)
+        assert c.shape == p.shape == (700 - m + 1,)
+        assert np.array_equal(c.view(np.uint32), p.view(np.uint32))
+    assert P.convolve(u[:3], u[:5]) == [] and oracle.convolve(u[:3], u[:5]).size == 0
+
+
 def test_python_restatement_micro_cases():
     from oracle import restated_py as P
     assert [float(P.i2f(b)) for b in (0, 127, 254)] == [-1.0, 0.0, 1.0]
