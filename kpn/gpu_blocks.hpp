@@ -11,6 +11,7 @@
 //   dsputils::convolve (+/D)  dsputils.rs:30      kpn_gpu::fir_decimate, fir_decimate_multi (channel ring)
 //   (north-star) discriminator                    kpn_gpu::fm_demod
 //   (north-star) FIR->FFT->|X|^2 chain            kpn_gpu::chain_psd
+//   (north-star) config-3 FM receiver, N channels  kpn_gpu::fm_receiver_multi (staged)
 //   trigger..shaper_optional  ratpak.rs:60-111    kpn_gpu::ook_decode
 //
 // Errors: a non-zero status of the C ABI is thrown as std::runtime_error -- the analogue of the
@@ -263,6 +264,85 @@ inline void resample(Gpu &g, Receiver<std::vector<float>> din, Sender<std::vecto
             dout.send(std::vector<float>(p, p + n_out));                                          // set_len(output_frames_gen) :84
         }
     } catch (...) { lrc_resampler_destroy(rs); in.release(g); out.release(g); throw; }
+}
+
+// ---- FM broadcast receiver over MANY channels (BASELINE config 3), device-resident between stages ------
+// rtlsdr u8 IQ chunks in, 48 kHz-style audio chunks out:  fused unpack + FIR/decimate (seam-exact stream state) ->
+// quadrature discriminator (carried x[-1]) -> rational resampler (carried history), three launches per batch with
+// the 1/decim-rate intermediates never leaving the device.  One chunk (chunk_bytes, even) is taken from every
+// channel's port and packed channel-major into a pinned slot; two slots alternate like fir_decimate_multi: while
+// slot A's batch is on the device the block is already packing slot B, and A's audio is scattered to the senders
+// when the block comes back to A.  The reference would wire rtlsdr::data_to_samples -> dsputils::convolve ->
+// (discriminator) -> samplerate::resample with one thread and one channel message per stage and chunk.
+// STAGED: compiled and linked here, exercised by kpn/test_gpu_blocks.cpp only when LRC_TEST_STAGED=1.
+inline void fm_receiver_multi(Gpu &g, std::vector<Receiver<std::vector<uint8_t>>> u, std::vector<Sender<std::vector<float>>> v,
+                              std::vector<float> taps, size_t decim, double ratio, size_t chunk_bytes)
+{
+    g.bind();
+    const size_t n_ch = u.size();
+    if (v.size() != n_ch || n_ch == 0) throw std::invalid_argument("fm_receiver_multi: port count mismatch");
+    if (chunk_bytes == 0 || (chunk_bytes & 1)) throw std::invalid_argument("fm_receiver_multi: chunk_bytes must be even");
+    const size_t chunk = chunk_bytes / 2;                                   // samples per channel and batch
+    const size_t cap_bb = (taps.size() + chunk) / decim + 2;               // decimated samples a batch can yield
+    const size_t cap_bb4 = (cap_bb + 3) / 4 * 4;                            // rows stay 16-byte aligned
+    const size_t cap_au = ((size_t)(ratio * (double)cap_bb + 1.0) + 1 + 3) / 4 * 4;
+    lrc_fir *fir = nullptr; lrc_fir_stream *fs = nullptr; lrc_resampler *rs = nullptr;
+    float *d_bb = nullptr, *d_fm = nullptr, *d_state = nullptr, *d_au = nullptr;
+    check(lrc_fir_create(g.ctx, taps.data(), (int)taps.size(), (int)decim, &fir), "lrc_fir_create");
+    check(lrc_fir_stream_create(fir, n_ch, chunk, 1, &fs), "lrc_fir_stream_create");
+    check(lrc_resampler_create(g.ctx, ratio, n_ch, cap_bb4, &rs), "lrc_resampler_create");
+    cuda_check(cudaMalloc((void **)&d_bb, n_ch * cap_bb4 * sizeof(cf32)), "cudaMalloc");
+    cuda_check(cudaMalloc((void **)&d_fm, n_ch * cap_bb4 * sizeof(float)), "cudaMalloc");
+    cuda_check(cudaMalloc((void **)&d_au, n_ch * cap_au * sizeof(float)), "cudaMalloc");
+    cuda_check(cudaMalloc((void **)&d_state, n_ch * sizeof(cf32)), "cudaMalloc");
+    cuda_check(cudaMemset(d_state, 0, n_ch * sizeof(cf32)), "cudaMemset");     // x[-1] = 0 at stream start
+    Stream st;
+    struct RingSlot { Slot in, out; cudaEvent_t done = nullptr; size_t n_out = 0; bool busy = false; } ring[2];
+    for (auto &r : ring) {
+        r.in.reserve(g, n_ch * chunk_bytes); r.out.reserve(g, n_ch * cap_au * sizeof(float));
+        cuda_check(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    auto drain = [&](RingSlot &r) {
+        if (!r.busy) return;
+        cuda_check(cudaEventSynchronize(r.done), "cudaEventSynchronize");
+        const float *p = (const float *)r.out.h;
+        if (r.n_out)
+            for (size_t c = 0; c < n_ch; ++c) v[c].send(std::vector<float>(p + c * cap_au, p + c * cap_au + r.n_out));
+        r.busy = false;
+    };
+    auto cleanup = [&]() {
+        lrc_resampler_destroy(rs); lrc_fir_stream_destroy(fs); lrc_fir_destroy(fir);
+        cudaFree(d_bb); cudaFree(d_fm); cudaFree(d_au); cudaFree(d_state);
+        for (auto &r : ring) { r.in.release(g); r.out.release(g); if (r.done) cudaEventDestroy(r.done); }
+    };
+    try {
+        for (size_t it = 0;; ++it) {
+            RingSlot &r = ring[it & 1];
+            drain(r);                                              // slot reuse: its previous batch must be out
+            for (size_t c = 0; c < n_ch; ++c) {
+                std::vector<uint8_t> x = u[c].recv();
+                if (x.size() != chunk_bytes) throw std::length_error("fm_receiver_multi: chunk length != chunk_bytes");
+                std::memcpy((uint8_t *)r.in.h + c * chunk_bytes, x.data(), chunk_bytes);
+            }
+            cuda_check(cudaMemcpyAsync(r.in.d, r.in.h, n_ch * chunk_bytes, cudaMemcpyHostToDevice, st.s), "H2D");
+            size_t n_bb = 0, n_au = 0;
+            check(lrc_fir_stream_push(fs, r.in.d, chunk, chunk, d_bb, cap_bb4, &n_bb, st.s), "lrc_fir_stream_push");
+            if (n_bb) {
+                check(lrc_fmdemod_run(g.ctx, d_bb, n_ch, n_bb, cap_bb4, d_state, d_fm, cap_bb4, st.s), "lrc_fmdemod_run");
+                check(lrc_resampler_process(rs, d_fm, n_bb, cap_bb4, d_au, cap_au, &n_au, st.s), "lrc_resampler_process");
+                if (n_au)
+                    cuda_check(cudaMemcpyAsync(r.out.h, d_au, n_ch * cap_au * sizeof(float), cudaMemcpyDeviceToHost, st.s), "D2H");
+            }
+            r.n_out = n_au;
+            cuda_check(cudaEventRecord(r.done, st.s), "cudaEventRecord");
+            r.busy = true;
+            drain(ring[(it + 1) & 1]);                             // hand out the batch submitted one step ago
+        }
+    } catch (...) {
+        try { drain(ring[0]); drain(ring[1]); } catch (...) {}
+        cleanup();
+        throw;
+    }
 }
 
 // ---- headline chain: cf32 chunks (whole frames' worth) -> rows of |X|^2 -----------------------------------
