@@ -344,6 +344,30 @@ class Resampler:
 
 
 # ---- long FIR (config 5) ----------------------------------------------------------------------------
+class FmReceiver:
+    """BASELINE config 3 as one streaming object: rtlsdr u8 IQ chunks [n_ch, 2 n] -> audio chunks [n_ch, m], through the
+    fused unpack + FIR/decimate stream (seam-exact), the discriminator (carried x[-1]) and the resampler (carried
+    history) -- the Python twin of kpn_gpu::fm_receiver_multi.  Output is independent of how the stream is chunked.
+    STAGED: a composition of individually tested stages; its own GPU test runs with LRC_TEST_STAGED=1."""
+
+    def __init__(self, ctx: Context, taps, decim: int, ratio: float, n_ch: int, max_chunk: int):
+        self.ctx, self.n_ch = ctx, n_ch
+        self.fir = Fir(ctx, taps, decim)
+        self.fs = FirStream(self.fir, n_ch, max_chunk, u8=True)
+        self.state = torch.zeros(n_ch, dtype=torch.complex64, device=ctx.tdev)
+        self.rs = Resampler(ctx, ratio, n_ch, (self.fir.taps.size + max_chunk) // decim + 2)
+
+    def push(self, iq: torch.Tensor) -> torch.Tensor:
+        assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous()
+        bb = self.fs.push(iq.reshape(self.n_ch, -1)).contiguous()
+        if bb.shape[1] == 0:
+            return torch.empty((self.n_ch, 0), dtype=torch.float32, device=iq.device)
+        return self.rs.process(fm_demod(self.ctx, bb, self.state))
+
+    def close(self):
+        self.rs.close(); self.fs.close(); self.fir.close()
+
+
 class FastFir:
     """kiss_fastfir: overlap-save convolution with the nh-1 transient removed (tools/kiss_fastfir.c)."""
 

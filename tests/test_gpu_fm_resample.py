@@ -3,6 +3,8 @@
 Tolerance (BASELINE.json): output SNR >= 100 dB against the f64 oracle (oracle/defined_f64.py).
 The resampler oracle is OUR definition -- libsamplerate parity is unpinned.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -188,4 +190,33 @@ def test_fm_broadcast_chain_config3(ctx):
     spec = np.abs(np.fft.rfft(audio[0][2000:] * np.hanning(audio[0][2000:].size)))
     f = np.fft.rfftfreq(audio[0][2000:].size, 1 / 48000.0)
     assert abs(f[np.argmax(spec[5:]) + 5] - 1000.0) < 30.0
+    fir.close(); rs.close()
+
+
+@pytest.mark.skipif(os.environ.get("LRC_TEST_STAGED") != "1", reason="staged composition: run with LRC_TEST_STAGED=1")
+def test_fm_receiver_streaming_is_chunk_independent_and_matches_stage_oracles(ctx):
+    """blocks.FmReceiver (config 3 as one streaming object): chunked == whole bit for bit, and the whole run equals the
+    three stages run one after the other (each of which has its own oracle test above)."""
+    from libredio_b200 import blocks
+    n_ch, n = 3, 120_000
+    taps = synth.lpf_taps(64, 0.04)
+    iq = np.stack([synth.fm_iq_u8(n, seed=30 + c) for c in range(n_ch)])
+    rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+    whole = rx.push(dev(iq, ctx)).cpu().numpy()
+    rx.close()
+    rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+    parts, pos = [], 0
+    for c in (2, 126, 20_000, 39_872, 60_000):
+        parts.append(rx.push(dev(iq[:, 2 * pos: 2 * (pos + c)], ctx)).cpu().numpy())
+        pos += c
+    rx.close()
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == whole.shape == (n_ch, ((n - 64) // 10 + 1 - 1) // 5 + 1)
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    fir = blocks.Fir(ctx, taps, 10)
+    bb = fir.run_u8(dev(iq, ctx))
+    d = blocks.fm_demod(ctx, bb)
+    rs = blocks.Resampler(ctx, 0.2, n_ch, d.shape[1])
+    ref = rs.process(d).cpu().numpy()
+    assert np.array_equal(ref.view(np.uint32), whole.view(np.uint32))
     fir.close(); rs.close()

@@ -185,8 +185,19 @@ def main():
             extra.update(cpu_rate(lambda: oracle.ref_fastfir(h, hx), hx.size))
             extra["cpu_what"] = "vendored tools/kiss_fastfir.c (-O3, tools/Makefile:43), 2^20-sample buffers"
         report("overlap-save FIR 4096 taps nfft 8192 (config 5, K4)", n, n * 16, ms, extra)
-        del x, out
+        del out
         ff.close()
+        if os.environ.get("LRC_FASTFIR_STAGED") == "1":
+            # the staged 16384-point blocks: 12289 of 16384 outputs kept per block instead of 4097 of 8192
+            ff = blocks.FastFir(ctx, h, 16384)
+            out = torch.empty(ff.out_len(n) + 1, dtype=torch.complex64, device=dev)
+            ms, _ = timeit(lambda: ff.run(x, out=out), iters=5)
+            flop16 = (2 * 5 * 16384 * 14 + 6 * 16384) / 12289.0
+            report("overlap-save FIR 4096 taps nfft 16384 (config 5, staged kernel)", n, n * 16, ms,
+                   {"flop_per_sample": flop16, "TFLOP/s": n * flop16 / (ms * 1e-3) / 1e12})
+            del out
+            ff.close()
+        del x
 
     if want("ook"):
         n_streams, n_blocks = 4096 // q, 500
