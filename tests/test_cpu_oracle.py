@@ -332,15 +332,49 @@ def test_resampler_definition_is_plain_polyphase_and_in_sinc_medium_class(ratio)
     assert abs(20 * np.log10(H[np.searchsorted(f, 0.9 * fc)]) + 6.02) < 0.1
 
 
+def _load_model(name):
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_packed_resampler_index_model_matches_the_definition_on_many_shapes():
+    """tools/models/resample_dec2_model.py follows the host and device index arithmetic of the packed two-tile
+    decimator line by line (virtual row, s0, tile pairing, the three fill paths, windows, store predicates, carry
+    update); swept here over kernel configurations, channel counts and chunkings the GPU tests do not reach -- odd tile
+    counts, a pair spanning two channels, outputs that are an exact multiple of a tile, one-sample chunks."""
+    m = _load_model("resample_dec2_model")
+    rng = np.random.default_rng(0)
+    seen = {"full": 0, "fast": 0, "generic": 0}
+    for M, R, NT in [(5, 6, 64), (5, 6, 128), (2, 7, 128), (3, 6, 128), (6, 5, 128)]:
+        h = D.resampler_taps(1, M)
+        tile = R * NT * M
+        for n_ch, chunks in [(1, [5000]), (3, [1, 4, 5, 990, 11_000]), (2, [1200 * M + 7, 3]), (5, [2 * tile]),
+                             (4, [2 * tile + 1, tile - 1]), (1, [6 * tile])]:
+            mod = m.Dec2Model(M, R, NT, n_ch, h)
+            x = rng.standard_normal((n_ch, sum(chunks)))
+            outs, pos = [], 0
+            for c in chunks:
+                outs.append(mod.process(x[:, pos:pos + c]))
+                pos += c
+            got = np.concatenate(outs, axis=1)
+            for c in range(n_ch):
+                ref = D.resample(x[c], 1.0 / M, taps=h)
+                assert got[c].shape == ref.shape
+                assert np.max(np.abs(got[c] - ref)) < 1e-10
+            for k in seen:
+                seen[k] += mod.paths[k]
+    assert all(v > 0 for v in seen.values()), seen            # every fill path was taken
+
+
 def test_fastfir16k_design_model_is_an_exact_overlap_save():
     """tools/models/fastfir16k_model.py mirrors, index for index, the data flow of the staged nfft = 16384 kernel
     (16 x 1024 split, padded rows, warp-level 32 x 32 sub-transforms through the row buffer, factorised P1 twiddles,
     H stored as Hp[k1][k2]); it must reproduce the direct convolution to f64 accuracy."""
-    import importlib.util
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models", "fastfir16k_model.py")
-    spec = importlib.util.spec_from_file_location("fastfir16k_model", path)
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
+    m = _load_model("fastfir16k_model")
     rng = np.random.default_rng(3)
     nh = 4096
     h = (rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64
