@@ -4,6 +4,8 @@
 #include <cstdio>
 #include "kpn.hpp"
 #include "sources.hpp"
+#include "dsputils.hpp"
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <string>
@@ -172,6 +174,29 @@ int main()
         CHECK(y[0] == 0x1B && y[1] == 0xFF);
         oblw_assemble_packet(y, bytes.data(), 2, true);
         CHECK(y[0] == 0xE4);
+    }
+    // dsputils tap designers (dsputils.rs:38-94): corrected window by default, the reference's NaN on request
+    {
+        using namespace dsputils;
+        auto gain = [](const std::vector<float> &h, double f) {
+            double re = 0, im = 0;
+            for (size_t n = 0; n < h.size(); ++n) { re += h[n] * std::cos(2 * M_PI * f * n); im -= h[n] * std::sin(2 * M_PI * f * n); }
+            return std::sqrt(re * re + im * im);
+        };
+        const auto lp = lpf(64, 0.1f), hp = hpf(64, 0.1f), bs = bsf(64, 0.05f, 0.2f), bp = bpf(64, 0.05f, 0.2f);
+        CHECK(window(64).size() == 65 && lp.size() == 64 && hp.size() == 64 && bs.size() == 64 && bp.size() == 64);
+        for (float v : lp) CHECK(std::isfinite(v));
+        CHECK(std::fabs(gain(lp, 0.0) - 1.0) < 2e-3 && gain(lp, 0.3) < 1e-3);          // low-pass
+        CHECK(gain(hp, 0.0) < 2e-3 && std::fabs(gain(hp, 0.3) - 1.0) < 2e-3);          // high-pass
+        CHECK(hp[31] == -lp[31] + 1.0f && hp[32] == -lp[32]);                           // the 1.0 sits at m/2 - 1 (:77)
+        for (size_t i = 0; i < 64; ++i) CHECK(bp[i] == -bs[i]);                         // bpf = -bsf (:91-94)
+        CHECK(std::fabs(gain(bs, 0.0) - 1.0) < 5e-3 && std::fabs(gain(bs, 0.35) - 1.0) < 5e-3 && gain(bs, 0.1) < 0.7);
+        bool nan = false;
+        for (float v : lpf(64, 0.1f, true)) nan = nan || std::isnan(v);
+        CHECK(nan);                                                                      // the reference's window bug (:49)
+        bool threw = false;
+        try { sinc(8, 0.5f); } catch (const std::logic_error &) { threw = true; }
+        CHECK(threw);                                                                    // assert!(fc < 0.5) :55
     }
     std::printf("kpn cpu OK\n");
     return 0;

@@ -23,6 +23,24 @@ def lpf_taps(m: int = 64, fc: float = 0.04) -> np.ndarray:
     return (w * s).astype(np.float32)
 
 
+def hpf_taps(m: int = 64, fc: float = 0.04) -> np.ndarray:
+    """dsputils::hpf(m, fc) (dsputils.rs:74-79) on the corrected window: -lpf with 1.0 added at index m/2 - 1 --
+    the reference's own position, one tap before the sinc's peak at m/2."""
+    h = (-lpf_taps(m, fc)).astype(np.float32)
+    h[m // 2 - 1] = np.float32(h[m // 2 - 1] + np.float32(1.0))
+    return h
+
+
+def bsf_taps(m: int, fc1: float, fc2: float) -> np.ndarray:
+    """dsputils::bsf(m, fc1, fc2) (dsputils.rs:82-88): lpf(fc1) + hpf(fc2)."""
+    return (lpf_taps(m, fc1) + hpf_taps(m, fc2)).astype(np.float32)
+
+
+def bpf_taps(m: int, fc1: float, fc2: float) -> np.ndarray:
+    """dsputils::bpf(m, fc1, fc2) (dsputils.rs:91-94): -bsf."""
+    return (-bsf_taps(m, fc1, fc2)).astype(np.float32)
+
+
 def hann_periodic(n: int) -> np.ndarray:
     k = np.arange(n, dtype=np.float64)
     return (0.5 - 0.5 * np.cos(2.0 * np.pi * k / n)).astype(np.float32)

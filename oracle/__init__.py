@@ -69,6 +69,9 @@ def lib() -> C.CDLL:
         L.orc_window.argtypes = [sz, vp, C.c_int]
         L.orc_sinc.argtypes = [sz, C.c_float, vp]
         L.orc_lpf.argtypes = [sz, C.c_float, vp, C.c_int]
+        L.orc_hpf.argtypes = [sz, C.c_float, vp, C.c_int]
+        L.orc_bsf.argtypes = [sz, C.c_float, C.c_float, vp, C.c_int]
+        L.orc_bpf.argtypes = [sz, C.c_float, C.c_float, vp, C.c_int]
         L.orc_fft.restype = C.c_int
         L.orc_fft.argtypes = [C.c_int, C.c_int, vp, vp]
         L.orc_fastfir.restype = sz
@@ -136,6 +139,24 @@ def fir_decimate(x: np.ndarray, taps: np.ndarray, d: int, full: bool = False) ->
 def lpf(m: int, fc: float, faithful: bool = False) -> np.ndarray:
     out = np.empty(m, dtype=np.float32)
     lib().orc_lpf(m, C.c_float(fc), _ptr(out), int(faithful))
+    return out
+
+
+def hpf(m: int, fc: float, faithful: bool = False) -> np.ndarray:
+    out = np.empty(m, dtype=np.float32)
+    lib().orc_hpf(m, C.c_float(fc), _ptr(out), int(faithful))
+    return out
+
+
+def bsf(m: int, fc1: float, fc2: float, faithful: bool = False) -> np.ndarray:
+    out = np.empty(m, dtype=np.float32)
+    lib().orc_bsf(m, C.c_float(fc1), C.c_float(fc2), _ptr(out), int(faithful))
+    return out
+
+
+def bpf(m: int, fc1: float, fc2: float, faithful: bool = False) -> np.ndarray:
+    out = np.empty(m, dtype=np.float32)
+    lib().orc_bpf(m, C.c_float(fc1), C.c_float(fc2), _ptr(out), int(faithful))
     return out
 
 

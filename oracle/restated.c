@@ -137,6 +137,34 @@ void orc_lpf(size_t m, float fc, float *out, int faithful)
     free(w); free(s);
 }
 
+/* src/dsputils/src/dsputils.rs:74-79 : -lpf with 1.0 added at index m/2 - 1 (the sinc peaks at m/2: the
+ * reference's delta sits one tap early; kept) */
+void orc_hpf(size_t m, float fc, float *out, int faithful)
+{
+    orc_lpf(m, fc, out, faithful);
+    for (size_t i = 0; i < m; ++i) out[i] = -out[i];
+    out[m / 2 - 1] += 1.0f;
+}
+
+/* src/dsputils/src/dsputils.rs:82-88 : lpf(fc1) + hpf(fc2); the `-= 0.0` of :86 is a no-op */
+void orc_bsf(size_t m, float fc1, float fc2, float *out, int faithful)
+{
+    float *lp = (float *)malloc(m * sizeof(float));
+    float *hp = (float *)malloc(m * sizeof(float));
+    orc_lpf(m, fc1, lp, faithful);
+    orc_hpf(m, fc2, hp, faithful);
+    for (size_t i = 0; i < m; ++i) out[i] = lp[i] + hp[i];
+    out[m / 2 - 1] -= 0.0f;
+    free(lp); free(hp);
+}
+
+/* src/dsputils/src/dsputils.rs:91-94 : -bsf */
+void orc_bpf(size_t m, float fc1, float fc2, float *out, int faithful)
+{
+    orc_bsf(m, fc1, fc2, out, faithful);
+    for (size_t i = 0; i < m; ++i) out[i] = -out[i];
+}
+
 /* ====================================================================================== */
 /* (3) FFT -- src/kissfft/libkissfft/kiss_fft.c                                            */
 /* ====================================================================================== */

@@ -49,6 +49,9 @@ size_t orc_fir_decimate_cf32(const orc_cpx *x, size_t n, const float *taps, size
 void   orc_window(size_t m, float *out_m_plus_1, int faithful);
 void   orc_sinc(size_t m, float fc, float *out_m);
 void   orc_lpf(size_t m, float fc, float *out_m, int faithful);
+void   orc_hpf(size_t m, float fc, float *out_m, int faithful);
+void   orc_bsf(size_t m, float fc1, float fc2, float *out_m, int faithful);
+void   orc_bpf(size_t m, float fc1, float fc2, float *out_m, int faithful);
 
 /* ---- (3) FFT: src/kissfft/libkissfft/kiss_fft.c:238-388 ------------------------------ */
 /* unscaled mixed-radix DIT, forward e^{-j..}, inverse e^{+j..}; fin != fout */

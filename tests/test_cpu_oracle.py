@@ -63,6 +63,33 @@ def test_window_bug_of_reference_is_reproduced_and_corrected_designer_is_finite(
     assert np.max(np.abs(synth.lpf_taps(64, 0.04) - good)) < 1e-6
 
 
+def test_hpf_bsf_bpf_designers_restated_and_corrected():
+    """dsputils.rs:74-94.  Faithful restatement: NaN like lpf (the window bug, :49).  Corrected window: finite, the
+    product's host designers (libredio_b200/synth.py) equal the oracle's, and the formulas are kept as written --
+    the 1.0 of hpf at index m/2 - 1 (:77), bsf = lpf(fc1) + hpf(fc2) (:82-88), bpf = -bsf (:91-94)."""
+    from libredio_b200 import synth
+    m = 64
+    for fn, args in ((oracle.hpf, (0.1,)), (oracle.bsf, (0.05, 0.2)), (oracle.bpf, (0.05, 0.2))):
+        assert np.isnan(fn(m, *args, faithful=True)).any()
+        assert np.isfinite(fn(m, *args)).all()
+    lp, hp = oracle.lpf(m, 0.1), oracle.hpf(m, 0.1)
+    want = -lp
+    want[m // 2 - 1] = np.float32(want[m // 2 - 1] + np.float32(1.0))
+    assert np.array_equal(hp.view(np.uint32), want.view(np.uint32))
+    bs, bp = oracle.bsf(m, 0.05, 0.2), oracle.bpf(m, 0.05, 0.2)
+    assert np.array_equal(bs.view(np.uint32), (oracle.lpf(m, 0.05) + oracle.hpf(m, 0.2)).view(np.uint32))
+    assert np.array_equal(bp.view(np.uint32), (-bs).view(np.uint32))
+    assert np.max(np.abs(synth.hpf_taps(m, 0.1) - hp)) < 1e-6
+    assert np.max(np.abs(synth.bsf_taps(m, 0.05, 0.2) - bs)) < 1e-6
+    assert np.max(np.abs(synth.bpf_taps(m, 0.05, 0.2) - bp)) < 1e-6
+
+    def gain(h, f):
+        n = np.arange(h.size)
+        return abs(np.sum(h.astype(np.float64) * np.exp(-2j * np.pi * f * n)))
+    assert gain(hp, 0.0) < 2e-3 and abs(gain(hp, 0.3) - 1.0) < 2e-3            # a high-pass
+    assert abs(gain(bs, 0.0) - 1.0) < 5e-3 and abs(gain(bs, 0.35) - 1.0) < 5e-3 and gain(bs, 0.1) < 0.7
+
+
 # ---- (3) FFT vs the reference's outputs -----------------------------------------------------------------
 def test_restated_fft_vs_golden_fixtures_from_vendored_kissfft(golden):
     import tests.golden.make_golden as mg
