@@ -159,6 +159,18 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm / baseline
 # ------------------------------------------------------------------------------------------------------
+def cpu_model() -> str:
+    """host CPU model string (the CPU baseline states core count and model of the box it ran on)"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_chain_rate(seconds_target: float, threads: int, frames_per_call: int = 64, full: bool = False):
     """Time the CPU chain (oracle FIR restatement + vendored kissfft at the reference's build flags) on a
     bounded sample with `threads` host threads.  Returns (Msamples/s, description, kind, frames, secs)."""
@@ -216,7 +228,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(FRAMES), "sample_per_step": desc},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": kind, "sample": desc,
                          "as_written_all_lags": {"value": f_msps, "unit": UNIT, "sample": f_desc,
                                                  "note": "informational: the reference has no decimating FIR; `value` is the "
                                                          "stronger CPU baseline that skips the 9 of 10 dropped outputs"}},
@@ -470,7 +482,8 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             msps, desc, kind, _, _ = cpu_chain_rate(args.cpu_seconds, os.cpu_count() or 1)
-            cpu = {"value": msps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": desc}
+            cpu = {"value": msps, "unit": UNIT, "cores": os.cpu_count() or 1, "cpu_model": cpu_model(), "kind": kind,
+                   "sample": desc}
             f_msps, f_desc, _, _, _ = cpu_chain_rate(0.4, os.cpu_count() or 1, full=True)
             cpu["as_written_all_lags"] = {"value": f_msps, "unit": UNIT, "sample": f_desc,
                                           "note": "informational: the reference has no decimating FIR; `value` is the "
