@@ -320,6 +320,7 @@ static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_
     if (rows == 0) return LRC_OK;
     LRC_REQUIRE(h_in && h_rows, LRC_ERR_INVALID, "lrc_chain_run_host: null buffer");
     const size_t adv = (size_t)c->nfft * c->decim;                      // input samples per frame
+    const size_t tile_in = (size_t)(c->nfft - 1) * c->decim + c->ntaps;  // input samples one frame reads
     const size_t tail = (size_t)c->ntaps > (size_t)c->decim ? (size_t)c->ntaps - c->decim : 0;  // samples past the last frame's advance
     // segment plan: whole rows per segment when rows are short, slices of one row otherwise
     const bool slice_rows = k_avg > SEG_FRAMES;
@@ -358,7 +359,9 @@ static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_
         }
         if (f + nfr > total_frames) nfr = total_frames - f;
         const int b = (int)(seg & 1);
-        const size_t ns = nfr * adv + tail;
+        // exactly what the segment's last frame reaches: (nfr-1)*adv + tile_in.  With decim > ntaps that is LESS than
+        // nfr*adv, and lrc_chain_frames guarantees the caller's buffer no further than this.
+        const size_t ns = (nfr - 1) * adv + tile_in;
         if (seg >= 2) LRC_CUDA(cudaStreamWaitEvent(cs, c->ev_free[b], 0));
         if (input_is_u8)      // 2 bytes per sample over PCIe; rtlsdr::data_to_samples runs on the device
             LRC_CUDA(cudaMemcpyAsync(c->d_ring_u8[b], h_in_u8 + 2 * f * adv, ns * 2, cudaMemcpyHostToDevice, cs));

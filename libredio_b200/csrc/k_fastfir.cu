@@ -17,20 +17,21 @@ using namespace lrfft;
 
 int lrc_make_twiddles(int nfft, float2 **d_tw);
 int lrc_log2_exact(int n);
-// k_fastfir16k.cu (staged nfft = 16384 kernel)
-void lrc_fastfir16k_permute_H(const float2 *H, float2 *Hp);
+// k_fastfir16k.cu (16384-point blocks)
+void lrc_fastfir16k_permute_H(const float2 *H, float2 *Hq);
 int lrc_fastfir16k_prepare(void);
 int lrc_fastfir16k_launch(int n_sm, const float2 *in, size_t n_in, float2 *out, size_t full, size_t nblk, size_t ngood,
                           size_t keep, const float2 *d_tw16k, const float2 *d_tw1k, const float2 *d_Hp, cudaStream_t s);
 
 struct lrc_fastfir {
     lrc_ctx *ctx;
-    size_t   nh, nfft, ngood;
+    size_t   nh, nfft, ngood;   // nfft/ngood: the block size that fixes the OUTPUT LENGTH (kiss_fastfir's, or the caller's)
     int      log2n;
     float2  *d_tw;
     float2  *d_H;
-    float2  *d_Hc;     // nfft == 8192: H in the order fastfir8k_kernel uses; nfft == 16384: Hp[k1][k2] = H[k1 + 16 k2]
-    float2  *d_tw1k;   // nfft == 16384: W_1024^k for the warp-level sub-transforms
+    float2  *d_Hc;     // 8192-point kernel: H in the order fastfir8k_kernel uses; 16384-point kernel: Hq (k_fastfir16k.cu)
+    float2  *d_tw1k;   // 16384-point kernel: W_1024^k for the warp-level sub-transforms
+    bool     compute16k;        // blocks are COMPUTED 16384 points at a time whatever nfft says (see lrc_fastfir_create)
 };
 
 // host-side f64 radix-2 FFT (forward), used only to build H for block sizes our own FFT plans do not cover
@@ -318,10 +319,11 @@ static void fastfir8k_permute_H(const std::vector<float2> &H, std::vector<float2
         }
 }
 
-extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t nh, size_t nfft, lrc_fastfir **out)
+extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t nh, size_t nfft_arg, lrc_fastfir **out)
 {
     LRC_BIND(ctx);
     LRC_REQUIRE(out && h_taps_cpx && nh >= 1, LRC_ERR_INVALID, "lrc_fastfir_create: bad arguments");
+    size_t nfft = nfft_arg;
     if (nfft == 0) {
         // kiss_fastfir.c:81-93: next power of two at least twice the impulse response, at least 1024
         size_t i = nh - 1;
@@ -329,37 +331,40 @@ extern "C" int lrc_fastfir_create(lrc_ctx *ctx, const float *h_taps_cpx, size_t 
         do { nfft <<= 1; } while (i >>= 1);
         if (nfft < 1024) nfft = 1024;
     }
+    const bool automatic = nfft_arg == 0;
     const int l2 = lrc_log2_exact((int)nfft);
-    // nfft = 16384 (75 % useful outputs per block for 4096 taps instead of 50 %): the kernel in k_fastfir16k.cu is
-    // STAGED -- checked once on hardware (profiles/r1_s8_fastfir16k_check.json), its pytest cases not yet -- and only
-    // reachable on request.  The automatic size stays kiss_fastfir's (8192 for 4096 taps): it fixes the output length.
-    const bool staged16k = nfft == 16384 && getenv("LRC_FASTFIR_STAGED") && atoi(getenv("LRC_FASTFIR_STAGED")) == 1;
-    if ((l2 < 1 || l2 > 13 || nfft > 8192) && !staged16k) {
-        lrc_set_error("lrc_fastfir_create: nfft=%zu: only powers of two in [2, 8192] (nh <= 4096 with the "
+    if (l2 < 1 || l2 > 14) {
+        lrc_set_error("lrc_fastfir_create: nfft=%zu: only powers of two in [2, 16384] (nh <= 8192 with the "
                       "automatic size)", nfft);
         return LRC_ERR_UNSUPPORTED;
     }
     LRC_REQUIRE(nfft >= nh, LRC_ERR_INVALID, "lrc_fastfir_create: nfft shorter than the impulse response");
-    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr, nullptr, nullptr};
+    // Overlap-save gives the same y[k] whatever the block size; the block size only fixes how many outputs a call
+    // without flush produces (kff_nocopy :199-204 stops at the last FULL block).  So `nfft` keeps that meaning, and
+    // long filters are COMPUTED in 16384-point blocks: 12289 of 16384 outputs kept per block for 4096 taps instead of
+    // 4097 of 8192.  An explicit nfft < 16384 is honoured for the arithmetic as well (A/B runs, golden tests of that size).
+    const bool c16 = nfft == 16384 || (automatic && nh > 1024);
+    lrc_fastfir *f = new (std::nothrow) lrc_fastfir{ctx, nh, nfft, nfft - nh + 1, l2, nullptr, nullptr, nullptr, nullptr, c16};
     LRC_REQUIRE(f != nullptr, LRC_ERR_NOMEM, "out of host memory");
-    if (staged16k) {
+    if (c16) {
+        const size_t n16 = 16384;
         int rc16 = lrc_make_twiddles(16384, &f->d_tw);
         if (!rc16) rc16 = lrc_make_twiddles(1024, &f->d_tw1k);
         if (!rc16) rc16 = lrc_fastfir16k_prepare();
         if (rc16) { lrc_fastfir_destroy(f); return rc16; }
         // H = FFT(h rotated) / nfft in f64 on the host (:148-169), rounded once to f32
         const float2 *h16 = reinterpret_cast<const float2 *>(h_taps_cpx);
-        std::vector<double> re(nfft, 0.0), im(nfft, 0.0);
+        std::vector<double> re(n16, 0.0), im(n16, 0.0);
         re[0] = h16[nh - 1].x; im[0] = h16[nh - 1].y;
-        for (size_t i = 0; i + 1 < nh; ++i) { re[nfft - nh + 1 + i] = h16[i].x; im[nfft - nh + 1 + i] = h16[i].y; }
+        for (size_t i = 0; i + 1 < nh; ++i) { re[n16 - nh + 1 + i] = h16[i].x; im[n16 - nh + 1 + i] = h16[i].y; }
         host_fft_f64(re, im);
-        std::vector<float2> H(nfft), Hp(nfft);
-        for (size_t i = 0; i < nfft; ++i) H[i] = make_float2((float)(re[i] / (double)nfft), (float)(im[i] / (double)nfft));
-        lrc_fastfir16k_permute_H(H.data(), Hp.data());
-        cudaError_t e16 = cudaMalloc(&f->d_H, nfft * sizeof(float2));
-        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_H, H.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
-        if (e16 == cudaSuccess) e16 = cudaMalloc(&f->d_Hc, nfft * sizeof(float2));
-        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_Hc, Hp.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice);
+        std::vector<float2> H(n16), Hq(n16);
+        for (size_t i = 0; i < n16; ++i) H[i] = make_float2((float)(re[i] / (double)n16), (float)(im[i] / (double)n16));
+        lrc_fastfir16k_permute_H(H.data(), Hq.data());
+        cudaError_t e16 = cudaMalloc(&f->d_H, n16 * sizeof(float2));
+        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_H, H.data(), n16 * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e16 == cudaSuccess) e16 = cudaMalloc(&f->d_Hc, n16 * sizeof(float2));
+        if (e16 == cudaSuccess) e16 = cudaMemcpy(f->d_Hc, Hq.data(), n16 * sizeof(float2), cudaMemcpyHostToDevice);
         if (e16 != cudaSuccess) {
             lrc_set_error("lrc_fastfir_create: %s", cudaGetErrorString(e16));
             lrc_fastfir_destroy(f);
@@ -468,8 +473,14 @@ extern "C" int lrc_fastfir_run(lrc_fastfir *f, const float *d_in, size_t n_in, f
     const float2 *in = (const float2 *)d_in;
     float2 *out = (float2 *)d_out;
     static const int variant = getenv("LRC_FASTFIR_VARIANT") ? atoi(getenv("LRC_FASTFIR_VARIANT")) : 1;
-    if (f->nfft == 16384)
-        return lrc_fastfir16k_launch(f->ctx->n_sm, in, n_in, out, full, nblk, f->ngood, keep, f->d_tw, f->d_tw1k, f->d_Hc, s);
+    if (f->compute16k) {
+        // the same full * ngood + keep outputs, cut into 16384-point blocks: every output k < n_total only needs
+        // x[k .. k + nh - 1], which the call holds; the last block keeps the remainder and reads zeros past the input
+        const size_t n_total = full * f->ngood + keep, ngood16 = 16384 - f->nh + 1;
+        const size_t full16 = n_total / ngood16, keep16 = n_total % ngood16;
+        return lrc_fastfir16k_launch(f->ctx->n_sm, in, n_in, out, full16, full16 + (keep16 ? 1 : 0), ngood16, keep16, f->d_tw,
+                                     f->d_tw1k, f->d_Hc, s);
+    }
     if (f->d_Hc && variant == 1) {
         size_t blocks = (size_t)f->ctx->n_sm * 2;
         if (blocks > nblk) blocks = nblk;

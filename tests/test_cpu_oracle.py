@@ -398,9 +398,9 @@ def test_packed_resampler_index_model_matches_the_definition_on_many_shapes():
 
 
 def test_fastfir16k_design_model_is_an_exact_overlap_save():
-    """tools/models/fastfir16k_model.py mirrors, index for index, the data flow of the staged nfft = 16384 kernel
-    (16 x 1024 split, padded rows, warp-level 32 x 32 sub-transforms through the row buffer, factorised P1 twiddles,
-    H stored as Hp[k1][k2]); it must reproduce the direct convolution to f64 accuracy."""
+    """tools/models/fastfir16k_model.py mirrors, index for index, the data flow of the nfft = 16384 kernel (k_fastfir16k.cu)
+    (16 x 1024 split, lane-slab rows of pitch 34, column pairs per P1 thread, warp-level 32 x 32 sub-transforms through
+    the row buffer, H stored as Hq[k1][i][lane][c]); it must reproduce the direct convolution to f64 accuracy."""
     m = _load_model("fastfir16k_model")
     rng = np.random.default_rng(3)
     nh = 4096

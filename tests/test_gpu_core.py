@@ -4,6 +4,8 @@ against oracle/ (the CPU restatement, itself pinned to the vendored kissfft and 
 Tolerances are BASELINE.json's: bit-exact for the u8 unpack; max |err| <= 1e-4 x RMS(reference output)
 for the float FIR / FFT stages.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -466,3 +468,52 @@ def test_chain_host_ring_u8_input_matches_unpack_then_chain(ctx):
     pref = D.psd_rows(oracle.fir_decimate(oracle.data_to_samples(iq), taps, 10), 1024, k, D.hann_periodic(1024))
     assert_close_rms(got, pref)
     ch.close()
+
+
+_TIGHT_HOST = r"""
+import ctypes, mmap, sys
+import os
+
+import numpy as np
+sys.path.insert(0, {root!r})
+import oracle
+from oracle import defined_f64 as D
+from libredio_b200 import blocks, synth
+ntaps, decim, nfft, frames, k = {ntaps}, {decim}, {nfft}, {frames}, {k}
+n = (frames - 1) * nfft * decim + (nfft - 1) * decim + ntaps          # the exact minimum for `frames` frames
+page = mmap.PAGESIZE
+nbytes = n * 8
+npages = (nbytes + page - 1) // page
+mm = mmap.mmap(-1, (npages + 1) * page)
+base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+libc = ctypes.CDLL(None, use_errno=True)
+assert libc.mprotect(ctypes.c_void_p(base + npages * page), ctypes.c_size_t(page), 0) == 0     # PROT_NONE guard page
+off = npages * page - nbytes                                           # the buffer ENDS at the guard page
+x = np.frombuffer(mm, dtype=np.complex64, count=n, offset=off)
+x[:] = synth.cf32_noise_tones(n, seed=9)
+rng = np.random.default_rng(1)
+taps = (rng.standard_normal(ntaps) / 3).astype(np.float32)
+ctx = blocks.Context(0)
+ch = blocks.Chain(ctx, taps, decim, nfft)
+assert ch.frames(n) == frames and ch.frames(n - 1) == frames - 1
+got = ch.run_host(x, k)
+ref = D.psd_rows(oracle.fir_decimate(np.array(x), taps, decim), nfft, k, D.hann_periodic(nfft))
+assert got.shape == ref.shape, (got.shape, ref.shape)
+err = np.max(np.abs(got - ref)) / np.sqrt(np.mean(ref ** 2))
+assert err <= 1e-4, err
+print("tight-host ok", err)
+"""
+
+
+@pytest.mark.parametrize("ntaps,decim,nfft,frames,k", [(5, 16, 256, 900, 4), (64, 10, 1024, 410, 5), (3, 7, 64, 40, 8)])
+def test_chain_host_ring_never_reads_past_the_callers_buffer(ntaps, decim, nfft, frames, k):
+    """lrc_chain_frames promises frames from exactly (frames-1)*nfft*decim + (nfft-1)*decim + ntaps samples; with
+    decim > ntaps that is LESS than frames*nfft*decim, and the host ring must not copy more (it once did).
+    The caller's buffer ends at a PROT_NONE page; run in a child process so an over-read is a failure, not a crash
+    of the test session."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _TIGHT_HOST.format(root=root, ntaps=ntaps, decim=decim, nfft=nfft, frames=frames, k=k)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "tight-host ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])

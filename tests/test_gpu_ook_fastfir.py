@@ -205,27 +205,12 @@ def test_fastfir_config5_shape_spot_windows(ctx):
     ff.close()
 
 
-# ---- staged: nfft = 16384 blocks (k_fastfir16k.cu) ----------------------------------------------------------
-STAGED = os.environ.get("LRC_FASTFIR_STAGED") == "1"
-
-
-def test_fastfir_nfft_16384_is_refused_unless_staged(ctx):
-    """the 16384-point kernel is written against a verified numpy model (tools/models/fastfir16k_model.py) and was
-    checked once on a B200 (profiles/r1_s8_fastfir16k_check.json), but the cases below have not run on hardware yet:
-    without LRC_FASTFIR_STAGED=1 the plan must be refused loudly, never silently mis-served"""
-    from libredio_b200 import blocks
-    if STAGED:
-        pytest.skip("LRC_FASTFIR_STAGED=1: the staged kernel is enabled in this run")
-    h = np.ones(4096, dtype=np.complex64)
-    with pytest.raises(capi.LrcError) as e:
-        blocks.FastFir(ctx, h, 16384)
-    assert e.value.status == capi.ERR_UNSUPPORTED
-
-
-@pytest.mark.skipif(not STAGED, reason="staged kernel: run with LRC_FASTFIR_STAGED=1 to validate it on a GPU")
+# ---- nfft = 16384 blocks (k_fastfir16k.cu) --------------------------------------------------------------------
 @pytest.mark.parametrize("nh,n", [(4096, 16384), (4096, 16384 + 12289 * 3 + 100), (4096, 20_000), (1000, 70_000),
-                                  (4096, 1 << 22)])
-def test_fastfir_staged_nfft_16384_vs_oracle(ctx, nh, n):
+                                  (4096, 1 << 22), (8192, 50_000), (5000, 16383)])
+def test_fastfir_nfft_16384_vs_oracle(ctx, nh, n):
+    """explicit 16384-point blocks: against the restated kiss_fastfir at the same block size (itself pinned to the
+    vendored build by the golden fixture) and against the f64 convolution on windows incl. block seams"""
     from libredio_b200 import blocks
     rng = np.random.default_rng(nh + n)
     h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / np.sqrt(nh)).astype(np.complex64)
@@ -238,7 +223,8 @@ def test_fastfir_staged_nfft_16384_vs_oracle(ctx, nh, n):
         if n <= 100_000:
             ref = oracle.fastfir(h, x, 16384, flush)
             assert got.shape == ref.shape
-            assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+            if ref.size:
+                assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
         # true convolution with the transient removed, on windows (incl. block seams)
         hr = h[::-1].astype(np.complex128)
         for s0 in [0, ff.ngood - 8, got.size - 64] + [int(v) for v in rng.integers(0, max(1, got.size - 64), 6)]:
@@ -248,3 +234,52 @@ def test_fastfir_staged_nfft_16384_vs_oracle(ctx, nh, n):
             ref = np.array([np.dot(seg[k:k + nh], hr) for k in range(64)])
             assert np.max(np.abs(got[s0:s0 + 64] - ref)) <= 1e-4 * rms(ref)
     ff.close()
+
+
+@pytest.mark.parametrize("nh,n", [(4096, 70_000), (4096, 8192), (4096, 8191), (4096, 8192 + 4097 * 5 - 1), (2049, 30_000),
+                                  (1025, 9000), (3000, 100_001), (6000, 60_000), (8192, 16384), (8192, 16383)])
+def test_fastfir_automatic_size_keeps_kiss_fastfir_output_length_whatever_the_compute_block(ctx, nh, n):
+    """nfft = 0: the OUTPUT LENGTH is the one kiss_fastfir's own block size gives (kiss_fastfir.c:81-93, :199-204 -- a call
+    without flush stops at the reference's last full block) although the arithmetic runs in 16384-point blocks for
+    nh > 1024; values against the restated kiss_fastfir at the reference's size"""
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(7 * nh + n)
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / np.sqrt(nh)).astype(np.complex64)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    ff = blocks.FastFir(ctx, h, 0)
+    ref_nfft = max(1024, 2 << max(1, (nh - 1).bit_length()))     # kiss_fastfir.c:81-93
+    assert ff.nfft == ref_nfft
+    for flush in (False, True):
+        got = ff.run(dev(x, ctx), flush).cpu().numpy()
+        ref = oracle.fastfir(h, x, 0, flush)
+        assert got.shape == ref.shape == (ff.out_len(n, flush),)
+        if ref.size:
+            assert np.max(np.abs(got - ref)) <= 1e-4 * rms(ref)
+    ff.close()
+
+
+def test_fastfir_explicit_8192_blocks_agree_with_the_automatic_plan(ctx):
+    """the two compute paths (8192-point kernel on request, 16384-point blocks by default) give the same stream"""
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(11)
+    nh, n = 4096, 1 << 21
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64).astype(np.complex64)
+    g = torch.Generator(device=ctx.tdev).manual_seed(3)
+    x = torch.view_as_complex(torch.randn(n, 2, device=ctx.tdev, generator=g))
+    a, b = blocks.FastFir(ctx, h, 0), blocks.FastFir(ctx, h, 8192)
+    assert a.nfft == b.nfft == 8192
+    for flush in (False, True):
+        ya, yb = a.run(x, flush), b.run(x, flush)
+        assert ya.shape == yb.shape
+        assert (ya - yb).abs().max().item() <= 1e-5 * yb.abs().pow(2).mean().sqrt().item()
+    a.close(); b.close()
+
+
+def test_fastfir_sizes_beyond_16384_are_refused(ctx):
+    from libredio_b200 import blocks
+    with pytest.raises(capi.LrcError) as e:
+        blocks.FastFir(ctx, np.ones(8193, dtype=np.complex64), 0)          # kiss_fastfir would pick 32768
+    assert e.value.status == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.LrcError) as e:
+        blocks.FastFir(ctx, np.ones(100, dtype=np.complex64), 32768)
+    assert e.value.status == capi.ERR_UNSUPPORTED

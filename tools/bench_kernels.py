@@ -176,25 +176,18 @@ def main():
         x = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
         rng = np.random.default_rng(6)
         h = ((rng.standard_normal(4096) + 1j * rng.standard_normal(4096)) / 64).astype(np.complex64)
-        ff = blocks.FastFir(ctx, h, 0)
-        out = torch.empty(ff.out_len(n) + 1, dtype=torch.complex64, device=dev)
-        ms, _ = timeit(lambda: ff.run(x, out=out), iters=5)
-        extra = {"flop_per_sample": 272, "TFLOP/s": n * 272 / (ms * 1e-3) / 1e12}
-        if a.cpu and oracle.have_ref():
-            hx = synth.cf32_noise_tones(1 << 20, seed=5)
-            extra.update(cpu_rate(lambda: oracle.ref_fastfir(h, hx), hx.size))
-            extra["cpu_what"] = "vendored tools/kiss_fastfir.c (-O3, tools/Makefile:43), 2^20-sample buffers"
-        report("overlap-save FIR 4096 taps nfft 8192 (config 5, K4)", n, n * 16, ms, extra)
-        del out
-        ff.close()
-        if os.environ.get("LRC_FASTFIR_STAGED") == "1":
-            # the staged 16384-point blocks: 12289 of 16384 outputs kept per block instead of 4097 of 8192
-            ff = blocks.FastFir(ctx, h, 16384)
+        flop16 = (2 * 5 * 16384 * 14 + 6 * 16384) / 12289.0
+        for nfft, label, flop in ((0, "overlap-save FIR 4096 taps, 16384-point blocks (config 5, K4)", flop16),
+                                  (8192, "overlap-save FIR 4096 taps, explicit nfft 8192 (fastfir8k_kernel)", 272.0)):
+            ff = blocks.FastFir(ctx, h, nfft)
             out = torch.empty(ff.out_len(n) + 1, dtype=torch.complex64, device=dev)
             ms, _ = timeit(lambda: ff.run(x, out=out), iters=5)
-            flop16 = (2 * 5 * 16384 * 14 + 6 * 16384) / 12289.0
-            report("overlap-save FIR 4096 taps nfft 16384 (config 5, staged kernel)", n, n * 16, ms,
-                   {"flop_per_sample": flop16, "TFLOP/s": n * flop16 / (ms * 1e-3) / 1e12})
+            extra = {"flop_per_sample_nominal": flop, "TFLOP/s_nominal": n * flop / (ms * 1e-3) / 1e12}
+            if a.cpu and oracle.have_ref() and nfft == 0:
+                hx = synth.cf32_noise_tones(1 << 20, seed=5)
+                extra.update(cpu_rate(lambda: oracle.ref_fastfir(h, hx), hx.size))
+                extra["cpu_what"] = "vendored tools/kiss_fastfir.c (-O3, tools/Makefile:43), 2^20-sample buffers"
+            report(label, n, n * 16, ms, extra)
             del out
             ff.close()
         del x
