@@ -211,6 +211,29 @@ int    lrc_resampler_process_host(lrc_resampler *rs, const float *h_in, size_t n
                                   size_t out_cap, size_t *n_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * (1)+(2)+(4a)+(4b) as one streaming receiver (BASELINE config 3): rtlsdr u8 IQ chunks -> FIR(ntaps)/decim ->
+ *     quadrature discriminator -> resampler(ratio) -> f32 audio, n_ch independent channels, state carried across
+ *     pushes so the audio stream does not depend on how the input is chunked.  Replaces the chain
+ *     rtlsdr::data_to_samples (rtlsdr.rs:160-162) -> dsputils::convolve (dsputils.rs:30-32) + decimation ->
+ *     discriminator -> samplerate::resample (samplerate.rs:59-87) of a KPN FM-receiver graph.
+ *     The BASELINE shape (64 taps / 10, ratio 1/5) runs as ONE kernel per push (HBM sees 2 B/sample in and the audio
+ *     out, nothing else); any other shape runs the three stand-alone stages behind the same interface.
+ *     Each stage's arithmetic is the stand-alone stage's, so the tolerances of (2), (4a), (4b) apply.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lrc_fmrx lrc_fmrx;
+int    lrc_fmrx_create(lrc_ctx *ctx, const float *h_taps, int ntaps, int decim, double ratio, size_t n_ch,
+                       size_t max_chunk, lrc_fmrx **rx);
+int    lrc_fmrx_destroy(lrc_fmrx *rx);
+int    lrc_fmrx_reset(lrc_fmrx *rx);
+int    lrc_fmrx_is_fused(const lrc_fmrx *rx);
+/* audio frames per channel the next push of n samples will produce */
+size_t lrc_fmrx_next_out_len(const lrc_fmrx *rx, size_t n);
+/* n new samples per channel (u8 I,Q interleaved; channel c at d_iq + 2*c*chunk_stride bytes); writes the audio that
+ * became computable to d_audio (+ c*out_stride) and its per-channel count to *n_out (host arithmetic, no readback) */
+int    lrc_fmrx_push(lrc_fmrx *rx, const uint8_t *d_iq, size_t n, size_t chunk_stride, float *d_audio,
+                     size_t out_stride, size_t *n_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (5) OOK packet decode, bit-exact.   Replaces, per stream, the chain of src/ratpak.rs:60-111:
  *     rtlsdr::data_to_samples (rtlsdr.rs:160) -> |x| (ratpak.rs:64-68) -> bitfount::trigger
  *     (bitfount.rs:36-85, 512-sample blocks) -> bitfount::discretize (:87-96) -> kpn::rle (kpn.rs:17-29)

@@ -11,7 +11,7 @@
 //   dsputils::convolve (+/D)  dsputils.rs:30      kpn_gpu::fir_decimate, fir_decimate_multi (channel ring)
 //   (north-star) discriminator                    kpn_gpu::fm_demod
 //   (north-star) FIR->FFT->|X|^2 chain            kpn_gpu::chain_psd
-//   (north-star) config-3 FM receiver, N channels  kpn_gpu::fm_receiver_multi (staged)
+//   (north-star) config-3 FM receiver, N channels  kpn_gpu::fm_receiver_multi (lrc_fmrx: one kernel per batch)
 //   trigger..shaper_optional  ratpak.rs:60-111    kpn_gpu::ook_decode
 //
 // Errors: a non-zero status of the C ABI is thrown as std::runtime_error -- the analogue of the
@@ -274,7 +274,7 @@ inline void resample(Gpu &g, Receiver<std::vector<float>> din, Sender<std::vecto
 // slot A's batch is on the device the block is already packing slot B, and A's audio is scattered to the senders
 // when the block comes back to A.  The reference would wire rtlsdr::data_to_samples -> dsputils::convolve ->
 // (discriminator) -> samplerate::resample with one thread and one channel message per stage and chunk.
-// STAGED: compiled and linked here, exercised by kpn/test_gpu_blocks.cpp only when LRC_TEST_STAGED=1.
+// The device side is lrc_fmrx: ONE kernel per batch for the BASELINE shape (64 taps / 10, ratio 1/5).
 inline void fm_receiver_multi(Gpu &g, std::vector<Receiver<std::vector<uint8_t>>> u, std::vector<Sender<std::vector<float>>> v,
                               std::vector<float> taps, size_t decim, double ratio, size_t chunk_bytes)
 {
@@ -284,18 +284,11 @@ inline void fm_receiver_multi(Gpu &g, std::vector<Receiver<std::vector<uint8_t>>
     if (chunk_bytes == 0 || (chunk_bytes & 1)) throw std::invalid_argument("fm_receiver_multi: chunk_bytes must be even");
     const size_t chunk = chunk_bytes / 2;                                   // samples per channel and batch
     const size_t cap_bb = (taps.size() + chunk) / decim + 2;               // decimated samples a batch can yield
-    const size_t cap_bb4 = (cap_bb + 3) / 4 * 4;                            // rows stay 16-byte aligned
     const size_t cap_au = ((size_t)(ratio * (double)cap_bb + 1.0) + 1 + 3) / 4 * 4;
-    lrc_fir *fir = nullptr; lrc_fir_stream *fs = nullptr; lrc_resampler *rs = nullptr;
-    float *d_bb = nullptr, *d_fm = nullptr, *d_state = nullptr, *d_au = nullptr;
-    check(lrc_fir_create(g.ctx, taps.data(), (int)taps.size(), (int)decim, &fir), "lrc_fir_create");
-    check(lrc_fir_stream_create(fir, n_ch, chunk, 1, &fs), "lrc_fir_stream_create");
-    check(lrc_resampler_create(g.ctx, ratio, n_ch, cap_bb4, &rs), "lrc_resampler_create");
-    cuda_check(cudaMalloc((void **)&d_bb, n_ch * cap_bb4 * sizeof(cf32)), "cudaMalloc");
-    cuda_check(cudaMalloc((void **)&d_fm, n_ch * cap_bb4 * sizeof(float)), "cudaMalloc");
+    lrc_fmrx *rx = nullptr;
+    float *d_au = nullptr;
+    check(lrc_fmrx_create(g.ctx, taps.data(), (int)taps.size(), (int)decim, ratio, n_ch, chunk, &rx), "lrc_fmrx_create");
     cuda_check(cudaMalloc((void **)&d_au, n_ch * cap_au * sizeof(float)), "cudaMalloc");
-    cuda_check(cudaMalloc((void **)&d_state, n_ch * sizeof(cf32)), "cudaMalloc");
-    cuda_check(cudaMemset(d_state, 0, n_ch * sizeof(cf32)), "cudaMemset");     // x[-1] = 0 at stream start
     Stream st;
     struct RingSlot { Slot in, out; cudaEvent_t done = nullptr; size_t n_out = 0; bool busy = false; } ring[2];
     for (auto &r : ring) {
@@ -311,8 +304,8 @@ inline void fm_receiver_multi(Gpu &g, std::vector<Receiver<std::vector<uint8_t>>
         r.busy = false;
     };
     auto cleanup = [&]() {
-        lrc_resampler_destroy(rs); lrc_fir_stream_destroy(fs); lrc_fir_destroy(fir);
-        cudaFree(d_bb); cudaFree(d_fm); cudaFree(d_au); cudaFree(d_state);
+        lrc_fmrx_destroy(rx);
+        cudaFree(d_au);
         for (auto &r : ring) { r.in.release(g); r.out.release(g); if (r.done) cudaEventDestroy(r.done); }
     };
     try {
@@ -325,14 +318,10 @@ inline void fm_receiver_multi(Gpu &g, std::vector<Receiver<std::vector<uint8_t>>
                 std::memcpy((uint8_t *)r.in.h + c * chunk_bytes, x.data(), chunk_bytes);
             }
             cuda_check(cudaMemcpyAsync(r.in.d, r.in.h, n_ch * chunk_bytes, cudaMemcpyHostToDevice, st.s), "H2D");
-            size_t n_bb = 0, n_au = 0;
-            check(lrc_fir_stream_push(fs, r.in.d, chunk, chunk, d_bb, cap_bb4, &n_bb, st.s), "lrc_fir_stream_push");
-            if (n_bb) {
-                check(lrc_fmdemod_run(g.ctx, d_bb, n_ch, n_bb, cap_bb4, d_state, d_fm, cap_bb4, st.s), "lrc_fmdemod_run");
-                check(lrc_resampler_process(rs, d_fm, n_bb, cap_bb4, d_au, cap_au, &n_au, st.s), "lrc_resampler_process");
-                if (n_au)
-                    cuda_check(cudaMemcpyAsync(r.out.h, d_au, n_ch * cap_au * sizeof(float), cudaMemcpyDeviceToHost, st.s), "D2H");
-            }
+            size_t n_au = 0;
+            check(lrc_fmrx_push(rx, (const uint8_t *)r.in.d, chunk, chunk, d_au, cap_au, &n_au, st.s), "lrc_fmrx_push");
+            if (n_au)
+                cuda_check(cudaMemcpyAsync(r.out.h, d_au, n_ch * cap_au * sizeof(float), cudaMemcpyDeviceToHost, st.s), "D2H");
             r.n_out = n_au;
             cuda_check(cudaEventRecord(r.done, st.s), "cudaEventRecord");
             r.busy = true;

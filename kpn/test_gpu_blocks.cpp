@@ -99,8 +99,8 @@ int main()
         for (size_t k = 400; k < 1000; ++k) CHECK(std::fabs(y[k] - 0.1f) < 5e-3f);   // demodulated DC = 0.1 rad/sample
         t0.drop(); a.join(); b.join(); c.join();
     }
-    // --- STAGED (LRC_TEST_STAGED=1): config-3 receiver ring, 3 channels; chunked == one big chunk, bit for bit --------
-    if (const char *e = std::getenv("LRC_TEST_STAGED"); e && std::atoi(e) == 1) {
+    // --- config-3 receiver ring (lrc_fmrx), 3 channels; chunked == one big chunk, bit for bit ------------------------
+    {
         const size_t n_ch = 3, n_samp = 60000, ntaps = 64, decim = 10;
         std::vector<float> taps(ntaps);
         for (size_t j = 0; j < ntaps; ++j) {                               // windowed sinc, cutoff 0.04, unity DC gain
@@ -139,10 +139,10 @@ int main()
         const size_t n_bb = (n_samp - ntaps) / decim + 1, n_au = (n_bb - 1) / 5 + 1;
         for (size_t c = 0; c < n_ch; ++c) {
             CHECK(whole[c].size() == n_au && parts[c].size() == n_au);
-            CHECK(std::memcmp(whole[c].data(), parts[c].data(), n_au * sizeof(float)) == 0);   // seam-exact in all three stages
+            CHECK(std::memcmp(whole[c].data(), parts[c].data(), n_au * sizeof(float)) == 0);   // seam-exact through all three stages
             for (size_t k = 300; k < n_au; ++k) CHECK(std::fabs(whole[c][k] - 0.04f * (float)(c + 1)) < 5e-3f);
         }
-        std::printf("kpn gpu staged OK\n");
+        std::printf("kpn gpu fm_receiver_multi OK\n");
     }
     std::printf("kpn gpu OK\n");
     return 0;

@@ -343,31 +343,45 @@ class Resampler:
             self.h = C.c_void_p()
 
 
-# ---- long FIR (config 5) ----------------------------------------------------------------------------
 class FmReceiver:
-    """BASELINE config 3 as one streaming object: rtlsdr u8 IQ chunks [n_ch, 2 n] -> audio chunks [n_ch, m], through the
-    fused unpack + FIR/decimate stream (seam-exact), the discriminator (carried x[-1]) and the resampler (carried
-    history) -- the Python twin of kpn_gpu::fm_receiver_multi.  Output is independent of how the stream is chunked.
-    STAGED: a composition of individually tested stages; its own GPU test runs with LRC_TEST_STAGED=1."""
+    """BASELINE config 3 as one streaming object: rtlsdr u8 IQ chunks [n_ch, 2 n] -> audio chunks [n_ch, m]
+    (lrc_fmrx: unpack + FIR/decimate, discriminator, resampler; ONE kernel per push for the BASELINE shape 64 taps / 10,
+    ratio 1/5, the three stand-alone stages otherwise) -- the Python twin of kpn_gpu::fm_receiver_multi.  Output is
+    independent of how the stream is chunked."""
 
     def __init__(self, ctx: Context, taps, decim: int, ratio: float, n_ch: int, max_chunk: int):
-        self.ctx, self.n_ch = ctx, n_ch
-        self.fir = Fir(ctx, taps, decim)
-        self.fs = FirStream(self.fir, n_ch, max_chunk, u8=True)
-        self.state = torch.zeros(n_ch, dtype=torch.complex64, device=ctx.tdev)
-        self.rs = Resampler(ctx, ratio, n_ch, (self.fir.taps.size + max_chunk) // decim + 2)
+        self.ctx, self.n_ch, self.max_chunk = ctx, n_ch, max_chunk
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.h = C.c_void_p()
+        check(ctx.lib.lrc_fmrx_create(ctx.h, _p(self.taps), self.taps.size, int(decim), C.c_double(float(ratio)), n_ch,
+                                      max_chunk, C.byref(self.h)), "lrc_fmrx_create")
+        self.fused = bool(ctx.lib.lrc_fmrx_is_fused(self.h))
 
-    def push(self, iq: torch.Tensor) -> torch.Tensor:
+    def next_out_len(self, n: int) -> int:
+        return int(self.ctx.lib.lrc_fmrx_next_out_len(self.h, n))
+
+    def reset(self):
+        check(self.ctx.lib.lrc_fmrx_reset(self.h), "lrc_fmrx_reset")
+
+    def push(self, iq: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous()
-        bb = self.fs.push(iq.reshape(self.n_ch, -1)).contiguous()
-        if bb.shape[1] == 0:
-            return torch.empty((self.n_ch, 0), dtype=torch.float32, device=iq.device)
-        return self.rs.process(fm_demod(self.ctx, bb, self.state))
+        q2 = iq.reshape(self.n_ch, -1)
+        n = q2.shape[1] // 2
+        want = self.next_out_len(n)
+        if out is None:
+            out = torch.empty((self.n_ch, max(want, 1)), dtype=torch.float32, device=iq.device)
+        no = C.c_size_t()
+        check(self.ctx.lib.lrc_fmrx_push(self.h, _p(q2), n, n, _p(out), out.shape[1], C.byref(no), _stream()), "lrc_fmrx_push")
+        assert no.value == want
+        return out[:, : no.value]
 
     def close(self):
-        self.rs.close(); self.fs.close(); self.fir.close()
+        if self.h:
+            self.ctx.lib.lrc_fmrx_destroy(self.h)
+            self.h = C.c_void_p()
 
 
+# ---- long FIR (config 5) ----------------------------------------------------------------------------
 class FastFir:
     """kiss_fastfir: overlap-save convolution with the nh-1 transient removed (tools/kiss_fastfir.c)."""
 

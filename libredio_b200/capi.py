@@ -83,6 +83,12 @@ SIGNATURES = {
     "lrc_resampler_next_out_len": (_sz, [_vp, _sz]),
     "lrc_resampler_process": (_i, [_vp, _fp, _sz, _sz, _fp, _sz, _szp, _vp]),
     "lrc_resampler_process_host": (_i, [_vp, _fp, _sz, _fp, _sz, _szp]),
+    "lrc_fmrx_create": (_i, [_vp, _fp, _i, _i, C.c_double, _sz, _sz, _pp]),
+    "lrc_fmrx_destroy": (_i, [_vp]),
+    "lrc_fmrx_reset": (_i, [_vp]),
+    "lrc_fmrx_is_fused": (_i, [_vp]),
+    "lrc_fmrx_next_out_len": (_sz, [_vp, _sz]),
+    "lrc_fmrx_push": (_i, [_vp, _u8p, _sz, _sz, _fp, _sz, _szp, _vp]),
     "lrc_ook_create": (_i, [_vp, _sz, _sz, C.c_uint, _sz, _sz, _pp]),
     "lrc_ook_destroy": (_i, [_vp]),
     "lrc_ook_decode": (_i, [_vp, _u8p, _sz, _vp]),

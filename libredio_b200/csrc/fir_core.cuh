@@ -58,11 +58,27 @@ struct FirTile {
     // to the scalar form.
     __device__ __forceinline__ static void run_u8(const uint32_t *sw, const FirTaps<NTAPS> &taps127, float2 *acc)
     {
+        run_u8_with(sw, taps127, acc, [](int) {});
+    }
+
+    // the same with a caller-supplied piece of independent work `side(j)` placed after the loads of step j (j = 0, 2, ...,
+    // WIN - 2, a compile-time constant once unrolled): the fused receiver (k_fmrx.cu) threads the previous round's
+    // discriminator through the filter this way, so its dependent chains issue between the packed FMAs.  The filter's own
+    // operation order is untouched: results are bit-identical to run_u8.
+    // TAPS_IN_REGS = false reads every tap where it is used: the compiler then brings it from the constant bank into a
+    // UNIFORM register (LDCU) for the packed instruction, 64 fewer vector registers per thread for one LDCU.128 per
+    // four taps -- what lets the fused receiver keep three CTAs per SM.
+    template <class Side, bool TAPS_IN_REGS = true>
+    __device__ __forceinline__ static void run_u8_with(const uint32_t *sw, const FirTaps<NTAPS> &taps127, float2 *acc, Side side)
+    {
         // taps live in registers: a packed instruction takes its broadcast operand from a register, not from
         // the constant bank
-        float h[NTAPS];
+        float h[TAPS_IN_REGS ? NTAPS : 1];
+        if (TAPS_IN_REGS) {
 #pragma unroll
-        for (int k = 0; k < NTAPS; ++k) h[k] = taps127.h[k];
+            for (int k = 0; k < NTAPS; ++k) h[k] = taps127.h[k];
+        }
+        auto tap = [&](int k) { return TAPS_IN_REGS ? h[TAPS_IN_REGS ? k : 0] : taps127.h[k]; };
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
         const float2 bias = make_float2(8388735.0f, 8388735.0f);
@@ -77,9 +93,10 @@ struct FirTile {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int k0 = j - r * DECIM, k1 = k0 + 1;
-                if (k0 >= 0 && k0 < NTAPS) acc[r] = fma2(x0, make_float2(h[k0], h[k0]), acc[r]);
-                if (k1 >= 0 && k1 < NTAPS) acc[r] = fma2(x1, make_float2(h[k1], h[k1]), acc[r]);
+                if (k0 >= 0 && k0 < NTAPS) acc[r] = fma2(x0, make_float2(tap(k0), tap(k0)), acc[r]);
+                if (k1 >= 0 && k1 < NTAPS) acc[r] = fma2(x1, make_float2(tap(k1), tap(k1)), acc[r]);
             }
+            side(j);
         }
     }
 };

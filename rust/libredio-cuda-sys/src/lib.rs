@@ -15,7 +15,7 @@ pub const LRC_WINDOW_NONE: c_int = 0;
 pub const LRC_WINDOW_HANN: c_int = 1;
 
 macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
-opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_rfft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_ook, lrc_gather);
+opaque!(lrc_ctx, lrc_fir, lrc_fir_stream, lrc_fft, lrc_rfft, lrc_psd, lrc_chain, lrc_fastfir, lrc_resampler, lrc_fmrx, lrc_ook, lrc_gather);
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -101,6 +101,17 @@ extern "C" {
                                  d_out: *mut c_float, out_stride: size_t, n_out: *mut size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_resampler_process_host(rs: *mut lrc_resampler, h_in: *const c_float, n_in: size_t, h_out: *mut c_float,
                                       out_cap: size_t, n_out: *mut size_t) -> c_int;
+
+    // BASELINE config 3 as one streaming receiver: u8 IQ -> FIR/decimate -> discriminator -> resampler (one kernel per push
+    // for 64 taps / 10, ratio 1/5)
+    pub fn lrc_fmrx_create(ctx: *mut lrc_ctx, h_taps: *const c_float, ntaps: c_int, decim: c_int, ratio: c_double, n_ch: size_t,
+                           max_chunk: size_t, rx: *mut *mut lrc_fmrx) -> c_int;
+    pub fn lrc_fmrx_destroy(rx: *mut lrc_fmrx) -> c_int;
+    pub fn lrc_fmrx_reset(rx: *mut lrc_fmrx) -> c_int;
+    pub fn lrc_fmrx_is_fused(rx: *const lrc_fmrx) -> c_int;
+    pub fn lrc_fmrx_next_out_len(rx: *const lrc_fmrx, n: size_t) -> size_t;
+    pub fn lrc_fmrx_push(rx: *mut lrc_fmrx, d_iq: *const u8, n: size_t, chunk_stride: size_t, d_audio: *mut c_float,
+                         out_stride: size_t, n_out: *mut size_t, stream: *mut c_void) -> c_int;
 
     pub fn lrc_ook_create(ctx: *mut lrc_ctx, n_streams: size_t, n_blocks: size_t, sample_rate: c_uint, max_runs: size_t,
                           max_packets: size_t, ook: *mut *mut lrc_ook) -> c_int;

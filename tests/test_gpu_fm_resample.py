@@ -193,30 +193,69 @@ def test_fm_broadcast_chain_config3(ctx):
     fir.close(); rs.close()
 
 
-@pytest.mark.skipif(os.environ.get("LRC_TEST_STAGED") != "1", reason="staged composition: run with LRC_TEST_STAGED=1")
-def test_fm_receiver_streaming_is_chunk_independent_and_matches_stage_oracles(ctx):
-    """blocks.FmReceiver (config 3 as one streaming object): chunked == whole bit for bit, and the whole run equals the
-    three stages run one after the other (each of which has its own oracle test above)."""
+def staged_pipeline(ctx, iq_dev, taps, n_ch):
+    """the three stand-alone stages one after the other (each has its own oracle test above)"""
     from libredio_b200 import blocks
-    n_ch, n = 3, 120_000
+    fir = blocks.Fir(ctx, taps, 10)
+    d = blocks.fm_demod(ctx, fir.run_u8(iq_dev))
+    rs = blocks.Resampler(ctx, 0.2, n_ch, d.shape[1])
+    ref = rs.process(d)
+    fir.close(); rs.close()
+    return ref
+
+
+@pytest.mark.parametrize("n_ch,chunks", [(3, (2, 126, 20_000, 39_872, 60_000)),          # chunk lengths not multiples of 8: copy path
+                                         (4, (8, 4000, 56_000, 59_992)),               # multiples of 8: TMA path
+                                         (1, (120_000,)), (2, (30, 30, 30, 119_910)), (5, (65_536, 54_464))])
+def test_fm_receiver_streaming_is_chunk_independent_and_matches_stage_oracles(ctx, n_ch, chunks):
+    """blocks.FmReceiver (config 3 as one streaming object, ONE kernel per push): chunked == whole bit for bit, and the
+    whole run equals the three stand-alone stages run one after the other bit for bit (the fused kernel performs the same
+    operation sequence per sample), each of which is held to its oracle above."""
+    from libredio_b200 import blocks
+    n = sum(chunks)
     taps = synth.lpf_taps(64, 0.04)
     iq = np.stack([synth.fm_iq_u8(n, seed=30 + c) for c in range(n_ch)])
     rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+    assert rx.fused
     whole = rx.push(dev(iq, ctx)).cpu().numpy()
-    rx.close()
-    rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+    rx.reset()
     parts, pos = [], 0
-    for c in (2, 126, 20_000, 39_872, 60_000):
+    for c in chunks:
         parts.append(rx.push(dev(iq[:, 2 * pos: 2 * (pos + c)], ctx)).cpu().numpy())
         pos += c
     rx.close()
     got = np.concatenate(parts, axis=1)
     assert got.shape == whole.shape == (n_ch, ((n - 64) // 10 + 1 - 1) // 5 + 1)
     assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
-    fir = blocks.Fir(ctx, taps, 10)
-    bb = fir.run_u8(dev(iq, ctx))
-    d = blocks.fm_demod(ctx, bb)
-    rs = blocks.Resampler(ctx, 0.2, n_ch, d.shape[1])
+    ref = staged_pipeline(ctx, dev(iq, ctx), taps, n_ch).cpu().numpy()
+    assert np.array_equal(ref.view(np.uint32), whole.view(np.uint32))
+    # and directly against the f64 definitions on the oracle's baseband (FIR 1e-4 x RMS feeds >= 100 dB stages)
+    bb = oracle.fir_decimate(oracle.data_to_samples(iq[0]), taps, 10)
+    want = D.resample(D.fm_discriminator(bb), 0.2)
+    assert D.snr_db(want[400:], whole[0][400:]) >= 80.0          # end to end: FIR rounding propagates through atan2
+
+
+def test_fm_receiver_other_shapes_run_the_three_stages_behind_the_same_interface(ctx):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(5)
+    n_ch, n = 2, 50_000
+    taps = (rng.standard_normal(33) / 6).astype(np.float32)
+    iq = np.stack([synth.fm_iq_u8(n, seed=70 + c) for c in range(n_ch)])
+    rx = blocks.FmReceiver(ctx, taps, 8, 0.25, n_ch, n)
+    assert not rx.fused
+    whole = rx.push(dev(iq, ctx)).cpu().numpy()
+    rx.reset()
+    parts, pos = [], 0
+    for c in (1000, 24_000, 25_000):
+        parts.append(rx.push(dev(iq[:, 2 * pos: 2 * (pos + c)], ctx)).cpu().numpy())
+        pos += c
+    rx.close()
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == whole.shape and whole.shape[1] > 1000
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    fir = blocks.Fir(ctx, taps, 8)
+    d = blocks.fm_demod(ctx, fir.run_u8(dev(iq, ctx)))
+    rs = blocks.Resampler(ctx, 0.25, n_ch, d.shape[1])
     ref = rs.process(d).cpu().numpy()
     assert np.array_equal(ref.view(np.uint32), whole.view(np.uint32))
     fir.close(); rs.close()

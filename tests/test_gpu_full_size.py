@@ -116,28 +116,31 @@ def test_config4_ook_4096_streams_bit_exact(ctx):
 
 def test_config5_fastfir_2pow30_stream_seam_windows(ctx):
     """configs[4]: 4096 taps over a 2^30-sample stream (8 GiB in, 8 GiB out), chunk-sharded at 2/4/8 GPUs: random
-    output windows and every shard seam against an f64 direct convolution; shard outputs equal the whole run."""
+    output windows and every shard seam against an f64 direct convolution; shard outputs equal the whole run.
+    Shards are cut on the 16384-point blocks the kernel computes in (explicit nfft = 16384 plan), so a shard repeats the
+    whole run's arithmetic exactly; the automatic plan (kiss_fastfir's output length) gives the same flushed stream."""
     from libredio_b200 import blocks, shard
     free, _ = torch.cuda.mem_get_info()
-    if free < 20 * (1 << 30):
-        pytest.skip("needs 20 GiB of free device memory")
-    nh, n = 4096, 1 << 30
+    if free < 30 * (1 << 30):
+        pytest.skip("needs 30 GiB of free device memory")
+    nh, n, nfft = 4096, 1 << 30, 16384
+    ngood = nfft - nh + 1
     rng = np.random.default_rng(6)
     h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64).astype(np.complex64)
     x = torch.empty(n, dtype=torch.complex64, device=ctx.tdev)
     g = torch.Generator(device=ctx.tdev).manual_seed(5)
     for lo in range(0, n, 1 << 27):                              # generated in pieces: randn's temporaries stay small
         x[lo: lo + (1 << 27)] = torch.view_as_complex(torch.randn(1 << 27, 2, device=ctx.tdev, generator=g))
-    ff = blocks.FastFir(ctx, h, 0)
-    assert ff.nfft == 8192 and ff.ngood == 4097
+    ff = blocks.FastFir(ctx, h, nfft)
+    assert ff.nfft == nfft and ff.ngood == ngood
     y = ff.run(x, flush=True)
     assert y.numel() == n - nh + 1 == ff.out_len(n, True)
     hr = h[::-1].astype(np.complex128)
     seams = []
     for world in (2, 4, 8):
         for rank in range(1, world):
-            seams.append(shard.fastfir_shard(n, nh, 8192, rank, world).out_start)
-    starts = [0, 4097 - 8, y.numel() - 64] + [s - 32 for s in seams] + [int(v) for v in rng.integers(0, y.numel() - 64, 16)]
+            seams.append(shard.fastfir_shard(n, nh, nfft, rank, world).out_start)
+    starts = [0, ngood - 8, y.numel() - 64] + [s - 32 for s in seams] + [int(v) for v in rng.integers(0, y.numel() - 64, 16)]
     for s0 in starts:
         seg = x[s0: s0 + 64 + nh - 1].cpu().numpy().astype(np.complex128)
         ref = np.array([np.dot(seg[k:k + nh], hr) for k in range(64)])
@@ -145,8 +148,47 @@ def test_config5_fastfir_2pow30_stream_seam_windows(ctx):
         assert np.max(np.abs(got - ref)) <= TOL * rms(ref), s0
     # block-aligned shards (each reading its own nh-1 halo from the source) reproduce the whole run bit for bit
     for rank in (0, 3, 7):
-        sh = shard.fastfir_shard(n, nh, 8192, rank, 8)
+        sh = shard.fastfir_shard(n, nh, nfft, rank, 8)
         part = ff.run(x[sh.in_start: sh.in_start + sh.in_len])
         assert part.numel() == sh.out_len
         assert torch.equal(torch.view_as_real(part), torch.view_as_real(y[sh.out_start: sh.out_start + sh.out_len]))
     ff.close()
+    # the drop-in plan: kiss_fastfir's own block size (8192) fixes the un-flushed length, the values are the same stream
+    auto = blocks.FastFir(ctx, h, 0)
+    assert auto.nfft == 8192 and auto.out_len(n) == ((n - 8192) // 4097 + 1) * 4097
+    ya = auto.run(x)
+    assert ya.numel() == auto.out_len(n)
+    assert torch.equal(torch.view_as_real(ya), torch.view_as_real(y[: ya.numel()]))
+    auto.close()
+
+
+def test_config3_fm_receiver_1024_channels_full_size(ctx):
+    """configs[2] at BASELINE size: 1024 channels x 2.4 Msps x 0.1 s of rtlsdr u8 IQ through the fused receiver (one
+    kernel), fed in two pushes; every channel equals the three stand-alone stages bit for bit, and randomly chosen
+    channels are held to the stage oracles (FIR 1e-4 x RMS, discriminator and resampler >= 100 dB on their inputs)."""
+    from libredio_b200 import blocks
+    n_ch, n, distinct = 1024, 240_000, 16
+    taps = synth.lpf_taps(64, 0.04)
+    base = np.stack([synth.fm_iq_u8(n, seed=3 + c) for c in range(distinct)])
+    perm = np.random.default_rng(3).permutation(n_ch) % distinct
+    iq = torch.from_numpy(base).to(ctx.tdev)[torch.from_numpy(perm).to(ctx.tdev)].contiguous()
+    rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+    assert rx.fused
+    cut = 96_000
+    audio = torch.cat([rx.push(iq[:, : 2 * cut].contiguous()), rx.push(iq[:, 2 * cut:].contiguous())], dim=1)
+    rx.close()
+    n_bb = (n - 64) // 10 + 1
+    assert audio.shape == (n_ch, (n_bb - 1) // 5 + 1)
+    fir = blocks.Fir(ctx, taps, 10)
+    bb = fir.run_u8(iq)
+    d = blocks.fm_demod(ctx, bb)
+    rs = blocks.Resampler(ctx, 0.2, n_ch, d.shape[1])
+    ref = rs.process(d)
+    assert torch.equal(audio, ref)
+    for c in [0, n_ch - 1] + [int(v) for v in np.random.default_rng(33).integers(0, n_ch, 3)]:
+        ref_bb = oracle.fir_decimate(oracle.data_to_samples(base[perm[c]]), taps, 10)
+        bb_c, d_c = bb[c].cpu().numpy(), d[c].cpu().numpy()
+        assert np.max(np.abs(bb_c - ref_bb)) <= TOL * rms(ref_bb), c
+        assert D.snr_db(D.fm_discriminator(bb_c), d_c) >= 100.0, c
+        assert D.snr_db(D.resample(d_c, 0.2), audio[c].cpu().numpy()) >= 100.0, c
+    fir.close(); rs.close()

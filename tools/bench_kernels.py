@@ -151,23 +151,35 @@ def main():
         rs.close()
 
     if want("fmchain"):
-        # config 3 as one pipeline: 1024 channels of rtlsdr u8 IQ at 2.4 Msps -> fused unpack+FIR64/10 ->
-        # discriminator -> resample 1/5 -> 48 kHz audio; 3 launches (+ the carry update), intermediates in HBM
+        # config 3: 1024 channels of rtlsdr u8 IQ at 2.4 Msps -> unpack+FIR64/10 -> discriminator -> resample 1/5 -> 48 kHz
+        # audio.  (a) the fused receiver, ONE kernel per push (lrc_fmrx); (b) the three stand-alone stages, 3 launches
+        # (+ the carry update) with the 240 kHz intermediates in HBM
         n_ch, n = 1024 // q, 240_000
         iq = torch.randint(0, 256, (n_ch, 2 * n), dtype=torch.uint8, device=dev, generator=g)
-        fir = blocks.Fir(ctx, taps, 10)
         n_bb = (n - 64) // 10 + 1
+        rx = blocks.FmReceiver(ctx, taps, 10, 0.2, n_ch, n)
+        n_audio = rx.next_out_len(n)
+        out = torch.empty((n_ch, n_audio), dtype=torch.float32, device=dev)
+        def fused():
+            rx.reset()
+            return rx.push(iq, out)
+        ms, _ = timeit(fused)
+        alg = n_ch * (n * 2 + n_audio * 4)                       # u8 IQ in, f32 audio out
+        flop = 25.6 + 12.84
+        report("config 3 fused receiver u8 IQ -> FIR64/10 -> FM -> 1/5 resample (one kernel)", n_ch * n, alg, ms,
+               {"n_ch": n_ch, "audio_samples_per_ch": int(n_audio), "fused": rx.fused,
+                "flop_per_sample": flop, "TFLOP/s": n_ch * n * flop / (ms * 1e-3) / 1e12})
+        rx.close()
+        fir = blocks.Fir(ctx, taps, 10)
         rs = blocks.Resampler(ctx, 0.2, n_ch, n_bb)
         def pipe():
             rs.reset()
             return rs.process(blocks.fm_demod(ctx, fir.run_u8(iq)))
         ms, _ = timeit(pipe)
-        n_audio = pipe().shape[-1]
-        alg = n_ch * (n * 2 + n_audio * 4)                       # u8 IQ in, f32 audio out
         moved = n_ch * (n * 2 + n_bb * 8 * 2 + n_bb * 4 * 2 + n_audio * 4)
-        report("config 3 pipeline u8 IQ -> FIR64/10 -> FM -> 1/5 resample (K1+K2, K5, K6)", n_ch * n, alg, ms,
-               {"n_ch": n_ch, "audio_samples_per_ch": int(n_audio), "bytes_moved_incl_intermediates": moved,
-                "flop_per_sample": 25.6 + 12.84, "TFLOP/s": n_ch * n * (25.6 + 12.84) / (ms * 1e-3) / 1e12})
+        report("config 3 three-stage pipeline (K1+K2, K5, K6)", n_ch * n, alg, ms,
+               {"n_ch": n_ch, "bytes_moved_incl_intermediates": moved,
+                "flop_per_sample": flop, "TFLOP/s": n_ch * n * flop / (ms * 1e-3) / 1e12})
         del iq
         fir.close(); rs.close()
 
