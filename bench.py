@@ -12,6 +12,10 @@ N > 1  : one process per GPU (torchrun); each rank owns an independent stream of
          default, NCCL all-gather with --gather nccl or when CUDA IPC is unavailable.
 e2e    : the same step through the host-buffer entry point lrc_chain_run_host (pinned host input, chunked
          H2D overlapped with the kernel through the double-buffered device ring, rows copied back).
+extra  : the other BASELINE.json configs measured in the same run (device-resident inputs >> L2, CUDA events, max over
+         ranks): config 1 from u8 IQ, config 2 (PSD), config 3 (1024-channel FM receiver, one fused kernel), config 4
+         (4096 OOK streams, sharded across the ranks) and config 5 (4096 taps over 2^30 samples, chunk-sharded across
+         the ranks; outputs left sharded and gathered to rank 0), each with its roofline fraction.  --no-extra skips it.
 --impl reference : the reference's own CPU path (oracle/: strict-f32 restatement of dsputils::convolve +
          the vendored kissfft built with the reference's flags), all host cores, bounded sample.
 """
@@ -44,6 +48,27 @@ def n_input(frames: int) -> int:
 def workload_name(frames: int) -> str:
     return (f"cf32 {n_input(frames)} samples -> FIR{NTAPS}/{DECIM} -> {frames} frames x {NFFT}-pt Hann FFT "
             f"(2^{int(np.log2(frames * NFFT))} samples into the FFT) -> |X|^2 avg K={K_AVG}")
+
+
+def chain_source_sha() -> str:
+    """sha256 over the sources the fused chain kernel is compiled from (what roofline.traffic is tied to)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("k_chain.cu", "fir_core.cuh", "fft_core.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "libredio_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def config_dict(frames: int, world: int) -> dict:
+    """what the number was measured on; the SAME dict in both arms (the CPU arm times a bounded sample of it, described
+    under cpu_baseline.sample)"""
+    return {"workload": workload_name(frames), "ntaps": NTAPS, "decim": DECIM, "nfft": NFFT, "k_avg": K_AVG,
+            "window": "hann", "frames": frames, "l2": "input 5.4 GB per step >> 126 MB L2, no flush needed",
+            "sharding": f"{world} independent streams, one per GPU; gather of output rows only"}
+
+
+FP32_PEAK_TFLOPS = 73.7      # packed FFMA2 micro-benchmark on a B200 (tools/ubench/f32x2.cu, profiles/r1_s8_f32x2_ubench.txt)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -227,7 +252,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(FRAMES), "sample_per_step": desc},
+        "config": config_dict(args.frames, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": kind, "sample": desc,
                          "as_written_all_lags": {"value": f_msps, "unit": UNIT, "sample": f_desc,
                                                  "note": "informational: the reference has no decimating FIR; `value` is the "
@@ -236,6 +261,152 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE configs, in the same run (device-resident inputs, CUDA events, max over ranks)
+# ------------------------------------------------------------------------------------------------------
+def _timed(fn, iters, warm, world, dev, inner=4):
+    """median / best milliseconds per call of fn(): `iters` measurements of `inner` back-to-back calls between two CUDA
+    events on the current stream (launch latency amortised as in a stream of chunks), after `warm` calls; with several
+    ranks every measurement starts behind a barrier and counts as the slowest rank's time"""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / inner], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t.item()))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def run_extras(ctx, world, rank, peak_hbm, quick=False):
+    """configs 1 (u8), 2, 3, 4, 5 of BASELINE.json.  Configs 1-3 are per-rank replicas of the full-size workload (weak
+    scaling, like the headline); configs 4 and 5 are ONE job of BASELINE size split across the ranks (strong scaling):
+    streams for config 4, 16384-point overlap-save blocks for config 5 (every rank reads its own nh-1 halo from its
+    slice of the source, no exchange), timed with the outputs left sharded and with the outputs gathered to rank 0."""
+    import torch
+    import torch.distributed as dist
+    from libredio_b200 import blocks, synth, capi, shard
+    dev = ctx.tdev
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    taps = synth.lpf_taps(NTAPS, 0.04)
+    q = 8 if quick else 1
+    out = {}
+
+    def entry(name, samples_total, ms, best, bound, alg_bytes_total, flop_per_sample=None, **kw):
+        e = {"value": samples_total / (ms * 1e-3) / 1e6, "unit": UNIT, "ms": ms, "ms_best": best, "n_gpus": world}
+        gbs = alg_bytes_total / (ms * 1e-3) / 1e9
+        roof = {"bound": bound, "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / (peak_hbm * world)}
+        if flop_per_sample is not None:
+            tf = samples_total * flop_per_sample / (ms * 1e-3) / 1e12
+            roof.update({"tflops_nominal": tf, "fp32_frac": tf / (FP32_PEAK_TFLOPS * world), "flop_per_sample_nominal": flop_per_sample,
+                         "fp32_peak_tflops": FP32_PEAK_TFLOPS})
+        roof["frac"] = roof["fp32_frac"] if bound == "fp32" else roof["hbm_frac"]
+        e["roofline"] = roof
+        e.update(kw)
+        out[name] = e
+
+    # ---- config 1 from the wire format: 1024 channels x 240 k samples of u8 IQ -> fused unpack + FIR64/10 ------------
+    n_ch, n = 1024 // q, 240_000
+    iq = torch.randint(0, 256, (n_ch, 2 * n), dtype=torch.uint8, device=dev, generator=g)
+    fir = blocks.Fir(ctx, taps, DECIM)
+    ms, best = _timed(lambda: fir.run_u8(iq), 6, 3, world, dev)
+    entry("config1_u8_fir64_decim10", world * n_ch * n, ms, best, "fp32", world * n_ch * n * 2.8, 25.6,
+          workload=f"{n_ch} channels x {n} samples of rtlsdr u8 IQ per GPU -> unpack + FIR64/10 (one kernel), cf32 out",
+          scaling="weak")
+    fir.close()
+    # ---- config 3: the same input through the whole FM receiver, one fused kernel -------------------------------------
+    rx = blocks.FmReceiver(ctx, taps, DECIM, 0.2, n_ch, n)
+    n_audio = rx.next_out_len(n)
+    audio = torch.empty((n_ch, max(n_audio, 1)), dtype=torch.float32, device=dev)
+
+    def fm():
+        rx.reset()
+        rx.push(iq, audio)
+    ms, best = _timed(fm, 6, 3, world, dev)
+    entry("config3_fm_receiver_1024ch", world * n_ch * n, ms, best, "fp32", world * n_ch * (n * 2 + n_audio * 4), 25.6 + 12.84,
+          workload=f"{n_ch} channels x {n} samples of u8 IQ per GPU -> FIR64/10 -> discriminator -> 1/5 resampler -> "
+                   f"{n_audio} audio samples per channel; one kernel per push (fused={rx.fused})",
+          scaling="weak", parity_note="resampler parity UNPINNED (libsamplerate absent): held to the builder's own f64 definition")
+    rx.close()
+    del iq, audio
+    # ---- config 2: Hann + FFT1024 + |X|^2 averaged over K = 64, 2^26 samples --------------------------------------------
+    n2 = (1 << 26) // q
+    x = torch.view_as_complex(torch.randn(n2, 2, device=dev, generator=g))
+    psd = blocks.Psd(ctx, NFFT, capi.WINDOW_HANN)
+    ms, best = _timed(lambda: psd.run(x, K_AVG), 6, 3, world, dev)
+    entry("config2_psd_1024_hann_k64", world * n2, ms, best, "hbm", world * (n2 * 8 + n2 // K_AVG * 4), 55.0,
+          workload=f"2^{int(np.log2(n2))} cf32 samples per GPU -> Hann -> FFT1024 -> |X|^2 averaged over K=64", scaling="weak")
+    psd.close()
+    del x
+    # ---- config 4: 4096 OOK streams, sharded across the ranks ---------------------------------------------------------
+    n_streams, n_blocks = 4096 // q, 500
+    lo, hi = shard.split_units(n_streams, rank, world)
+    caps = [synth.ook_capture_u8(n_blocks, seed=4 + s, n_packets=2)[0] for s in range(16)]
+    iq = torch.from_numpy(np.stack(caps)).to(dev)[torch.arange(lo, hi, device=dev) % 16].contiguous()
+    ook = blocks.Ook(ctx, hi - lo, n_blocks, 256000, 4096, 64)
+    ms, best = _timed(lambda: ook.decode(iq), 4, 2, world, dev, inner=3)
+    ns = n_streams * n_blocks * 512
+    n_pk = torch.tensor([len(ook.packets())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(n_pk)
+    entry("config4_ook_4096_streams", ns, ms, best, "hbm", ns * 2.0,
+          workload=f"{n_streams} streams x {n_blocks} blocks of 512 u8 IQ samples, {n_streams // world} streams per GPU, "
+                   "envelope -> trigger -> slicer -> rle -> matchers -> packets (bit-exact chain, 4 kernels)",
+          scaling="strong", packets_decoded=int(n_pk.item()))
+    ook.close()
+    del iq
+    # ---- config 5: 4096 taps over 2^30 samples, 16384-point blocks sharded across the ranks -------------------------------
+    nh, n5, nfft = 4096, (1 << 30) // q, 16384
+    rng = np.random.default_rng(6)
+    h = ((rng.standard_normal(nh) + 1j * rng.standard_normal(nh)) / 64).astype(np.complex64)
+    sh = shard.fastfir_shard(n5, nh, nfft, rank, world)
+    xs = torch.empty(max(sh.in_len, 1), dtype=torch.complex64, device=dev)
+    for a0 in range(0, sh.in_len, 1 << 27):                      # generated in pieces: randn's temporaries stay small
+        a1 = min(sh.in_len, a0 + (1 << 27))
+        xs[a0:a1] = torch.view_as_complex(torch.randn(a1 - a0, 2, device=dev, generator=g))
+    ff = blocks.FastFir(ctx, h, nfft)
+    ys = torch.empty(sh.out_len + 1, dtype=torch.complex64, device=dev)
+    ms, best = _timed(lambda: ff.run(xs[: sh.in_len], out=ys), 4, 2, world, dev, inner=2)
+    n_out_all = shard.fastfir_shard(n5, nh, nfft, world - 1, world)
+    n_out_all = n_out_all.out_start + n_out_all.out_len          # outputs of the whole job
+    flop16 = (2 * 5 * nfft * 14 + 6 * nfft) / float(nfft - nh + 1)
+    entry("config5_fastfir_4096taps_2pow30", n_out_all, ms, best, "fp32", n_out_all * 16.0, flop16,
+          workload=f"4096 complex taps over a 2^{int(np.log2(n5))}-sample cf32 stream, overlap-save in 16384-point blocks "
+                   f"(12289 outputs kept per block), {world} contiguous block ranges, outputs left sharded",
+          scaling="strong")
+    if world > 1:
+        # the same with every shard's output gathered on rank 0 (SURVEY 7.7: the gather, not the filter, bounds this form)
+        width = max(shard.fastfir_shard(n5, nh, nfft, r, world).out_len for r in range(world)) + 1
+        ysend = ys if ys.numel() == width else torch.cat([ys, ys.new_zeros(width - ys.numel())])
+        glist = [torch.empty(width, dtype=torch.complex64, device=dev) for _ in range(world)] if rank == 0 else None
+
+        def filt_and_gather():
+            ff.run(xs[: sh.in_len], out=ysend[: sh.out_len + 1])
+            dist.gather(torch.view_as_real(ysend), [torch.view_as_real(t) for t in glist] if rank == 0 else None, dst=0)
+        ms_g, best_g = _timed(filt_and_gather, 3, 1, world, dev, inner=1)
+        out["config5_fastfir_4096taps_2pow30"]["gathered_to_rank0"] = {
+            "value": n_out_all / (ms_g * 1e-3) / 1e6, "unit": UNIT, "ms": ms_g, "ms_best": best_g,
+            "gather": f"dist.gather (NCCL) of {width * 8 / 2**30:.2f} GiB per rank into rank 0"}
+        del glist, ysend
+    ff.close()
+    del xs, ys
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -287,10 +458,15 @@ def run_ours(args):
             except Exception as e:                         # e.g. CUDA IPC not permitted in this container
                 print(f"bench.py rank {rank}: lrc_gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
                 gather = None
-        # bounded-time probe before the timed loop depends on it: one push + arrival wait per slot on a side stream,
-        # polled from the host.  A peer whose flag write never arrives would otherwise hang the bench inside a
-        # device-side wait.  The probing stream can never drain in that case, so the process cannot fall back: it
-        # fails fast with a message instead (rerun with --gather nccl).
+        dist.all_reduce(ok)                                # all ranks must agree on the mechanism BEFORE anyone waits on a peer
+        if int(ok.item()) != world:
+            if gather is not None:
+                gather.close()
+            gather = None
+        # bounded-time probe before the timed loop depends on it (every rank created and connected its Gather): one push +
+        # arrival wait per slot on a side stream, polled from the host.  A peer whose flag write never arrives would
+        # otherwise hang the bench inside a device-side wait; the probing stream can never drain in that case, so the
+        # process cannot fall back: it fails fast with a message instead (rerun with --gather nccl).
         if gather is not None:
             side = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(side):
@@ -309,11 +485,6 @@ def run_ours(args):
                 print(f"bench.py rank {rank}: lrc_gather probe did not complete in {args.gather_probe_s:.0f} s "
                       "(a peer's arrival flag never came); rerun with --gather nccl", file=sys.stderr, flush=True)
                 os._exit(3)
-        dist.all_reduce(ok)                                # all ranks must agree on the mechanism
-        if int(ok.item()) != world:
-            if gather is not None:
-                gather.close()
-            gather = None
         if gather is None:
             gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
             gather_kind = "NCCL all_gather_into_tensor of output rows (async, 2 slots)"
@@ -391,6 +562,41 @@ def run_ours(args):
                 raise SystemExit(f"bench.py rank {rank}: lrc_gather slot {b} differs from the NCCL all-gather")
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    # ---- where a multi-GPU step's time goes (0.93 at 8 GPUs unexplained): every rank's own kernel time, and
+    # the same timed loop again WITHOUT the gather (no pushes, no arrival waits), max over ranks
+    diag = None
+    if world > 1:
+        kall = torch.zeros(world, device=dev, dtype=torch.float64)
+        kall[rank] = kern_ms
+        dist.all_reduce(kall)
+        dist.barrier()
+        torch.cuda.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for i in range(args.steps):
+            chain.run(x, K_AVG, outs[i & 1])
+        n1.record()
+        torch.cuda.synchronize()
+        tn = torch.tensor([n0.elapsed_time(n1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        # one rank alone (the others idle): is the kernel itself slower when its peers run (power, NVLink inbound writes)?
+        solo = torch.zeros(1, device=dev, dtype=torch.float64)
+        dist.barrier()
+        if rank == 0:
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.steps):
+                chain.run(x, K_AVG, outs[i & 1])
+            s1.record()
+            torch.cuda.synchronize()
+            solo[0] = s0.elapsed_time(s1) / args.steps
+        dist.barrier()
+        diag = {"kernel_ms_per_rank": [float(v) for v in kall.tolist()],
+                "ms_per_step_without_gather_max_over_ranks": float(tn.item()) / args.steps,
+                "ms_per_step_rank0_alone_peers_idle": float(solo.item()),
+                "note": "ms_per_step - ms_per_step_without_gather = cost of the gather (pushes, arrival waits, final drain over "
+                        "`steps` steps); without_gather - rank0_alone = what running next to busy peers costs the kernel"}
     clocks = None
     if sampler:
         # NVML refreshes its clock reading only every few tens of ms: when the timed region was too short
@@ -418,9 +624,10 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     e2e_frames = min(frames, args.e2e_frames)
     n_e = n_input(e2e_frames)
-    xh = torch.empty(n_e, dtype=torch.complex64, pin_memory=True)
+    bound_cpus = ctx.bind_thread()                         # this rank's thread on the GPU's NUMA node (no-op on one node)
+    xh = ctx.pinned(n_e, torch.complex64)                  # lrc_host_alloc: pinned, on the GPU's NUMA node
     xh.copy_(x[:n_e])
-    rows_h = torch.empty((e2e_frames // K_AVG, NFFT), dtype=torch.float32, pin_memory=True)
+    rows_h = ctx.pinned((e2e_frames // K_AVG, NFFT), torch.float32)
     chain.run_host(xh, K_AVG, rows_h)                      # warm-up (allocates the ring)
     if world > 1:
         dist.barrier()
@@ -434,9 +641,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e * e2e_steps / float(te.item()) / 1e6
-    # the same chain fed in the reference's wire format (rtlsdr u8 I,Q: 2 bytes per sample over PCIe, unpacked on
-    # the device): informational, NOT the headline e2e (which keeps cf32 host buffers like the metric says)
-    iqh = torch.empty(2 * n_e, dtype=torch.uint8, pin_memory=True)
+    # the same chain fed in the reference's own wire format (rtlsdr u8 I,Q, rtlsdr.rs:160-162: 2 bytes per sample over
+    # PCIe, data_to_samples on the device): first-class beside the cf32 figure, with its own copies declared
+    iqh = ctx.pinned(2 * n_e, torch.uint8)
     iqh.copy_((x[:n_e].view(torch.float32).reshape(-1).clamp(-1, 1) * 127 + 127).round().to(torch.uint8))
     chain.run_host_u8(iqh, K_AVG, rows_h)
     torch.cuda.synchronize()
@@ -450,33 +657,51 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tu, op=dist.ReduceOp.MAX)
     e2e_u8_value = world * n_e * e2e_steps / float(tu.item()) / 1e6
-    del iqh
-    # what bounds e2e: a bare pinned-host -> device copy of the same buffer on this box's PCIe link
+    # what bounds e2e: bare pinned-host -> device copies of the same buffer, ALL ranks copying at the same time (the host
+    # side -- DRAM and PCIe root complexes -- is shared by the GPUs of a box), max over ranks
     xd = torch.empty(n_e, dtype=torch.complex64, device=dev)
     xd.copy_(xh, non_blocking=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(3):
         xd.copy_(xh, non_blocking=True)
     c1.record()
     torch.cuda.synchronize()
-    h2d_gbs = 3 * n_e * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    tc = torch.tensor([c0.elapsed_time(c1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_gbs = 3 * n_e * 8 / float(tc.item()) / 1e9        # per GPU, with every GPU of the job copying
     del xd
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+    # ---- the other BASELINE configs (every rank takes part: configs 4 and 5 are sharded across the ranks) ----------------
+    extra = None
+    if not args.no_extra:
+        del x, xh
+        torch.cuda.empty_cache()
+        extra = run_extras(ctx, world, rank, peak, quick=args.quick_extra)
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
         alg_bytes = n_in * BYTES_PER_SAMPLE + rows * NFFT * 4
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes per launch from the committed ncu capture -- only while the capture still describes THIS kernel: the
+        # file records the sha256 of the kernel's sources at capture time (tools/chain_traffic.py writes it)
+        traffic, traffic_note = None, "no ncu capture committed for this kernel source"
         tp = os.path.join(ROOT, "profiles", "chain_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("kernel_source_sha256") == chain_source_sha():
+                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic_note = f"ncu dram__bytes_read+write of one launch, {tj.get('capture', 'profiles/')}"
+                else:
+                    traffic_note = "profiles/chain_traffic.json was captured for an older kernel source: not reported"
             except Exception:
                 traffic = None
         cpu = None
@@ -492,24 +717,32 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(frames), "ntaps": NTAPS, "decim": DECIM, "nfft": NFFT, "k_avg": K_AVG,
-                       "window": "hann", "l2": "input 5.4 GB per step >> 126 MB L2, no flush needed",
-                       "sharding": f"{world} independent streams, one per GPU; gather of output rows only",
-                       "gather": gather_kind,
-                       "e2e_workload": workload_name(e2e_frames) + f", {e2e_steps} steps through lrc_chain_run_host"},
+            "config": config_dict(frames, world),
+            "run": {"gather": gather_kind, "numa": {"gpu_node": ctx.numa_node, "host_nodes": ctx.numa_nodes,
+                                                    "rank_thread_bound_to_cpus": bound_cpus,
+                                                    "pinned_buffers": "lrc_host_alloc (preferred node = the GPU's)"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "chain_kernel<64,10,10,7> (+ psd_reduce)",
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                         "kernel": "chain_kernel<64,10,10,7> (+ psd_reduce)",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e * 8,
                     "d2h_bytes_per_step": (e2e_frames // K_AVG) * NFFT * 4,
-                    "bound": "pcie h2d", "h2d_copy_gbs_measured": h2d_gbs,
+                    "workload": workload_name(e2e_frames) + f" ({e2e_steps} steps through lrc_chain_run_host; a smaller batch than "
+                                "the device-resident step: the rate is PCIe-bound and does not depend on it)",
+                    "bound": "pcie h2d", "h2d_copy_gbs_per_gpu_all_ranks_copying": h2d_gbs,
                     "frac_of_h2d_copy": (e2e_value / world) * 8e6 / (h2d_gbs * 1e9)},
-            "e2e_u8_wire_format": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": n_e * 2,
-                                   "note": "same chain through lrc_chain_run_host_u8: host buffers hold rtlsdr u8 I,Q, "
-                                           "data_to_samples runs on the device; informational"},
+            "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": n_e * 2,
+                       "d2h_bytes_per_step": (e2e_frames // K_AVG) * NFFT * 4,
+                       "frac_of_h2d_copy": (e2e_u8_value / world) * 2e6 / (h2d_gbs * 1e9),
+                       "note": "the same chain and step through lrc_chain_run_host_u8: host buffers hold the reference's own wire "
+                               "format, rtlsdr u8 I,Q (rtlsdr.rs:160-162); data_to_samples runs on the device"},
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
         }
+        if diag:
+            line["scaling_diagnostics"] = diag
+        if extra:
+            line["extra"] = extra
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -535,6 +768,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1.5, dest="cpu_seconds",
                     help="per-thread seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra", help="skip the per-config extra block")
+    ap.add_argument("--quick-extra", action="store_true", dest="quick_extra", help="extra block at 1/8 size (smoke runs)")
     ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
                     help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],

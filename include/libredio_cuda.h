@@ -52,7 +52,13 @@ int lrc_ctx_create(int device, lrc_ctx **ctx);
 int lrc_ctx_destroy(lrc_ctx *ctx);
 int lrc_ctx_sync(lrc_ctx *ctx);                       /* cudaStreamSynchronize of the context stream */
 int lrc_ctx_sm_count(lrc_ctx *ctx, int *n_sm);
-/* pinned host memory for the ring / *_host entry points */
+/* NUMA node of the GPU (-1 if sysfs does not say) and the number of online nodes of the host */
+int lrc_ctx_numa_node(lrc_ctx *ctx, int *node, int *n_nodes);
+/* pin the calling thread to the CPUs of the GPU's NUMA node (no-op on a single-node host); *n_cpus = CPUs bound to */
+int lrc_ctx_bind_thread(lrc_ctx *ctx, int *n_cpus);
+/* pinned host memory for the ring / *_host entry points, placed on the GPU's NUMA node when the host has several.
+ * A plan object (lrc_fir_stream, lrc_psd, lrc_chain, lrc_resampler, lrc_fmrx, lrc_ook, ...) owns scratch and carried
+ * state: use it from ONE thread / stream at a time.  Different plans of one context are independent. */
 int lrc_host_alloc(lrc_ctx *ctx, size_t bytes, void **h_ptr);
 int lrc_host_free(lrc_ctx *ctx, void *h_ptr);
 /* synchronous device -> host copy (for the debug views below and bindings without a CUDA runtime) */

@@ -54,17 +54,39 @@ class Context:
         check(self.lib.lrc_ctx_sm_count(self.h, C.byref(n)), "lrc_ctx_sm_count")
         self.sm_count = n.value
         self.tdev = torch.device("cuda", device)
+        node, nodes = C.c_int(), C.c_int()
+        check(self.lib.lrc_ctx_numa_node(self.h, C.byref(node), C.byref(nodes)), "lrc_ctx_numa_node")
+        self.numa_node, self.numa_nodes = node.value, nodes.value
+        self._pinned = []
 
     def sync(self):
         torch.cuda.synchronize(self.device)
 
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.lib.lrc_host_free(self.h, p)
+            self._pinned = []
             self.lib.lrc_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
+    def bind_thread(self) -> int:
+        """pin the calling thread to the CPUs of the GPU's NUMA node; returns the CPUs bound to (0 = left alone)"""
+        n = C.c_int()
+        check(self.lib.lrc_ctx_bind_thread(self.h, C.byref(n)), "lrc_ctx_bind_thread")
+        return n.value
+
     def pinned(self, shape, dtype):
-        return torch.empty(shape, dtype=dtype, pin_memory=True)
+        """pinned host tensor from lrc_host_alloc (placed on the GPU's NUMA node); lives until the context closes"""
+        if isinstance(shape, int):
+            shape = (shape,)
+        n = int(np.prod(shape))
+        es = torch.empty(0, dtype=dtype).element_size()
+        p = C.c_void_p()
+        check(self.lib.lrc_host_alloc(self.h, max(n * es, 1), C.byref(p)), "lrc_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_char * max(n * es, 1)).from_address(p.value)
+        return torch.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 # ---- (1) -------------------------------------------------------------------------------------------

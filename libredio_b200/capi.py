@@ -39,6 +39,8 @@ SIGNATURES = {
     "lrc_ctx_destroy": (_i, [_vp]),
     "lrc_ctx_sync": (_i, [_vp]),
     "lrc_ctx_sm_count": (_i, [_vp, C.POINTER(_i)]),
+    "lrc_ctx_numa_node": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "lrc_ctx_bind_thread": (_i, [_vp, C.POINTER(_i)]),
     "lrc_host_alloc": (_i, [_vp, _sz, _pp]),
     "lrc_host_free": (_i, [_vp, _vp]),
     "lrc_copy_to_host": (_i, [_vp, _vp, _vp, _sz]),

@@ -18,6 +18,8 @@ struct lrc_ctx {
     cudaStream_t stream;       // default compute stream of the context
     cudaStream_t copy_stream;  // H2D ring copies
     cudaStream_t out_stream;   // D2H of results
+    int          numa_node;    // NUMA node the GPU hangs off (sysfs), -1 if unknown
+    int          numa_nodes;   // online NUMA nodes of the host
 };
 
 void lrc_set_error(const char *fmt, ...);

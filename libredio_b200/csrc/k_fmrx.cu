@@ -62,16 +62,16 @@ struct Args {
 // length (+-1 tile): no tail wave, whatever the channel count.  A range starts with a priming round (history of its first
 // tile) and primes again wherever it crosses into the next channel pair.
 struct RoundIter {
-    long long g, g_end;                                   // current global tile, end of the range
+    int g, g_end;                                         // current global tile, end of the range
     int q, nq;                                            // round within the tile (-1 = priming round), rounds of the tile
-    long long pair, ti;                                   // channel pair, tile within the pair
+    int pair, ti;                                         // channel pair, tile within the pair
     __device__ void load(const Args &a)
     {
-        pair = g / a.tiles_per_pair;
-        ti = g % a.tiles_per_pair;
+        pair = g / (int)a.tiles_per_pair;
+        ti = g - pair * (int)a.tiles_per_pair;
         nq = ti == a.tiles_per_pair - 1 ? a.last_rounds : ROUNDS;
     }
-    __device__ void init(const Args &a, long long g0, long long g1) { g = g0; g_end = g1; q = -1; if (g < g_end) load(a); }
+    __device__ void init(const Args &a, int g0, int g1) { g = g0; g_end = g1; q = -1; nq = ROUNDS; pair = ti = 0; if (g < g_end) load(a); }
     __device__ bool valid() const { return g < g_end; }
     __device__ void next(const Args &a)
     {
@@ -82,12 +82,13 @@ struct RoundIter {
         }
     }
     __device__ bool last_of_segment(const Args &a) const { return q == nq - 1 && (g + 1 == g_end || ti + 1 == a.tiles_per_pair); }
-    __device__ long long m_tile0(const Args &a) const { return a.m0 + ti * TILE_A; }
+    __device__ long long m_tile0(const Args &a) const { return a.m0 + (long long)ti * TILE_A; }
     __device__ long long nz0(const Args &a) const { return M * m_tile0(a) + (long long)ROUND_Z * q; }   // first baseband index
 };
 }  // namespace fmrx
 
-__global__ void __launch_bounds__(fmrx::NT, 3)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(fmrx::NT, MIN_CTAS)
 fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTaps<fmrx::NTAPS> taps127,
             const __grid_constant__ RsTaps<fmrx::TPP> rtaps)
 {
@@ -119,11 +120,11 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
         long long c_lo = lo, c_hi = hi < HB ? hi : HB, k_lo = lo > HB ? lo : HB, k_hi = hi;
         const uint32_t nc = c_hi > c_lo ? (uint32_t)(c_hi - c_lo) : 0u, nk = k_hi > k_lo ? (uint32_t)(k_hi - k_lo) : 0u;
         int live = 0;
-        for (int c = 0; c < 2; ++c) live += (2 * it.pair + c < a.n_ch);
+        for (int c = 0; c < 2; ++c) live += (2 * (long long)it.pair + c < a.n_ch);
         total = (nc + nk) * live;
         mbar_expect_tx(&bar[stage], total);
         for (int c = 0; c < 2; ++c) {
-            const long long chn = 2 * it.pair + c;
+            const long long chn = 2 * (long long)it.pair + c;
             if (chn >= a.n_ch) continue;
             uint8_t *dst = fmrx_smem + (stage * 2 + c) * RAW_BYTES;
             if (nc) tma_load_1d(dst + (c_lo - a0), a.carry + chn * a.carry_stride + c_lo, nc, &bar[stage]);
@@ -135,7 +136,7 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
         long long lo, hi, a0;
         span(it.nz0(a), &lo, &hi, &a0);
         for (int c = 0; c < 2; ++c) {
-            const long long chn = 2 * it.pair + c;
+            const long long chn = 2 * (long long)it.pair + c;
             if (chn >= a.n_ch) continue;
             uint16_t *dst = reinterpret_cast<uint16_t *>(fmrx_smem + (stage * 2 + c) * RAW_BYTES);
             const uint8_t *crow = a.carry + chn * a.carry_stride, *krow = a.chunk + chn * a.chunk_stride;
@@ -149,8 +150,8 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
     RoundIter cur, ld;
     {
         const long long g0 = a.total_tiles * blockIdx.x / gridDim.x, g1 = a.total_tiles * (blockIdx.x + 1) / gridDim.x;
-        cur.init(a, g0, g1);
-        ld.init(a, g0, g1);
+        cur.init(a, (int)g0, (int)g1);
+        ld.init(a, (int)g0, (int)g1);
     }
     if (a.use_tma) {
         for (int s = 0; s < 2; ++s) {
@@ -164,7 +165,7 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
     // registers) in the same straight-line block, so the discriminator's dependent chain (x conj(x'), reciprocal, degree-6
     // polynomial) fills issue slots between the FIR's packed FMAs instead of standing alone between two barriers -- as a
     // phase of its own it took 30 % of the kernel for 13 % of its instructions (profiles/r2_fmrx_v1_ncu_phases.txt).
-    struct Pend { bool valid, tile_end, seg_end; int base, k0; long long k0o, pair; } pend;
+    struct Pend { bool valid, tile_end, seg_end; int base, k0, k0o, pair; } pend;
     pend.valid = pend.tile_end = pend.seg_end = false; pend.base = 0; pend.k0 = RF + 1; pend.k0o = 0; pend.pair = 0;
     float2 zp[RF];
 #pragma unroll
@@ -219,7 +220,7 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
             for (int r = 0; r < R2; ++r) acc[r] = make_float2(0.f, 0.f);
             RsDec2Steps<M, R2, TPP, 0, WIN2>::run(ring + t * (R2 * M), rtaps, acc);
             const long long k0o = pend.k0o + R2 * t;                                // index into the call's output
-            const long long chA = 2 * pend.pair, chB = chA + 1;
+            const long long chA = 2 * (long long)pend.pair, chB = chA + 1;
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
                 if (k0o + r < a.n_out) {
@@ -240,7 +241,7 @@ fmrx_kernel(const __grid_constant__ fmrx::Args a, const __grid_constant__ FirTap
             pend.base = cur.q < 0 ? RF * tt - (ROUND_Z - HIST) : HIST + ROUND_Z * cur.q + RF * tt;
             pend.tile_end = cur.q == cur.nq - 1;
             pend.seg_end = cur.last_of_segment(a);
-            pend.k0o = cur.m_tile0(a) - a.m0;
+            pend.k0o = cur.ti * TILE_A;
             pend.pair = cur.pair;
             cur.next(a);
         }
@@ -320,7 +321,8 @@ extern "C" int lrc_fmrx_create(lrc_ctx *ctx, const float *h_taps, int ntaps, int
                 return LRC_ERR_CUDA;
             }
         }
-        cudaError_t e = cudaFuncSetAttribute(fmrx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fmrx::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(fmrx_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmrx::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fmrx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmrx::SMEM_BYTES);
         if (e != cudaSuccess) { lrc_set_error("lrc_fmrx_create: %s", cudaGetErrorString(e)); lrc_fmrx_destroy(f); return LRC_ERR_CUDA; }
     } else {
         rc = lrc_fir_stream_create(f->fir, n_ch, max_chunk, 1, &f->fs);
@@ -406,13 +408,15 @@ extern "C" int lrc_fmrx_push(lrc_fmrx *f, const uint8_t *d_iq, size_t n, size_t 
         a.tiles_per_pair = (no + TILE_A - 1) / TILE_A;
         const long long outs_last = no - (a.tiles_per_pair - 1) * TILE_A;         // outputs of a pair's last tile
         a.last_rounds = (int)((M * (outs_last - 1) + 1 + ROUND_Z - 1) / ROUND_Z);
-        const long long pairs = ((long long)f->n_ch + 1) / 2, slots = (long long)f->ctx->n_sm * 3;
+        static const int occ = getenv("LRC_FMRX_OCC") ? atoi(getenv("LRC_FMRX_OCC")) : 3;      // CTAs per SM (A/B: 2 = 128 registers)
+        const long long pairs = ((long long)f->n_ch + 1) / 2, slots = (long long)f->ctx->n_sm * (occ == 2 ? 2 : 3);
         a.total_tiles = pairs * a.tiles_per_pair;
         // TMA needs 16-byte aligned rows and piece boundaries: held and n multiples of 8 samples, aligned bases / strides
         a.use_tma = (f->held % 8 == 0) && (n % 8 == 0) && (((uintptr_t)d_iq & 15) == 0) && (a.chunk_stride % 16 == 0) &&
                     (a.row_abs0 % 8 == 0);
         long long blocks = slots < a.total_tiles ? slots : a.total_tiles;
-        fmrx_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, s>>>(a, f->taps127, f->rtaps);
+        if (occ == 2) fmrx_kernel<2><<<(unsigned)blocks, NT, SMEM_BYTES, s>>>(a, f->taps127, f->rtaps);
+        else          fmrx_kernel<3><<<(unsigned)blocks, NT, SMEM_BYTES, s>>>(a, f->taps127, f->rtaps);
         LRC_CUDA(cudaGetLastError());
     }
     // carry for the next call: everything from the start of the next segment's priming round, floored to 8 samples

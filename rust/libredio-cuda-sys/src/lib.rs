@@ -35,6 +35,8 @@ extern "C" {
     pub fn lrc_ctx_destroy(ctx: *mut lrc_ctx) -> c_int;
     pub fn lrc_ctx_sync(ctx: *mut lrc_ctx) -> c_int;
     pub fn lrc_ctx_sm_count(ctx: *mut lrc_ctx, n_sm: *mut c_int) -> c_int;
+    pub fn lrc_ctx_numa_node(ctx: *mut lrc_ctx, node: *mut c_int, n_nodes: *mut c_int) -> c_int;
+    pub fn lrc_ctx_bind_thread(ctx: *mut lrc_ctx, n_cpus: *mut c_int) -> c_int;
     pub fn lrc_host_alloc(ctx: *mut lrc_ctx, bytes: size_t, h_ptr: *mut *mut c_void) -> c_int;
     pub fn lrc_host_free(ctx: *mut lrc_ctx, h_ptr: *mut c_void) -> c_int;
     pub fn lrc_copy_to_host(ctx: *mut lrc_ctx, h_dst: *mut c_void, d_src: *const c_void, bytes: size_t) -> c_int;
