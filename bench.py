@@ -329,6 +329,18 @@ def run_extras(ctx, world, rank, peak_hbm, quick=False):
           workload=f"{n_ch} channels x {n} samples of rtlsdr u8 IQ per GPU -> unpack + FIR64/10 (one kernel), cf32 out",
           scaling="weak")
     fir.close()
+    # ---- the headline chain fed the wire format (device-resident u8 IQ): unpack inside the kernel's tile load ------------
+    fr8 = 16384 // q
+    n8 = n_input(fr8)
+    iq8 = torch.randint(0, 256, (2 * n8,), dtype=torch.uint8, device=dev, generator=g)
+    ch8 = blocks.Chain(ctx, taps, DECIM, NFFT, capi.WINDOW_HANN)
+    rows8 = torch.empty((fr8 // K_AVG, NFFT), dtype=torch.float32, device=dev)
+    ms, best = _timed(lambda: ch8.run_u8(iq8, K_AVG, rows8), 6, 3, world, dev)
+    entry("headline_chain_from_u8", world * n8, ms, best, "fp32", world * (n8 * 2.0 + rows8.numel() * 4), 31.6 + 20.0,
+          workload=f"{n8} samples of u8 IQ per GPU -> i2f in the tile (bit-exact) -> FIR64/10 -> {fr8} x 1024-pt Hann FFT -> |X|^2 "
+                   f"avg K={K_AVG}; one kernel, 2 B/sample from HBM", scaling="weak")
+    ch8.close()
+    del iq8, rows8
     # ---- config 3: the same input through the whole FM receiver, one fused kernel -------------------------------------
     rx = blocks.FmReceiver(ctx, taps, DECIM, 0.2, n_ch, n)
     n_audio = rx.next_out_len(n)
@@ -527,26 +539,34 @@ def run_ours(args):
     torch.cuda.synchronize()
     if sampler:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev[0].record()
-    for i in range(args.steps):
-        b = i & 1
-        if gather is not None:
-            gather.wait_sent(b)
-        elif pending[b] is not None:
-            pending[b].wait()
-            pending[b] = None
-        kev[i][0].record()
-        chain.run(x, K_AVG, outs[b])
-        kev[i][1].record()
-        if gather is not None:
-            gather.push(b, outs[b])
-        elif world > 1:
-            pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
-        if i == args.steps - 1:
-            drain()                                        # the last gathers are inside the timed region
-        ev[i + 1].record()
+    def timed_loop(with_gather: bool):
+        """EXACTLY `steps` steps between two events (per-step kernel events inside); the last gathers are drained inside"""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ev0.record()
+        for i in range(args.steps):
+            b = i & 1
+            if with_gather:
+                if gather is not None:
+                    gather.wait_sent(b)
+                elif pending[b] is not None:
+                    pending[b].wait()
+                    pending[b] = None
+            kev[i][0].record()
+            chain.run(x, K_AVG, outs[b])
+            kev[i][1].record()
+            if with_gather:
+                if gather is not None:
+                    gather.push(b, outs[b])
+                elif world > 1:
+                    pending[b] = dist.all_gather_into_tensor(gath[b], outs[b], async_op=True)
+                if i == args.steps - 1:
+                    drain()                                    # the last gathers are inside the timed region
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1), float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    total_ms, kern_ms = timed_loop(True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -560,10 +580,8 @@ def run_ours(args):
             got = gather.buffer(b).reshape(world * rows, NFFT)
             if not torch.equal(got, want):
                 raise SystemExit(f"bench.py rank {rank}: lrc_gather slot {b} differs from the NCCL all-gather")
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    # ---- where a multi-GPU step's time goes (0.93 at 8 GPUs unexplained): every rank's own kernel time, and
-    # the same timed loop again WITHOUT the gather (no pushes, no arrival waits), max over ranks
+    # ---- where a multi-GPU step's time goes (0.93 at 8 GPUs unexplained): every rank's own kernel time, the
+    # same timed loop again WITHOUT the gather (no pushes, no arrival waits; max over ranks), and rank 0 alone
     diag = None
     if world > 1:
         kall = torch.zeros(world, device=dev, dtype=torch.float64)
@@ -571,30 +589,22 @@ def run_ours(args):
         dist.all_reduce(kall)
         dist.barrier()
         torch.cuda.synchronize()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record()
-        for i in range(args.steps):
-            chain.run(x, K_AVG, outs[i & 1])
-        n1.record()
-        torch.cuda.synchronize()
-        tn = torch.tensor([n0.elapsed_time(n1)], device=dev, dtype=torch.float64)
+        ng_ms, ng_kern = timed_loop(False)
+        tn = torch.tensor([ng_ms, ng_kern], device=dev, dtype=torch.float64)
         dist.all_reduce(tn, op=dist.ReduceOp.MAX)
         # one rank alone (the others idle): is the kernel itself slower when its peers run (power, NVLink inbound writes)?
-        solo = torch.zeros(1, device=dev, dtype=torch.float64)
+        solo = torch.zeros(2, device=dev, dtype=torch.float64)
         dist.barrier()
         if rank == 0:
-            torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for i in range(args.steps):
-                chain.run(x, K_AVG, outs[i & 1])
-            s1.record()
-            torch.cuda.synchronize()
-            solo[0] = s0.elapsed_time(s1) / args.steps
+            a_ms, a_kern = timed_loop(False)
+            solo[0], solo[1] = a_ms / args.steps, a_kern
         dist.barrier()
+        dist.all_reduce(solo)
         diag = {"kernel_ms_per_rank": [float(v) for v in kall.tolist()],
-                "ms_per_step_without_gather_max_over_ranks": float(tn.item()) / args.steps,
-                "ms_per_step_rank0_alone_peers_idle": float(solo.item()),
+                "ms_per_step_without_gather_max_over_ranks": float(tn[0].item()) / args.steps,
+                "kernel_ms_without_gather_max_over_ranks": float(tn[1].item()),
+                "ms_per_step_rank0_alone_peers_idle": float(solo[0].item()),
+                "kernel_ms_rank0_alone_peers_idle": float(solo[1].item()),
                 "note": "ms_per_step - ms_per_step_without_gather = cost of the gather (pushes, arrival waits, final drain over "
                         "`steps` steps); without_gather - rank0_alone = what running next to busy peers costs the kernel"}
     clocks = None

@@ -160,12 +160,17 @@ int    lrc_chain_destroy(lrc_chain *chain);
 size_t lrc_chain_frames(const lrc_chain *chain, size_t n_in);       /* whole frames in n_in samples */
 int    lrc_chain_run(lrc_chain *chain, const float *d_in, size_t n_in, size_t k_avg, float *d_rows,
                      size_t *n_rows, void *stream);
+/* same with rtlsdr u8 I,Q on the DEVICE (2 bytes per sample; rtlsdr::data_to_samples, rtlsdr.rs:160-162, folded into the
+ * kernel's tile load for the fused 64/10/1024 instance: HBM carries 2 B/sample, rows equal unpack-then-chain bit for bit) */
+int    lrc_chain_run_u8(lrc_chain *chain, const uint8_t *d_iq, size_t n_in, size_t k_avg, float *d_rows,
+                        size_t *n_rows, void *stream);
 /* same through HOST buffers (pinned recommended): chunked H2D on a copy stream overlapped with the
  * kernel through a double-buffered device ring, rows copied back; synchronous. */
 int    lrc_chain_run_host(lrc_chain *chain, const float *h_in, size_t n_in, size_t k_avg, float *h_rows,
                           size_t *n_rows);
 /* same with the rtlsdr wire format as host input: n_in samples of interleaved u8 I,Q (2 bytes per sample over
- * PCIe instead of 8); rtlsdr::data_to_samples (rtlsdr.rs:160-162) runs on the device in front of the chain. */
+ * PCIe instead of 8); rtlsdr::data_to_samples (rtlsdr.rs:160-162) runs on the device: inside the chain kernel's tile load
+ * for the fused instance, as a separate launch in front of the chain otherwise. */
 int    lrc_chain_run_host_u8(lrc_chain *chain, const uint8_t *h_iq, size_t n_in, size_t k_avg, float *h_rows,
                              size_t *n_rows);
 

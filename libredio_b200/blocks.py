@@ -283,6 +283,18 @@ class Chain:
         assert nr.value == rows
         return out
 
+    def run_u8(self, iq: torch.Tensor, k_avg: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """iq: device uint8 [2 n] of interleaved I,Q (the rtlsdr wire format); the unpack happens inside the kernel"""
+        assert iq.dtype == torch.uint8 and iq.is_cuda and iq.is_contiguous() and iq.dim() == 1 and iq.numel() % 2 == 0
+        n = iq.numel() // 2
+        rows = self.frames(n) // k_avg
+        if out is None:
+            out = torch.empty((rows, self.nfft), dtype=torch.float32, device=iq.device)
+        nr = C.c_size_t()
+        check(self.ctx.lib.lrc_chain_run_u8(self.h, _p(iq), n, k_avg, _p(out), C.byref(nr), _stream()), "lrc_chain_run_u8")
+        assert nr.value == rows
+        return out
+
     def run_host(self, x, k_avg: int, out=None):
         """x: pinned CPU complex64 tensor (or numpy array); returns rows as a CPU tensor/array of the same kind."""
         n = x.numel() if isinstance(x, torch.Tensor) else x.size

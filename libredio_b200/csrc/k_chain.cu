@@ -16,6 +16,7 @@
 // arithmetic of the other CTA on the SM.
 #include "fir_core.cuh"
 #include "fft_core.cuh"
+#include "unpack.cuh"
 #include <vector>
 #include <cmath>
 
@@ -44,6 +45,7 @@ struct lrc_chain {
     uint8_t *d_ring_u8[2]; size_t ring_u8_cap; // samples per slot (u8 IQ staging of lrc_chain_run_host_u8)
     cudaEvent_t ev_ready[2], ev_free[2];
     float   *d_rows; size_t rows_cap;          // floats
+    float   *d_u8tmp; size_t u8tmp_cap;        // lrc_chain_run_u8 without a fused instance: unpacked input (samples)
 };
 
 template <int NTAPS, int DECIM, int LOG2N, int R>
@@ -59,6 +61,14 @@ struct ChainCfg {
     static constexpr int NT = NFIR_T + NFFT_T;
     static constexpr int TILE_SAMPLES = (NFIR - 1) * Tile::STEP + Tile::WIN;   // last thread's window end
     static constexpr uint32_t TMA_BYTES = TILE_IN * 8;
+    // u8 instance: the raw IQ tile (2 B per sample) lands at the END of the cf32 tile buffer and is expanded in place
+    static constexpr uint32_t RAW_BYTES = TILE_IN * 2;
+    static constexpr uint32_t RAW_TMA_BYTES = RAW_BYTES & ~15u;                   // bulk part; the < 16-byte rest by hand
+    static constexpr int RAW_WORDS = (RAW_BYTES + 3) / 4;                         // two samples per word
+    static constexpr int RAW_OFF = (TILE_SAMPLES * 8 - (int)((RAW_BYTES + 15) & ~15u)) & ~15;
+    static constexpr int RAW_PER_THREAD = (RAW_WORDS + NFIR_T - 1) / NFIR_T;
+    static_assert(RAW_BYTES % 4 == 0, "whole words");
+    static_assert((RAW_BYTES - RAW_TMA_BYTES) / 4 <= NFIR_T, "the rest words fall into the last two words of their owners");
     static constexpr int OFF_HAND = TILE_SAMPLES * 8;                   // FIR -> FFT hand-over buffer
     static constexpr int OFF_XCHG = OFF_HAND + FFT::SMEM_CPX * 8;       // FFT pass exchange buffer
     static constexpr int OFF_BAR = OFF_XCHG + FFT::SMEM_CPX * 8;
@@ -69,7 +79,11 @@ struct ChainCfg {
 
 enum { BAR_FULL = 1, BAR_EMPTY = 2, BAR_TILE = 3, BAR_FFT = 4 };
 
-template <int NTAPS, int DECIM, int LOG2N, int R>
+// IS_U8: `in` points at rtlsdr u8 I,Q (2 bytes per sample, rtlsdr.rs:160-162).  The producers expand the raw tile to cf32
+// IN SHARED MEMORY with the one device definition of i2f (unpack.cuh: the reference's division and subtraction, bit-exact),
+// then run the very same FIR code on it, so the rows equal unpack-then-chain bit for bit while HBM (and PCIe, through
+// lrc_chain_run_host_u8) carries 2 bytes per sample instead of 8 and no separate unpack launch exists.
+template <int NTAPS, int DECIM, int LOG2N, int R, bool IS_U8>
 __global__ void __launch_bounds__(ChainCfg<NTAPS, DECIM, LOG2N, R>::NT, 2)
 chain_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
              float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items,
@@ -104,12 +118,52 @@ chain_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const
         size_t item = blockIdx.x, f0, f1;
         item_range(item, f0, f1);
         size_t f = f0;
-        if (tid == 0) {
-            mbar_expect_tx(bar, Cfg::TMA_BYTES);
-            tma_load_1d_evict_first(tile, in + f * Cfg::FRAME_ADV, Cfg::TMA_BYTES, bar);
-        }
+        const uint8_t *in8 = reinterpret_cast<const uint8_t *>(in);
+        uint8_t *raw = smem + Cfg::RAW_OFF;
+        auto load_frame = [&](size_t fr) {                       // thread 0
+            if (IS_U8) {
+                mbar_expect_tx(bar, Cfg::RAW_TMA_BYTES);
+                tma_load_1d_evict_first(raw, in8 + fr * (size_t)Cfg::FRAME_ADV * 2, Cfg::RAW_TMA_BYTES, bar);
+            } else {
+                mbar_expect_tx(bar, Cfg::TMA_BYTES);
+                tma_load_1d_evict_first(tile, in + fr * Cfg::FRAME_ADV, Cfg::TMA_BYTES, bar);
+            }
+        };
+        if (tid == 0) load_frame(f);
         while (true) {
-            mbar_wait(bar, phase);
+            if (IS_U8) {
+                // the last < 16 bytes of the raw tile are not a whole TMA unit: their owners fetch them with plain loads,
+                // issued before the wait (they can only fall into a thread's last two words)
+                constexpr int TMA_WORDS = (int)(Cfg::RAW_TMA_BYTES / 4), KL = Cfg::RAW_PER_THREAD;
+                uint32_t rest[2] = {0u, 0u};
+#pragma unroll
+                for (int k = KL - 2; k < KL; ++k) {
+                    const int i = tid + k * Cfg::NFIR_T;
+                    if (k >= 0 && i >= TMA_WORDS && i < Cfg::RAW_WORDS)
+                        rest[k - (KL - 2)] = *reinterpret_cast<const uint32_t *>(in8 + f * (size_t)Cfg::FRAME_ADV * 2 + 4 * (size_t)i);
+                }
+                mbar_wait(bar, phase);
+                // expand in place: every producer first takes its share of the raw words into registers, then (barrier)
+                // writes them back as cf32 -- the cf32 tile grows over the raw bytes only after all of them were read
+                uint32_t wv[Cfg::RAW_PER_THREAD];
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw);
+#pragma unroll
+                for (int k = 0; k < KL; ++k) {
+                    const int i = tid + k * Cfg::NFIR_T;
+                    wv[k] = i < TMA_WORDS ? rw[i] : (k >= KL - 2 ? rest[k - (KL - 2)] : 0u);
+                }
+                named_bar_sync(BAR_TILE, Cfg::NFIR_T);
+                float4 *t4 = reinterpret_cast<float4 *>(tile);
+#pragma unroll
+                for (int k = 0; k < Cfg::RAW_PER_THREAD; ++k) {
+                    const int i = tid + k * Cfg::NFIR_T;
+                    if (i < Cfg::RAW_WORDS)
+                        t4[i] = make_float4(lr_i2f_byte(wv[k], 0), lr_i2f_byte(wv[k], 1), lr_i2f_byte(wv[k], 2), lr_i2f_byte(wv[k], 3));
+                }
+                named_bar_sync(BAR_TILE, Cfg::NFIR_T);
+            } else {
+                mbar_wait(bar, phase);
+            }
             phase ^= 1;
             float2 acc[R];
             if (tid < Cfg::NFIR) Tile::run_cf32(tile + (size_t)tid * Tile::STEP, taps, acc);
@@ -122,10 +176,7 @@ chain_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const
             const bool has_next = nitem < n_items;
             // every FIR thread is done with the tile -> re-arm the TMA for the next frame
             named_bar_sync(BAR_TILE, Cfg::NFIR_T);
-            if (tid == 0 && has_next) {
-                mbar_expect_tx(bar, Cfg::TMA_BYTES);
-                tma_load_1d_evict_first(tile, in + nf * Cfg::FRAME_ADV, Cfg::TMA_BYTES, bar);
-            }
+            if (tid == 0 && has_next) load_frame(nf);
             // hand-over buffer free? (the FFT warps arrive on EMPTY once they hold the previous frame)
             if (!first) named_bar_sync(BAR_EMPTY, Cfg::NT);
             first = false;
@@ -204,6 +255,7 @@ extern "C" int lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, in
     c->fir = nullptr; c->psd = nullptr; c->d_tmp = nullptr; c->tmp_cap = 0;
     c->d_ring[0] = c->d_ring[1] = nullptr; c->ring_cap = 0; c->d_rows = nullptr; c->rows_cap = 0;
     c->d_ring_u8[0] = c->d_ring_u8[1] = nullptr; c->ring_u8_cap = 0;
+    c->d_u8tmp = nullptr; c->u8tmp_cap = 0;
     c->ev_ready[0] = c->ev_ready[1] = c->ev_free[0] = c->ev_free[1] = nullptr;
     int rc = lrc_fir_create(ctx, h_taps, ntaps, decim, &c->fir);       // also validates the taps
     if (!rc) rc = lrc_psd_create(ctx, nfft, window, &c->psd);
@@ -231,7 +283,7 @@ extern "C" int lrc_chain_destroy(lrc_chain *c)
     lrc_fir_destroy(c->fir); lrc_psd_destroy(c->psd);
     cudaFree(c->d_tw); cudaFree(c->d_win); cudaFree(c->d_partial); cudaFree(c->d_tmp);
     cudaFree(c->d_ring[0]); cudaFree(c->d_ring[1]); cudaFree(c->d_rows);
-    cudaFree(c->d_ring_u8[0]); cudaFree(c->d_ring_u8[1]);
+    cudaFree(c->d_ring_u8[0]); cudaFree(c->d_ring_u8[1]); cudaFree(c->d_u8tmp);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -248,10 +300,32 @@ extern "C" size_t lrc_chain_frames(const lrc_chain *c, size_t n_in)
     return (n_in - tile_in) / ((size_t)c->nfft * c->decim) + 1;
 }
 
-// rows_local rows of k_local frames each, starting at d_in; rows[r] (op)= scale * sum |X|^2
-static int chain_launch(lrc_chain *c, const float *d_in, size_t rows_local, size_t k_local, float *d_rows,
+template <bool IS_U8>
+static int chain_launch_fused(lrc_chain *c, const void *d_in, size_t k_local, size_t fpi, size_t ipr, size_t n_items, cudaStream_t s)
+{
+    using Cfg = ChainCfg<64, 10, 10, 7>;
+    auto kern = chain_kernel<64, 10, 10, 7, IS_U8>;
+    LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 1;
+    LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::SMEM_BYTES));
+    if (occ < 1) occ = 1;
+    static const size_t gm = lrc_grid_mult("LRC_CHAIN_GRID", 1);
+    size_t blocks = (size_t)c->ctx->n_sm * occ * gm;
+    if (blocks > n_items) blocks = n_items;
+    FirTaps<64> taps;
+    for (int i = 0; i < 64; ++i) taps.h[i] = c->taps[i];
+    kern<<<(unsigned)blocks, Cfg::NT, Cfg::SMEM_BYTES, s>>>((const float2 *)d_in, c->d_tw, c->d_win, c->d_partial,
+                                                           k_local, fpi, ipr, n_items, taps);
+    LRC_CUDA(cudaGetLastError());
+    return LRC_OK;
+}
+
+// rows_local rows of k_local frames each, starting at d_in (cf32, or u8 I,Q when input_is_u8 -- fused instance only);
+// rows[r] (op)= scale * sum |X|^2
+static int chain_launch(lrc_chain *c, const void *d_in_any, int input_is_u8, size_t rows_local, size_t k_local, float *d_rows,
                         float scale, int accumulate, cudaStream_t s)
 {
+    const float *d_in = (const float *)d_in_any;
     if (rows_local == 0 || k_local == 0) return LRC_OK;
     const size_t fpi = lrc_psd_frames_per_item(k_local);
     const size_t ipr = ceil_div(k_local, fpi);
@@ -259,22 +333,12 @@ static int chain_launch(lrc_chain *c, const float *d_in, size_t rows_local, size
     int rc = lrc_psd_ensure_partial(&c->d_partial, &c->partial_cap, n_items * (size_t)c->nfft);
     if (rc) return rc;
     if (c->fused) {
-        using Cfg = ChainCfg<64, 10, 10, 7>;
-        auto kern = chain_kernel<64, 10, 10, 7>;
-        LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int occ = 1;
-        LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::SMEM_BYTES));
-        if (occ < 1) occ = 1;
-        static const size_t gm = lrc_grid_mult("LRC_CHAIN_GRID", 1);
-        size_t blocks = (size_t)c->ctx->n_sm * occ * gm;
-        if (blocks > n_items) blocks = n_items;
-        FirTaps<64> taps;
-        for (int i = 0; i < 64; ++i) taps.h[i] = c->taps[i];
-        kern<<<(unsigned)blocks, Cfg::NT, Cfg::SMEM_BYTES, s>>>((const float2 *)d_in, c->d_tw, c->d_win, c->d_partial,
-                                                               k_local, fpi, ipr, n_items, taps);
-        LRC_CUDA(cudaGetLastError());
+        rc = input_is_u8 ? chain_launch_fused<true>(c, d_in_any, k_local, fpi, ipr, n_items, s)
+                         : chain_launch_fused<false>(c, d_in_any, k_local, fpi, ipr, n_items, s);
+        if (rc) return rc;
         return lrc_psd_reduce(c->d_partial, d_rows, c->nfft, ipr, rows_local, scale, accumulate, s);
     }
+    LRC_REQUIRE(!input_is_u8, LRC_ERR_INVALID, "chain_launch: u8 input without a fused instance");
     // unfused fallback: FIR into a scratch signal, then the PSD kernel
     const size_t n_frames = rows_local * k_local;
     const size_t n_dec = n_frames * (size_t)c->nfft;
@@ -304,7 +368,35 @@ extern "C" int lrc_chain_run(lrc_chain *c, const float *d_in, size_t n_in, size_
     if (rows == 0) return LRC_OK;
     LRC_REQUIRE(d_in && d_rows, LRC_ERR_INVALID, "lrc_chain_run: null buffer");
     LRC_REQUIRE(((uintptr_t)d_in & 15) == 0, LRC_ERR_INVALID, "lrc_chain_run: input must be 16-byte aligned");
-    return chain_launch(c, d_in, rows, k_avg, d_rows, 1.0f / (float)k_avg, 0, lrc_stream(c->ctx, stream));
+    return chain_launch(c, d_in, 0, rows, k_avg, d_rows, 1.0f / (float)k_avg, 0, lrc_stream(c->ctx, stream));
+}
+
+// device-resident rtlsdr u8 I,Q input: the fused instance expands the tile on chip; other shapes unpack into a scratch
+// buffer first (lrc_unpack_u8_cf32) and run the cf32 path
+extern "C" int lrc_chain_run_u8(lrc_chain *c, const uint8_t *d_iq, size_t n_in, size_t k_avg, float *d_rows,
+                                size_t *n_rows, void *stream)
+{
+    LRC_REQUIRE(c != nullptr, LRC_ERR_INVALID, "null plan");
+    LRC_BIND(c->ctx);
+    LRC_REQUIRE(k_avg >= 1, LRC_ERR_INVALID, "lrc_chain_run_u8: k_avg must be >= 1");
+    const size_t rows = lrc_chain_frames(c, n_in) / k_avg;
+    if (n_rows) *n_rows = rows;
+    if (rows == 0) return LRC_OK;
+    LRC_REQUIRE(d_iq && d_rows, LRC_ERR_INVALID, "lrc_chain_run_u8: null buffer");
+    cudaStream_t s = lrc_stream(c->ctx, stream);
+    if (c->fused) {
+        LRC_REQUIRE(((uintptr_t)d_iq & 15) == 0, LRC_ERR_INVALID, "lrc_chain_run_u8: input must be 16-byte aligned");
+        return chain_launch(c, d_iq, 1, rows, k_avg, d_rows, 1.0f / (float)k_avg, 0, s);
+    }
+    const size_t need = (rows * k_avg - 1) * (size_t)c->nfft * c->decim + (size_t)(c->nfft - 1) * c->decim + c->ntaps;
+    if (c->u8tmp_cap < need) {
+        cudaFree(c->d_u8tmp); c->d_u8tmp = nullptr; c->u8tmp_cap = 0;
+        LRC_CUDA(cudaMalloc(&c->d_u8tmp, need * sizeof(float2)));
+        c->u8tmp_cap = need;
+    }
+    const int urc = lrc_unpack_u8_cf32(c->ctx, d_iq, need * 2, c->d_u8tmp, s);
+    if (urc) return urc;
+    return chain_launch(c, c->d_u8tmp, 0, rows, k_avg, d_rows, 1.0f / (float)k_avg, 0, s);
 }
 
 static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_u8, size_t n_in, size_t k_avg,
@@ -326,7 +418,8 @@ static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_
     const bool slice_rows = k_avg > SEG_FRAMES;
     const size_t seg_frames = slice_rows ? SEG_FRAMES / 16 * 16 : (SEG_FRAMES / k_avg) * k_avg;
     const size_t slot_samples = seg_frames * adv + tail + 8;
-    if (c->ring_cap < slot_samples) {
+    const bool direct_u8 = input_is_u8 && c->fused;     // the fused u8 instance reads the raw slot itself
+    if (!direct_u8 && c->ring_cap < slot_samples) {
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
         c->ring_cap = 0;
         for (int i = 0; i < 2; ++i) LRC_CUDA(cudaMalloc(&c->d_ring[i], slot_samples * sizeof(float2)));
@@ -369,16 +462,17 @@ static int chain_run_host_impl(lrc_chain *c, const void *h_in_any, int input_is_
             LRC_CUDA(cudaMemcpyAsync(c->d_ring[b], h_in + 2 * f * adv, ns * sizeof(float2), cudaMemcpyHostToDevice, cs));
         LRC_CUDA(cudaEventRecord(c->ev_ready[b], cs));
         LRC_CUDA(cudaStreamWaitEvent(ks, c->ev_ready[b], 0));
-        if (input_is_u8) {
+        if (input_is_u8 && !direct_u8) {
             const int urc = lrc_unpack_u8_cf32(c->ctx, c->d_ring_u8[b], ns * 2, c->d_ring[b], ks);
             if (urc) return urc;
         }
+        const void *seg_in = direct_u8 ? (const void *)c->d_ring_u8[b] : (const void *)c->d_ring[b];
         int rc;
         if (slice_rows) {
             const size_t row = f / k_avg;
-            rc = chain_launch(c, c->d_ring[b], 1, nfr, c->d_rows + row * c->nfft, scale, (f % k_avg) != 0, ks);
+            rc = chain_launch(c, seg_in, direct_u8, 1, nfr, c->d_rows + row * c->nfft, scale, (f % k_avg) != 0, ks);
         } else {
-            rc = chain_launch(c, c->d_ring[b], nfr / k_avg, k_avg, c->d_rows + (f / k_avg) * c->nfft, scale, 0, ks);
+            rc = chain_launch(c, seg_in, direct_u8, nfr / k_avg, k_avg, c->d_rows + (f / k_avg) * c->nfft, scale, 0, ks);
         }
         if (rc) return rc;
         LRC_CUDA(cudaEventRecord(c->ev_free[b], ks));

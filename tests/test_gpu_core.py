@@ -517,3 +517,35 @@ def test_chain_host_ring_never_reads_past_the_callers_buffer(ntaps, decim, nfft,
     code = _TIGHT_HOST.format(root=root, ntaps=ntaps, decim=decim, nfft=nfft, frames=frames, k=k)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "tight-host ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("frames,k", [(1, 1), (40, 8), (130, 64)])
+def test_chain_u8_instance_expands_the_tile_on_chip_bit_exact(ctx, frames, k):
+    """lrc_chain_run_u8: rtlsdr bytes on the DEVICE; the fused kernel's producers run i2f on the TMA-loaded raw tile in shared
+    memory (HBM carries 2 B per sample, no unpack launch) and then the same FIR code, so the rows equal the cf32 chain fed
+    with the bit-exact unpack of the same bytes, bit for bit -- and the oracle within 1e-4 x RMS."""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    n = frames * 10240 + 54
+    iq = synth.iq_tone_noise_u8(n, seed=100 + frames)
+    ch = blocks.Chain(ctx, taps, 10, 1024, capi.WINDOW_HANN)
+    got = ch.run_u8(dev(iq, ctx), k).cpu().numpy()
+    x = oracle.data_to_samples(iq)
+    ref = ch.run(dev(x, ctx), k).cpu().numpy()
+    assert got.shape == ref.shape == (frames // k, 1024)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert_close_rms(got, chain_ref(x, taps, 10, 1024, k))
+    ch.close()
+
+
+def test_chain_u8_generic_shape_unpacks_then_runs_the_cf32_path(ctx):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(2)
+    taps = (rng.standard_normal(33) / 6).astype(np.float32)
+    frames, k, nfft, decim = 24, 4, 256, 4
+    n = frames * nfft * decim + 33 - decim
+    iq = synth.iq_tone_noise_u8(n, seed=8)
+    ch = blocks.Chain(ctx, taps, decim, nfft)
+    got = ch.run_u8(dev(iq, ctx), k).cpu().numpy()
+    assert_close_rms(got, chain_ref(oracle.data_to_samples(iq), taps, decim, nfft, k))
+    ch.close()
