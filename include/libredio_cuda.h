@@ -61,6 +61,23 @@ int lrc_ctx_bind_thread(lrc_ctx *ctx, int *n_cpus);
  * state: use it from ONE thread / stream at a time.  Different plans of one context are independent. */
 int lrc_host_alloc(lrc_ctx *ctx, size_t bytes, void **h_ptr);
 int lrc_host_free(lrc_ctx *ctx, void *h_ptr);
+/* device memory, streams and asynchronous copies for FFI hosts that carry no CUDA bindings of their own (rust/kpn-gpu):
+ * together with lrc_host_alloc they are what a KPN block needs to run a pinned, double-buffered ring around the plan entry
+ * points (copy in, launch, copy out on the block's stream, an event per ring slot to know when its batch is out).
+ * `stream` NULL = the context's own stream. */
+int lrc_dev_alloc(lrc_ctx *ctx, size_t bytes, void **d_ptr);
+int lrc_dev_free(lrc_ctx *ctx, void *d_ptr);
+int lrc_dev_memset(lrc_ctx *ctx, void *d_ptr, int value, size_t bytes, void *stream);
+int lrc_stream_create(lrc_ctx *ctx, void **stream);
+int lrc_stream_destroy(lrc_ctx *ctx, void *stream);
+int lrc_stream_sync(lrc_ctx *ctx, void *stream);
+/* completion of one ring slot's batch when several slots share a stream */
+int lrc_event_create(lrc_ctx *ctx, void **event);
+int lrc_event_destroy(lrc_ctx *ctx, void *event);
+int lrc_event_record(lrc_ctx *ctx, void *event, void *stream);
+int lrc_event_sync(lrc_ctx *ctx, void *event);
+int lrc_copy_h2d_async(lrc_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int lrc_copy_d2h_async(lrc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
 /* synchronous device -> host copy (for the debug views below and bindings without a CUDA runtime) */
 int lrc_copy_to_host(lrc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 

@@ -362,7 +362,7 @@ struct OokPacket { uint32_t stream, proto; std::vector<size_t> bits; };
 // rtl_source_cmplx would have delivered 1024 at a time, bitfount.rs:16-34).  Packets come out ordered by
 // (stream, proto, sequence) -- per stream exactly what shaper_optional(36) / shaper_optional(24) send.
 inline void ook_decode(Gpu &g, Receiver<std::vector<uint8_t>> u, Sender<OokPacket> v, size_t n_streams, size_t n_blocks,
-                       unsigned s_rate = 256000, size_t max_runs = 1 << 16, size_t max_packets = 256)
+                       unsigned s_rate, size_t max_runs = 1 << 16, size_t max_packets = 256)
 {
     g.bind();
     lrc_ook *ook = nullptr;
@@ -387,6 +387,16 @@ inline void ook_decode(Gpu &g, Receiver<std::vector<uint8_t>> u, Sender<OokPacke
             }
         }
     } catch (...) { lrc_ook_destroy(ook); in.release(g); throw; }
+}
+
+// the packets of ook_decode back onto the reference's two ports: what shaper_optional(36) and shaper_optional(24) send
+// towards binconv (ratpak.rs:105-119) -- the bit vector of every protocol-A packet on `a`, of every protocol-B packet on `b`
+inline void split_protocols(Receiver<OokPacket> u, Sender<std::vector<size_t>> a, Sender<std::vector<size_t>> b)
+{
+    for (;;) {
+        OokPacket p = u.recv();
+        (p.proto == 0 ? a : b).send(std::move(p.bits));
+    }
 }
 
 }  // namespace kpn_gpu

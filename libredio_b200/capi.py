@@ -43,6 +43,18 @@ SIGNATURES = {
     "lrc_ctx_bind_thread": (_i, [_vp, C.POINTER(_i)]),
     "lrc_host_alloc": (_i, [_vp, _sz, _pp]),
     "lrc_host_free": (_i, [_vp, _vp]),
+    "lrc_dev_alloc": (_i, [_vp, _sz, _pp]),
+    "lrc_dev_free": (_i, [_vp, _vp]),
+    "lrc_dev_memset": (_i, [_vp, _vp, _i, _sz, _vp]),
+    "lrc_stream_create": (_i, [_vp, _pp]),
+    "lrc_stream_destroy": (_i, [_vp, _vp]),
+    "lrc_stream_sync": (_i, [_vp, _vp]),
+    "lrc_event_create": (_i, [_vp, _pp]),
+    "lrc_event_destroy": (_i, [_vp, _vp]),
+    "lrc_event_record": (_i, [_vp, _vp, _vp]),
+    "lrc_event_sync": (_i, [_vp, _vp]),
+    "lrc_copy_h2d_async": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "lrc_copy_d2h_async": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "lrc_copy_to_host": (_i, [_vp, _vp, _vp, _sz]),
     "lrc_unpack_u8_cf32": (_i, [_vp, _u8p, _sz, _fp, _vp]),
     "lrc_fir_create": (_i, [_vp, _fp, _i, _i, _pp]),

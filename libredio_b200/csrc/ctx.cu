@@ -193,6 +193,105 @@ extern "C" int lrc_host_free(lrc_ctx *c, void *h_ptr)
     return LRC_OK;
 }
 
+// ---- device memory, streams and asynchronous copies for FFI hosts without CUDA bindings of their own (rust/kpn-gpu): with
+// lrc_host_alloc these are what a KPN block needs to run a pinned, double-buffered ring around the plan entry points --------
+extern "C" int lrc_dev_alloc(lrc_ctx *c, size_t bytes, void **d_ptr)
+{
+    LRC_BIND(c);
+    LRC_REQUIRE(d_ptr != nullptr, LRC_ERR_INVALID, "null out pointer");
+    LRC_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return LRC_OK;
+}
+
+extern "C" int lrc_dev_free(lrc_ctx *c, void *d_ptr)
+{
+    LRC_BIND(c);
+    if (d_ptr) LRC_CUDA(cudaFree(d_ptr));
+    return LRC_OK;
+}
+
+extern "C" int lrc_dev_memset(lrc_ctx *c, void *d_ptr, int value, size_t bytes, void *stream)
+{
+    LRC_BIND(c);
+    if (bytes) LRC_CUDA(cudaMemsetAsync(d_ptr, value, bytes, lrc_stream(c, stream)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_stream_create(lrc_ctx *c, void **stream)
+{
+    LRC_BIND(c);
+    LRC_REQUIRE(stream != nullptr, LRC_ERR_INVALID, "null out pointer");
+    cudaStream_t s = nullptr;
+    LRC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return LRC_OK;
+}
+
+extern "C" int lrc_stream_destroy(lrc_ctx *c, void *stream)
+{
+    LRC_BIND(c);
+    if (stream) LRC_CUDA(cudaStreamDestroy(reinterpret_cast<cudaStream_t>(stream)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_stream_sync(lrc_ctx *c, void *stream)
+{
+    LRC_BIND(c);
+    LRC_CUDA(cudaStreamSynchronize(lrc_stream(c, stream)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_event_create(lrc_ctx *c, void **event)
+{
+    LRC_BIND(c);
+    LRC_REQUIRE(event != nullptr, LRC_ERR_INVALID, "null out pointer");
+    cudaEvent_t e = nullptr;
+    LRC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *event = e;
+    return LRC_OK;
+}
+
+extern "C" int lrc_event_destroy(lrc_ctx *c, void *event)
+{
+    LRC_BIND(c);
+    if (event) LRC_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_event_record(lrc_ctx *c, void *event, void *stream)
+{
+    LRC_BIND(c);
+    LRC_REQUIRE(event != nullptr, LRC_ERR_INVALID, "null event");
+    LRC_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), lrc_stream(c, stream)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_event_sync(lrc_ctx *c, void *event)
+{
+    LRC_BIND(c);
+    LRC_REQUIRE(event != nullptr, LRC_ERR_INVALID, "null event");
+    LRC_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_copy_h2d_async(lrc_ctx *c, void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    LRC_BIND(c);
+    if (bytes == 0) return LRC_OK;
+    LRC_REQUIRE(d_dst && h_src, LRC_ERR_INVALID, "lrc_copy_h2d_async: null pointer");
+    LRC_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, lrc_stream(c, stream)));
+    return LRC_OK;
+}
+
+extern "C" int lrc_copy_d2h_async(lrc_ctx *c, void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+    LRC_BIND(c);
+    if (bytes == 0) return LRC_OK;
+    LRC_REQUIRE(h_dst && d_src, LRC_ERR_INVALID, "lrc_copy_d2h_async: null pointer");
+    LRC_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, lrc_stream(c, stream)));
+    return LRC_OK;
+}
+
 extern "C" int lrc_copy_to_host(lrc_ctx *c, void *h_dst, const void *d_src, size_t bytes)
 {
     LRC_BIND(c);

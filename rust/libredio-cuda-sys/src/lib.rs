@@ -39,6 +39,19 @@ extern "C" {
     pub fn lrc_ctx_bind_thread(ctx: *mut lrc_ctx, n_cpus: *mut c_int) -> c_int;
     pub fn lrc_host_alloc(ctx: *mut lrc_ctx, bytes: size_t, h_ptr: *mut *mut c_void) -> c_int;
     pub fn lrc_host_free(ctx: *mut lrc_ctx, h_ptr: *mut c_void) -> c_int;
+    // device memory, streams and asynchronous copies: what kpn-gpu builds its pinned double-buffered rings from
+    pub fn lrc_dev_alloc(ctx: *mut lrc_ctx, bytes: size_t, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn lrc_dev_free(ctx: *mut lrc_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn lrc_dev_memset(ctx: *mut lrc_ctx, d_ptr: *mut c_void, value: c_int, bytes: size_t, stream: *mut c_void) -> c_int;
+    pub fn lrc_stream_create(ctx: *mut lrc_ctx, stream: *mut *mut c_void) -> c_int;
+    pub fn lrc_stream_destroy(ctx: *mut lrc_ctx, stream: *mut c_void) -> c_int;
+    pub fn lrc_stream_sync(ctx: *mut lrc_ctx, stream: *mut c_void) -> c_int;
+    pub fn lrc_event_create(ctx: *mut lrc_ctx, event: *mut *mut c_void) -> c_int;
+    pub fn lrc_event_destroy(ctx: *mut lrc_ctx, event: *mut c_void) -> c_int;
+    pub fn lrc_event_record(ctx: *mut lrc_ctx, event: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn lrc_event_sync(ctx: *mut lrc_ctx, event: *mut c_void) -> c_int;
+    pub fn lrc_copy_h2d_async(ctx: *mut lrc_ctx, d_dst: *mut c_void, h_src: *const c_void, bytes: size_t, stream: *mut c_void) -> c_int;
+    pub fn lrc_copy_d2h_async(ctx: *mut lrc_ctx, h_dst: *mut c_void, d_src: *const c_void, bytes: size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_copy_to_host(ctx: *mut lrc_ctx, h_dst: *mut c_void, d_src: *const c_void, bytes: size_t) -> c_int;
 
     pub fn lrc_unpack_u8_cf32(ctx: *mut lrc_ctx, d_iq: *const u8, n_bytes: size_t, d_out: *mut c_float, stream: *mut c_void) -> c_int;

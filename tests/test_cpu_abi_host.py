@@ -160,3 +160,46 @@ def test_world_size_2_gloo_sharded_chain_and_gather(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_rust_kpn_gpu_mirrors_every_cpp_gpu_block_name_and_argument_order():
+    """north_star: 'Host code stays in Rust'.  rust/kpn-gpu cannot be compiled here (no rustc), so it is kept in step with
+    the compiled and GPU-tested C++ mirror kpn/gpu_blocks.hpp by text: every block of namespace kpn_gpu has a `pub fn` of the
+    same name whose parameters are the same, in the same order (ports first, then parameters: kpn.rs:127-131); C++ parameters
+    that have a default value are tuning knobs the Rust side fixes."""
+    hpp = open(os.path.join(ROOT, "kpn", "gpu_blocks.hpp")).read()
+    rs = open(os.path.join(ROOT, "rust", "kpn-gpu", "src", "lib.rs")).read()
+    hpp = re.sub(r"//[^\n]*", "", hpp)
+    cpp = {}
+    for m in re.finditer(r"inline\s+void\s+(\w+)\s*\(([^)]*)\)", hpp):
+        name, params = m.group(1), m.group(2)
+        names = []
+        depth, cur = 0, ""
+        for ch in params + ",":                                  # split on top-level commas (templates contain commas)
+            if ch in "<(":
+                depth += 1
+            elif ch in ">)":
+                depth -= 1
+            if ch == "," and depth == 0:
+                if cur.strip():
+                    names.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        keep = [re.sub(r"\s*=.*", "", p).split()[-1].lstrip("&*") for p in names if "=" not in p]
+        cpp[name] = keep
+    blocks = {k: v for k, v in cpp.items() if k not in ("check", "cuda_check")}
+    assert {"data_to_samples", "fft", "fir_decimate", "fir_decimate_multi", "fm_demod", "resample", "fm_receiver_multi",
+            "chain_psd", "ook_decode", "split_protocols"} <= set(blocks)
+    rust = {m.group(1): [p.split(":")[0].strip() for p in m.group(2).split(",") if p.strip()]
+            for m in re.finditer(r"pub fn (\w+)\s*\(([^)]*)\)", rs)}
+    alias = {"g": "gpu"}
+    for name, params in blocks.items():
+        assert name in rust, f"kpn_gpu::{name} has no Rust counterpart in rust/kpn-gpu/src/lib.rs"
+        want = [alias.get(p, p) for p in params]
+        assert rust[name] == want, f"{name}: Rust parameters {rust[name]} != C++ {want}"
+    # and it binds only symbols the -sys crate declares
+    sys_txt = open(os.path.join(ROOT, "rust", "libredio-cuda-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\bpub fn (lrc_[a-z0-9_]+)\s*\(", sys_txt))
+    used = set(re.findall(r"sys::(lrc_[a-z0-9_]+)\s*\(", rs)) | set(re.findall(r", sys::(lrc_[a-z0-9_]+_destroy)\)", rs))
+    assert used and used <= declared, sorted(used - declared)

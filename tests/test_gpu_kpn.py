@@ -14,3 +14,75 @@ def test_cpp_programs(exe, ok):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kpn"), exe])
     out = subprocess.run([os.path.join(ROOT, "kpn", exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and ok in out.stdout, out.stdout + out.stderr
+
+
+def _apps_exe():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kpn"), "test_gpu_apps"])
+    return os.path.join(ROOT, "kpn", "test_gpu_apps")
+
+
+def test_ook_application_graph_from_an_iq_capture_file(tmp_path):
+    """the reference's one complete application (ratpak.rs:60-119) as a KPN graph on the GPU block, fed from the raw
+    rtl_sdr capture format: iq_file_source_u8 -> batch -> kpn_gpu::ook_decode -> split_protocols -> binconv x 2.  The field
+    tuples must equal kpn::eat over (a) the bits the capture was built to carry and (b) the CPU oracle's packets."""
+    import numpy as np
+    import oracle
+    from libredio_b200 import synth
+    n_blocks = 600
+    iq, sent = synth.ook_capture_u8(n_blocks, seed=77, n_packets=3)          # protocols B, B, A
+    ref = oracle.ook_decode(iq)
+    fields = {0: (4, 8, 4, 12, 8), 1: (4, 8, 2, 10, 12)}          # ratpak.rs:115,119
+
+    def eat(bits, widths):
+        out, i = [], 0
+        for w in widths:
+            out.append(int("".join(str(int(b)) for b in bits[i:i + w]), 2))
+            i += w
+        return out
+    lines = []
+    for proto, key in ((0, "a_packets"), (1, "b_packets")):
+        from_oracle = [eat(list(p), fields[proto]) for p in ref[key]]
+        by_construction = [eat(list(b), fields[proto]) for pr, b in sent if pr == proto]
+        assert from_oracle == by_construction and len(from_oracle) == sum(1 for pr, _ in sent if pr == proto)
+        lines += ["AB"[proto] + " " + " ".join(str(v) for v in f) for f in from_oracle]
+    assert lines
+    cap = tmp_path / "capture.iq"
+    iq.tofile(cap)
+    exp = tmp_path / "expected.txt"
+    exp.write_text("\n".join(lines) + "\n")
+    out = subprocess.run([_apps_exe(), "ook", str(cap), str(n_blocks), str(exp)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "kpn app ook OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_psd_application_graph_from_a_wav_file(tmp_path):
+    """wavio's complex source (2-channel WAV, wavio.rs:30-46, as Vec chunks) -> kpn_gpu::chain_psd: every chunk's rows against
+    the oracle FIR + f64 Hann PSD of the same chunk."""
+    import struct
+    import numpy as np
+    import oracle
+    from oracle import defined_f64 as D
+    from libredio_b200 import synth
+    rate, k, rows_per_chunk = 2_400_000, 4, 3
+    chunk = rows_per_chunk * k * 10240 + 54
+    n = 2 * chunk + chunk // 2                                   # two full chunks and a short one (1 row)
+    x = (synth.cf32_noise_tones(n, seed=12) * 0.1).astype(np.complex64)
+    wav = tmp_path / "capture.wav"
+    data = x.view(np.float32).tobytes()
+    with open(wav, "wb") as f:                                   # IEEE-float stereo WAV: I = left, Q = right
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, 3, 2, rate, rate * 8, 8, 32))
+        f.write(b"data" + struct.pack("<I", len(data)) + data)
+    taps = synth.lpf_taps(64, 0.04)
+    rows = []
+    for lo in range(0, n, chunk):
+        seg = x[lo: lo + chunk]
+        z = oracle.fir_decimate(seg, taps, 10)
+        r = D.psd_rows(z, 1024, k, D.hann_periodic(1024))
+        if r.size:
+            rows.append(r.astype(np.float32))
+    exp = tmp_path / "expected.f32"
+    np.concatenate(rows).astype(np.float32).tofile(exp)
+    taps.astype(np.float32).tofile(str(exp) + ".taps")
+    out = subprocess.run([_apps_exe(), "psd", str(wav), str(rate), str(chunk), str(k), str(exp)], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "kpn app psd OK" in out.stdout, out.stdout + out.stderr
