@@ -3,7 +3,8 @@
 //   ook   <capture.iq> <n_blocks> <expected.txt>
 //         iq_file_source_u8 (raw rtl_sdr capture, 512-sample blocks as read_async delivers them, bitfount.rs:16-34)
 //           -> batch (n_blocks messages -> one capture) -> kpn_gpu::ook_decode
-//           -> split_protocols -> binconv([4,8,4,12,8]) / binconv([4,8,2,10,12])          (ratpak.rs:60-119)
+//           -> split_protocols -> protocol A (36 bits): fork -> binconv([4,8,4,12,8]) and binconv([4,8,2,10,12])
+//                                 protocol B (24 bits): applicator(|x| {x.push(0); x})          (ratpak.rs:60-123)
 //         every field tuple must equal the expected file's (written by tests/test_gpu_kpn.py from the bits the synthetic
 //         capture was built to carry AND from the CPU oracle's decode of the same capture).
 //   psd   <file.wav> <rate> <chunk> <k_avg> <expected.f32>
@@ -46,7 +47,10 @@ static int app_ook(int argc, char **argv)
     auto [s2, r2] = channel<kpn_gpu::OokPacket>();
     auto [sa, ra] = channel<std::vector<size_t>>();
     auto [sb, rb] = channel<std::vector<size_t>>();
-    auto [sfa, rfa] = channel<std::vector<size_t>>();
+    auto [sa1, ra1] = channel<std::vector<size_t>>();
+    auto [sa2, ra2] = channel<std::vector<size_t>>();
+    auto [sf1, rf1] = channel<std::vector<size_t>>();
+    auto [sf2, rf2] = channel<std::vector<size_t>>();
     auto [sfb, rfb] = channel<std::vector<size_t>>();
     std::thread t0 = spawn([s = std::move(s0), cap]() mutable { iq_file_source_u8(std::move(s), cap, 512); });
     std::thread t1 = spawn([r = std::move(r0), s = std::move(s1), n_blocks]() mutable { batch(std::move(r), std::move(s), n_blocks); });
@@ -54,11 +58,19 @@ static int app_ook(int argc, char **argv)
         kpn_gpu::ook_decode(gpu, std::move(r), std::move(s), 1, n_blocks, 256000); });
     std::thread t3 = spawn([r = std::move(r2), a = std::move(sa), b = std::move(sb)]() mutable {
         kpn_gpu::split_protocols(std::move(r), std::move(a), std::move(b)); });
-    std::thread t4 = spawn([r = std::move(ra), s = std::move(sfa)]() mutable { binconv(std::move(r), std::move(s), {4, 8, 4, 12, 8}); });     // ratpak.rs:115
-    std::thread t5 = spawn([r = std::move(rb), s = std::move(sfb)]() mutable { binconv(std::move(r), std::move(s), {4, 8, 2, 10, 12}); });    // ratpak.rs:119
-    for (std::thread *t : {&t0, &t1, &t2, &t3, &t4, &t5}) t->join();
-    // expected: lines "A f0 f1 f2 f3 f4" / "B ..." in emission order per protocol
-    std::vector<std::vector<size_t>> want[2];
+    // ratpak.rs:98-101: the 36-bit packets fork to BOTH field layouts; :112-119
+    std::thread t4 = spawn([r = std::move(ra), a = std::move(sa1), b = std::move(sa2)]() mutable {
+        std::vector<Sender<std::vector<size_t>>> outs; outs.push_back(std::move(a)); outs.push_back(std::move(b));
+        fork(std::move(r), std::move(outs)); });
+    std::thread t5 = spawn([r = std::move(ra1), s = std::move(sf1)]() mutable { binconv(std::move(r), std::move(s), {4, 8, 4, 12, 8}); });
+    std::thread t6 = spawn([r = std::move(ra2), s = std::move(sf2)]() mutable { binconv(std::move(r), std::move(s), {4, 8, 2, 10, 12}); });
+    // ratpak.rs:120-123: the 24-bit packets get a trailing 0
+    std::thread t7 = spawn([r = std::move(rb), s = std::move(sfb)]() mutable {
+        applicator(std::move(r), std::move(s), [](std::vector<size_t> x) { x.push_back(0); return x; }); });
+    for (std::thread *t : {&t0, &t1, &t2, &t3, &t4, &t5, &t6, &t7}) t->join();
+    // expected: lines "A f0 .. f4" (36-bit packets, first layout), "C f0 .. f4" (same packets, second layout),
+    // "B b0 .. b23 0" (24-bit packets with the appended 0), each kind in emission order
+    std::vector<std::vector<size_t>> want[3];
     std::ifstream in(expf);
     std::string line;
     while (std::getline(in, line)) {
@@ -66,18 +78,18 @@ static int app_ook(int argc, char **argv)
         char p; ls >> p;
         std::vector<size_t> f; size_t v;
         while (ls >> v) f.push_back(v);
-        want[p == 'B'].push_back(f);
+        want[p == 'A' ? 0 : (p == 'C' ? 1 : 2)].push_back(f);
     }
     size_t n_got = 0;
-    for (int p = 0; p < 2; ++p) {
-        auto &rx = p ? rfb : rfa;
+    Receiver<std::vector<size_t>> *rxs[3] = {&rf1, &rf2, &rfb};
+    for (int p = 0; p < 3; ++p) {
         for (const auto &w : want[p]) {
-            auto got = rx.try_recv();
+            auto got = rxs[p]->try_recv();
             CHECK(got.has_value());
             CHECK(*got == w);
             ++n_got;
         }
-        CHECK(!rx.try_recv().has_value());
+        CHECK(!rxs[p]->try_recv().has_value());
     }
     CHECK(n_got >= 1);
     std::printf("kpn app ook OK (%zu packets)\n", n_got);

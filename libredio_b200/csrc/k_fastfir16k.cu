@@ -96,6 +96,14 @@ __device__ __forceinline__ void warp_fft1024(float2 *v, float2 *row, const float
 }
 }  // namespace ff16k
 
+// Measured and rejected for the P1 phase (whose global loads cannot be held in registers across P2 at 128 registers/thread):
+//   - staging the next block's first column in shared memory with cp.async during P2 (P1 twiddles factorised into two
+//     small tables to make room): 121 Gsamples/s against 140 -- 8192 LDGSTS per CTA sit in the LSU queue in front of the
+//     barrier (lg_throttle 0.12 -> 0.79, barrier 0.63 -> 1.07 per issue), profiles/r2_ff16k_staged_ncu_phases.txt;
+//   - a CTA-uniform fast path with unpredicated loads: 133 against 140.
+// A TMA tensor copy would take the loads off the LSU, but block starts (multiples of ngood = 12289 samples) are only
+// 8-byte aligned every other block.
+//
 // NT = 512: one column pair and one row per thread / warp, 128 registers.  NT = 256: two pairs and two rows, 255 registers --
 // room to request a whole pair of the next block BEFORE P2 and the other pair at the head of the P1 phase, so no load is
 // ever waited for; half the warps to hide everything else.  Chosen by measurement (lrc_fastfir16k_launch).

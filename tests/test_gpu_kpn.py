@@ -23,28 +23,31 @@ def _apps_exe():
 
 def test_ook_application_graph_from_an_iq_capture_file(tmp_path):
     """the reference's one complete application (ratpak.rs:60-119) as a KPN graph on the GPU block, fed from the raw
-    rtl_sdr capture format: iq_file_source_u8 -> batch -> kpn_gpu::ook_decode -> split_protocols -> binconv x 2.  The field
-    tuples must equal kpn::eat over (a) the bits the capture was built to carry and (b) the CPU oracle's packets."""
+    rtl_sdr capture format: iq_file_source_u8 -> batch -> kpn_gpu::ook_decode -> split_protocols -> fork -> binconv x 2 (36-bit
+    packets) / applicator (24-bit packets).  What the sinks receive must equal kpn::eat over (a) the bits the capture was built
+    to carry and (b) the CPU oracle's packets."""
     import numpy as np
     import oracle
     from libredio_b200 import synth
     n_blocks = 600
     iq, sent = synth.ook_capture_u8(n_blocks, seed=77, n_packets=3)          # protocols B, B, A
     ref = oracle.ook_decode(iq)
-    fields = {0: (4, 8, 4, 12, 8), 1: (4, 8, 2, 10, 12)}          # ratpak.rs:115,119
+    layouts = {"A": (4, 8, 4, 12, 8), "C": (4, 8, 2, 10, 12)}     # ratpak.rs:115,119: BOTH applied to the 36-bit packets (fork :98)
 
-    def eat(bits, widths):
+    def eat(bits, widths):                                        # kpn.rs:111-124
         out, i = [], 0
         for w in widths:
             out.append(int("".join(str(int(b)) for b in bits[i:i + w]), 2))
             i += w
         return out
+    a_ref, b_ref = [list(p) for p in ref["a_packets"]], [list(p) for p in ref["b_packets"]]
+    a_sent, b_sent = [list(b) for pr, b in sent if pr == 0], [list(b) for pr, b in sent if pr == 1]
+    assert [[int(v) for v in p] for p in a_ref] == [[int(v) for v in p] for p in a_sent] and len(a_ref) >= 1
+    assert [[int(v) for v in p] for p in b_ref] == [[int(v) for v in p] for p in b_sent] and len(b_ref) >= 1
     lines = []
-    for proto, key in ((0, "a_packets"), (1, "b_packets")):
-        from_oracle = [eat(list(p), fields[proto]) for p in ref[key]]
-        by_construction = [eat(list(b), fields[proto]) for pr, b in sent if pr == proto]
-        assert from_oracle == by_construction and len(from_oracle) == sum(1 for pr, _ in sent if pr == proto)
-        lines += ["AB"[proto] + " " + " ".join(str(v) for v in f) for f in from_oracle]
+    for tag, widths in layouts.items():
+        lines += [tag + " " + " ".join(str(v) for v in eat(p, widths)) for p in a_ref]
+    lines += ["B " + " ".join(str(int(v)) for v in p) + " 0" for p in b_ref]      # applicator(|x| {x.push(0); x}) ratpak.rs:120-123
     assert lines
     cap = tmp_path / "capture.iq"
     iq.tofile(cap)
