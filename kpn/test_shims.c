@@ -4,6 +4,7 @@
  * the drop-in seams, exercised exactly as the unmodified reference would. */
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 typedef struct { float r, i; } kiss_fft_cpx;
@@ -92,6 +93,44 @@ int main(void)
     /* a too-small output buffer consumes less input instead of overflowing */
     d.input_frames = 100; d.output_frames = 50;
     CHECK(src_process(st, &d) == 0 && d.output_frames_gen <= 50 && d.input_frames_used == 25);
+    /* what samplerate.rs:64-84 meets when the library takes less than it was given: input_frames_used < input_frames; a
+     * caller that re-submits the remainder gets the same stream as one call with enough room */
+    {
+        SRC_STATE *a = src_new(1, 1, &err), *b = src_new(1, 1, &err);
+        CHECK(a && b);
+        static float x[6000], ya[3100], yb[3100];
+        for (int k = 0; k < 6000; ++k) x[k] = sinf(0.01f * (float)k) + 0.25f * sinf(0.37f * (float)k);
+        SRC_DATA da = { x, ya, 6000, 3100, 0, 0, 0, 0.5 };
+        CHECK(src_process(a, &da) == 0 && da.input_frames_used == 6000 && da.output_frames_gen == 3000);
+        long used = 0, made = 0;
+        int calls = 0;
+        while (used < 6000 && calls < 100) {
+            SRC_DATA db = { x + used, yb + made, 6000 - used, 700, 0, 0, 0, 0.5 };       /* room for 700 frames per call */
+            CHECK(src_process(b, &db) == 0);
+            CHECK(db.input_frames_used > 0 && db.output_frames_gen <= 700);
+            used += db.input_frames_used; made += db.output_frames_gen; ++calls;
+        }
+        CHECK(used == 6000 && made == 3000 && calls >= 5);
+        CHECK(memcmp(ya, yb, 3000 * sizeof(float)) == 0);
+        src_delete(a); src_delete(b);
+    }
+    /* chunks may grow: libsamplerate puts no bound on input_frames (a first chunk of 10, then 100 000) */
+    {
+        SRC_STATE *g = src_new(1, 1, &err);
+        static float big[100000], bo[50002];
+        for (int k = 0; k < 100000; ++k) big[k] = sinf(0.001f * (float)k);
+        SRC_DATA dg = { big, bo, 10, 50002, 0, 0, 0, 0.5 };
+        CHECK(src_process(g, &dg) == 0 && dg.input_frames_used == 10);
+        dg.data_in = big + 10; dg.input_frames = 99990;
+        CHECK(src_process(g, &dg) == 0 && dg.input_frames_used == 99990 && dg.output_frames_gen == 49995);
+        src_delete(g);
+    }
+    /* kiss_fft_alloc / free cycles: the cfg block is the caller's, the device plan is the shim's (no growth per cycle) */
+    for (int k = 0; k < 200; ++k) {
+        kiss_fft_cfg c3 = kiss_fft_alloc(256, k & 1, NULL, NULL);
+        CHECK(c3 != NULL);
+        free(c3);
+    }
     d.src_ratio = 1e-9;
     int rc = src_process(st, &d);
     CHECK(rc != 0 && src_strerror(rc) != NULL);                          /* samplerate.rs:77-83 would panic with this text */

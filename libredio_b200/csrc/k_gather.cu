@@ -84,12 +84,19 @@ extern "C" int lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes
         lrc_set_error("lrc_gather_create: cudaMalloc(%zu) -> %s", g->total_bytes, cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? LRC_ERR_NOMEM : LRC_ERR_CUDA;
     }
-    LRC_CUDA(cudaMemset(g->base, 0, g->total_bytes));
-    LRC_CUDA(cudaStreamCreateWithFlags(&g->push_stream, cudaStreamNonBlocking));
-    LRC_CUDA(cudaEventCreateWithFlags(&g->ev_src, cudaEventDisableTiming));
-    g->ev_sent = new cudaEvent_t[slots];
+    // from here on a failure releases what exists: every member lrc_gather_destroy touches is initialised first
+    g->push_stream = nullptr; g->ev_src = nullptr;
+    g->ev_sent = new cudaEvent_t[slots]();
     g->seq = new uint32_t[slots]();
-    for (int s = 0; s < slots; ++s) LRC_CUDA(cudaEventCreateWithFlags(&g->ev_sent[s], cudaEventDisableTiming));
+    e = cudaMemset(g->base, 0, g->total_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->push_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_src, cudaEventDisableTiming);
+    for (int s = 0; s < slots && e == cudaSuccess; ++s) e = cudaEventCreateWithFlags(&g->ev_sent[s], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        lrc_set_error("lrc_gather_create: %s", cudaGetErrorString(e));
+        lrc_gather_destroy(g);
+        return LRC_ERR_CUDA;
+    }
     g->peer[rank] = g->base;
     if (world == 1) g->connected = true;
     *out = g;
@@ -100,12 +107,12 @@ extern "C" int lrc_gather_destroy(lrc_gather *g)
 {
     if (!g) return LRC_OK;
     cudaSetDevice(g->ctx->device);
-    cudaStreamSynchronize(g->push_stream);
+    if (g->push_stream) cudaStreamSynchronize(g->push_stream);
     for (int p = 0; p < g->world; ++p)
         if (g->opened[p]) cudaIpcCloseMemHandle(g->peer[p]);
-    for (int s = 0; s < g->slots; ++s) cudaEventDestroy(g->ev_sent[s]);
-    cudaEventDestroy(g->ev_src);
-    cudaStreamDestroy(g->push_stream);
+    for (int s = 0; s < g->slots; ++s) if (g->ev_sent && g->ev_sent[s]) cudaEventDestroy(g->ev_sent[s]);
+    if (g->ev_src) cudaEventDestroy(g->ev_src);
+    if (g->push_stream) cudaStreamDestroy(g->push_stream);
     cudaFree(g->base);
     delete[] g->ev_sent;
     delete[] g->seq;

@@ -7,8 +7,21 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include "../../include/libredio_cuda.h"
+
+// Device plans are shared and cached per (nfft, direction, real?): a kiss_fft_cfg is ONE malloc block that callers release
+// with free() (kiss_fft.h:102; LibRedio's Rust never releases it at all, kissfft.rs:19), so the block itself may only
+// hold a pointer into this cache -- alloc/free cycles then cost no device memory, whatever the caller does with the cfg.
+// The cache is bounded by the number of distinct sizes a process asks for.  A plan owns scratch, so calls through one plan
+// are serialised by its mutex (kiss_fft is documented thread-safe, README:103; different sizes still run concurrently).
+namespace {
+struct CachedPlan { void *plan = nullptr; std::mutex mu; };
+std::mutex g_cache_mu;
+std::map<std::pair<int, int>, CachedPlan *> g_cache;      // key: (nfft, inverse | real << 1)
+}
 
 extern "C" {
 
@@ -17,7 +30,7 @@ typedef struct { float r, i; } kiss_fft_cpx;           // kiss_fft.h:51-54 with 
 struct kiss_fft_state {                                  // opaque to callers; one malloc block so free() works
     unsigned magic;
     int nfft, inverse;
-    lrc_fft *plan;                                       // device plan (leaks by design if the caller free()s the cfg)
+    CachedPlan *entry;                                   // shared device plan (shim-owned: free(cfg) leaks nothing)
 };
 typedef struct kiss_fft_state *kiss_fft_cfg;
 
@@ -38,6 +51,23 @@ static lrc_ctx *shim_ctx()
     return g_ctx;
 }
 
+static CachedPlan *cached_plan(int nfft, int inverse, int real)
+{
+    lrc_ctx *ctx = shim_ctx();
+    if (!ctx) return nullptr;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const std::pair<int, int> key(nfft, (inverse ? 1 : 0) | (real ? 2 : 0));
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) return it->second;
+    void *plan = nullptr;
+    const int rc = real ? lrc_rfft_create(ctx, nfft, inverse, (lrc_rfft **)&plan) : lrc_fft_create(ctx, nfft, inverse, (lrc_fft **)&plan);
+    if (rc != LRC_OK) return nullptr;
+    CachedPlan *e = new CachedPlan();
+    e->plan = plan;
+    g_cache[key] = e;
+    return e;
+}
+
 kiss_fft_cfg kiss_fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem)
 {
     const size_t memneeded = sizeof(struct kiss_fft_state);
@@ -49,21 +79,21 @@ kiss_fft_cfg kiss_fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem
         *lenmem = memneeded;
     }
     if (!st) return nullptr;
-    lrc_ctx *ctx = shim_ctx();
-    lrc_fft *plan = nullptr;
-    if (!ctx || lrc_fft_create(ctx, nfft, inverse_fft, &plan) != LRC_OK) {
+    CachedPlan *e = cached_plan(nfft, inverse_fft, 0);
+    if (!e) {
         fprintf(stderr, "libkissfft (libredio_b200 shim): kiss_fft_alloc(%d) failed: %s\n", nfft, lrc_last_error());
         if (lenmem == nullptr) free(st);
         return nullptr;
     }
-    st->magic = 0x4b495353u; st->nfft = nfft; st->inverse = inverse_fft; st->plan = plan;
+    st->magic = 0x4b495353u; st->nfft = nfft; st->inverse = inverse_fft; st->entry = e;
     return st;
 }
 
 void kiss_fft(kiss_fft_cfg cfg, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
 {
     if (!cfg || cfg->magic != 0x4b495353u) { fprintf(stderr, "kiss_fft: bad cfg\n"); abort(); }
-    int rc = lrc_fft_run_host(cfg->plan, (const float *)fin, (float *)fout, (size_t)cfg->nfft);   // fin == fout allowed
+    std::lock_guard<std::mutex> lk(cfg->entry->mu);
+    int rc = lrc_fft_run_host((lrc_fft *)cfg->entry->plan, (const float *)fin, (float *)fout, (size_t)cfg->nfft);   // fin == fout allowed
     if (rc != LRC_OK) { fprintf(stderr, "kiss_fft: %s [%s]\n", lrc_strerror(rc), lrc_last_error()); abort(); }
 }
 
@@ -96,7 +126,7 @@ int kiss_fft_next_fast_size(int n)
 struct kiss_fftr_state {
     unsigned magic;
     int nfft, inverse;
-    lrc_rfft *plan;
+    CachedPlan *entry;
 };
 typedef struct kiss_fftr_state *kiss_fftr_cfg;
 
@@ -115,14 +145,13 @@ kiss_fftr_cfg kiss_fftr_alloc(int nfft, int inverse_fft, void *mem, size_t *lenm
         *lenmem = memneeded;
     }
     if (!st) return nullptr;
-    lrc_ctx *ctx = shim_ctx();
-    lrc_rfft *plan = nullptr;
-    if (!ctx || lrc_rfft_create(ctx, nfft, inverse_fft, &plan) != LRC_OK) {
+    CachedPlan *e = cached_plan(nfft, inverse_fft, 1);
+    if (!e) {
         fprintf(stderr, "libkissfft (libredio_b200 shim): kiss_fftr_alloc(%d) failed: %s\n", nfft, lrc_last_error());
         if (lenmem == nullptr) free(st);
         return nullptr;
     }
-    st->magic = 0x4b465452u; st->nfft = nfft; st->inverse = inverse_fft; st->plan = plan;
+    st->magic = 0x4b465452u; st->nfft = nfft; st->inverse = inverse_fft; st->entry = e;
     return st;
 }
 
@@ -130,7 +159,8 @@ void kiss_fftr(kiss_fftr_cfg cfg, const float *timedata, kiss_fft_cpx *freqdata)
 {
     if (!cfg || cfg->magic != 0x4b465452u) { fprintf(stderr, "kiss_fftr: bad cfg\n"); abort(); }
     if (cfg->inverse) { fprintf(stderr, "kiss fft usage error: improper alloc\n"); exit(1); }   // kiss_fftr.c:73-76
-    int rc = lrc_rfft_run_host(cfg->plan, timedata, (float *)freqdata, 1);
+    std::lock_guard<std::mutex> lk(cfg->entry->mu);
+    int rc = lrc_rfft_run_host((lrc_rfft *)cfg->entry->plan, timedata, (float *)freqdata, 1);
     if (rc != LRC_OK) { fprintf(stderr, "kiss_fftr: %s [%s]\n", lrc_strerror(rc), lrc_last_error()); abort(); }
 }
 
@@ -138,7 +168,8 @@ void kiss_fftri(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, float *timedata
 {
     if (!cfg || cfg->magic != 0x4b465452u) { fprintf(stderr, "kiss_fftri: bad cfg\n"); abort(); }
     if (!cfg->inverse) { fprintf(stderr, "kiss fft usage error: improper alloc\n"); exit(1); }  // kiss_fftr.c:126-129
-    int rc = lrc_rfft_run_host(cfg->plan, (const float *)freqdata, timedata, 1);
+    std::lock_guard<std::mutex> lk(cfg->entry->mu);
+    int rc = lrc_rfft_run_host((lrc_rfft *)cfg->entry->plan, (const float *)freqdata, timedata, 1);
     if (rc != LRC_OK) { fprintf(stderr, "kiss_fftri: %s [%s]\n", lrc_strerror(rc), lrc_last_error()); abort(); }
 }
 

@@ -80,9 +80,10 @@ int src_process(SRC_STATE *st, SRC_DATA *data)
     data->input_frames_used = data->output_frames_gen = 0;
     const size_t n_in_all = (size_t)data->input_frames;
     if (st->rs && std::fabs(st->ratio - data->src_ratio) > 1e-12 * st->ratio) return st->last_error = SRC_ERR_RATIO_CHANGE;
-    if (!st->rs || st->max_chunk < n_in_all) {
-        if (st->rs) return st->last_error = SRC_ERR_BAD_DATA;     // chunks may not grow past the first one x16
-        st->max_chunk = n_in_all * 16 + 4096;
+    if (!st->rs) {
+        // libsamplerate puts no bound on input_frames and a caller may grow its chunks at will (samplerate.rs:64-84 passes
+        // whatever Vec arrives): lrc_resampler sizes nothing from max_chunk, it only guards against a wild length
+        st->max_chunk = (size_t)1 << 40;
         st->ratio = data->src_ratio;
         if (lrc_resampler_create(shim_ctx(), st->ratio, 1, st->max_chunk, &st->rs) != LRC_OK) {
             st->rs = nullptr;
