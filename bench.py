@@ -460,12 +460,15 @@ def run_ours(args):
     # the only exchange: every rank's output rows go to every peer.  Default: lrc_gather (copy engines over NVLink,
     # zero SMs, overlaps the next step's persistent kernel); fallback / --gather nccl: NCCL all-gather, whose kernel
     # cannot start while the chain kernel fills every SM and therefore serialises with it.
-    gather, gather_kind, gath = None, "none (1 GPU)", None
+    gather, gather_kind, gath, gather_all = None, "none (1 GPU)", None, None
     if world > 1:
         ok = torch.zeros(1, device=dev)
         if args.gather == "ce":
             try:
                 gather = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
+                if args.gather_to == "root":
+                    gather.set_root(0)
+                    gather_all = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()   # diagnostics only
                 ok += 1
             except Exception as e:                         # e.g. CUDA IPC not permitted in this container
                 print(f"bench.py rank {rank}: lrc_gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
@@ -474,7 +477,9 @@ def run_ours(args):
         if int(ok.item()) != world:
             if gather is not None:
                 gather.close()
-            gather = None
+            if gather_all is not None:
+                gather_all.close()
+            gather = gather_all = None
         # bounded-time probe before the timed loop depends on it (every rank created and connected its Gather): one push +
         # arrival wait per slot on a side stream, polled from the host.  A peer whose flag write never arrives would
         # otherwise hang the bench inside a device-side wait; the probing stream can never drain in that case, so the
@@ -501,7 +506,9 @@ def run_ours(args):
             gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
             gather_kind = "NCCL all_gather_into_tensor of output rows (async, 2 slots)"
         else:
-            gather_kind = "lrc_gather: copy-engine P2P push of output rows into every peer's slot (CUDA IPC, 2 slots)"
+            gather_kind = ("lrc_gather, root 0: copy-engine P2P push of every rank's output rows into rank 0's slot (CUDA IPC, 2 slots)"
+                           if args.gather_to == "root" else
+                           "lrc_gather, all ranks: copy-engine P2P push of output rows into every peer's slot (CUDA IPC, 2 slots)")
 
     def step(i):
         b = i & 1
@@ -539,8 +546,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     if sampler:
         sampler.start()
-    def timed_loop(with_gather: bool):
+    def timed_loop(with_gather: bool, gather=gather):
         """EXACTLY `steps` steps between two events (per-step kernel events inside); the last gathers are drained inside"""
+        def drain():
+            for b in range(2):
+                if gather is not None:
+                    gather.wait(b)                             # every peer's rows for this slot have ARRIVED here
+                elif pending[b] is not None:
+                    pending[b].wait()
+                    pending[b] = None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         ev0.record()
@@ -578,7 +592,7 @@ def run_ours(args):
             want = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(want, outs[b])
             got = gather.buffer(b).reshape(world * rows, NFFT)
-            if not torch.equal(got, want):
+            if (args.gather_to == "all" or rank == 0) and not torch.equal(got, want):
                 raise SystemExit(f"bench.py rank {rank}: lrc_gather slot {b} differs from the NCCL all-gather")
     # ---- where a multi-GPU step's time goes (0.93 at 8 GPUs unexplained): every rank's own kernel time, the
     # same timed loop again WITHOUT the gather (no pushes, no arrival waits; max over ranks), and rank 0 alone
@@ -592,6 +606,13 @@ def run_ours(args):
         ng_ms, ng_kern = timed_loop(False)
         tn = torch.tensor([ng_ms, ng_kern], device=dev, dtype=torch.float64)
         dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        ta = None
+        if gather_all is not None:                             # the same loop with the rows pushed to EVERY rank
+            dist.barrier()
+            torch.cuda.synchronize()
+            ag_ms, ag_kern = timed_loop(True, gather_all)
+            ta = torch.tensor([ag_ms, ag_kern], device=dev, dtype=torch.float64)
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
         # one rank alone (the others idle): is the kernel itself slower when its peers run (power, NVLink inbound writes)?
         solo = torch.zeros(2, device=dev, dtype=torch.float64)
         dist.barrier()
@@ -603,6 +624,8 @@ def run_ours(args):
         diag = {"kernel_ms_per_rank": [float(v) for v in kall.tolist()],
                 "ms_per_step_without_gather_max_over_ranks": float(tn[0].item()) / args.steps,
                 "kernel_ms_without_gather_max_over_ranks": float(tn[1].item()),
+                "ms_per_step_all_gather_max_over_ranks": (float(ta[0].item()) / args.steps) if ta is not None else None,
+                "kernel_ms_all_gather_max_over_ranks": float(ta[1].item()) if ta is not None else None,
                 "ms_per_step_rank0_alone_peers_idle": float(solo[0].item()),
                 "kernel_ms_rank0_alone_peers_idle": float(solo[1].item()),
                 "note": "ms_per_step - ms_per_step_without_gather = cost of the gather (pushes, arrival waits, final drain over "
@@ -760,6 +783,8 @@ def run_ours(args):
         dist.barrier()
     if gather is not None:
         gather.close()
+    if gather_all is not None:
+        gather_all.close()
     chain.close()
     ctx.close()
     if world > 1:
@@ -782,6 +807,8 @@ def main():
     ap.add_argument("--quick-extra", action="store_true", dest="quick_extra", help="extra block at 1/8 size (smoke runs)")
     ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
                     help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
+    ap.add_argument("--gather-to", default="root", choices=["root", "all"], dest="gather_to",
+                    help="N > 1: who receives the output rows: rank 0 only (a gather, default) or every rank (all-gather)")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
                     help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()

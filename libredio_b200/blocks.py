@@ -528,6 +528,11 @@ class Gather:
         self.h = C.c_void_p()
         check(ctx.lib.lrc_gather_create(ctx.h, rank, world, bytes_per_rank, slots, C.byref(self.h)), "lrc_gather_create")
 
+    def set_root(self, root: int):
+        """root >= 0: only that rank receives (a gather); -1: every rank receives everything (the default)"""
+        check(self.ctx.lib.lrc_gather_set_root(self.h, root), "lrc_gather_set_root")
+        return self
+
     def export(self) -> bytes:
         n = self.ctx.lib.lrc_gather_handle_bytes()
         buf = C.create_string_buffer(n)

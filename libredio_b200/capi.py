@@ -113,6 +113,7 @@ SIGNATURES = {
     "lrc_ook_envelope_table": (_i, [_vp, _fp, _vp]),
     "lrc_gather_create": (_i, [_vp, _i, _i, _sz, _i, _pp]),
     "lrc_gather_destroy": (_i, [_vp]),
+    "lrc_gather_set_root": (_i, [_vp, _i]),
     "lrc_gather_handle_bytes": (_sz, []),
     "lrc_gather_export": (_i, [_vp, _vp, _sz]),
     "lrc_gather_connect": (_i, [_vp, _vp]),

@@ -24,6 +24,7 @@ typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct lrc_gather {
     lrc_ctx     *ctx;
     int          rank, world, slots;
+    int          root;                          // -1: every rank receives every block (all-gather); r: only rank r receives
     size_t       bytes_per_rank, block_stride, slot_stride, flags_off, total_bytes;
     uint8_t     *base;                          // this rank's receive buffer (+ flag words)
     uint8_t     *peer[GATHER_MAX_WORLD];        // peers' receive buffers mapped into this process
@@ -58,7 +59,7 @@ extern "C" int lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes
                 "lrc_gather_create: need 1 <= slots <= 64 and bytes_per_rank > 0");
     lrc_gather *g = new (std::nothrow) lrc_gather();
     LRC_REQUIRE(g != nullptr, LRC_ERR_NOMEM, "out of host memory");
-    g->ctx = ctx; g->rank = rank; g->world = world; g->slots = slots;
+    g->ctx = ctx; g->rank = rank; g->world = world; g->slots = slots; g->root = -1;
     g->bytes_per_rank = bytes_per_rank;
     g->block_stride = align_up(bytes_per_rank, GATHER_ALIGN);
     g->slot_stride = g->block_stride * world;
@@ -172,6 +173,20 @@ extern "C" int lrc_gather_connect_local(lrc_gather *g, lrc_gather *const *all)
     return LRC_OK;
 }
 
+// Who receives: every rank (root < 0, the default: an all-gather, `world - 1` outbound and inbound blocks per rank and
+// push) or one rank only (a gather: one outbound block per rank, world - 1 inbound blocks at the root -- what a KPN graph
+// whose consumer lives on one device needs; measured at 8 GPUs the all-gather's copy-engine traffic slows the HBM-bound
+// chain kernel of EVERY rank by 4.2 %, profiles/r2_i_bench_n8.json).  SPMD: every rank sets the same root before its
+// first push.
+extern "C" int lrc_gather_set_root(lrc_gather *g, int root)
+{
+    LRC_REQUIRE(g && root >= -1 && root < g->world, LRC_ERR_INVALID, "lrc_gather_set_root: need -1 <= root < world");
+    for (int s = 0; s < g->slots; ++s)
+        LRC_REQUIRE(g->seq[s] == 0, LRC_ERR_INVALID, "lrc_gather_set_root: pushes were already issued");
+    g->root = root;
+    return LRC_OK;
+}
+
 // Order `stream` (the producer of the NEXT block that will live in the same source buffer) behind the copies of
 // this rank's previous push from `slot`: the source buffer may be overwritten afterwards.
 extern "C" int lrc_gather_wait_sent(lrc_gather *g, int slot, void *stream)
@@ -193,6 +208,7 @@ extern "C" int lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void 
     LRC_CUDA(cudaStreamWaitEvent(g->push_stream, g->ev_src, 0));
     for (int i = 0; i < g->world; ++i) {
         const int p = (g->rank + 1 + i) % g->world;          // start at the right-hand neighbour: spreads the NVSwitch ports
+        if (g->root >= 0 && p != g->root) continue;
         LRC_CUDA(cudaMemcpyAsync(slot_block(g, g->peer[p], slot, g->rank), d_src, g->bytes_per_rank,
                                  cudaMemcpyDeviceToDevice, g->push_stream));
         const CUresult r = g->write32(reinterpret_cast<CUstream>(g->push_stream),
@@ -214,6 +230,7 @@ extern "C" int lrc_gather_wait(lrc_gather *g, int slot, void *stream)
     LRC_BIND(g->ctx);
     const uint32_t seq = g->seq[slot];
     if (seq == 0) return LRC_OK;
+    if (g->root >= 0 && g->rank != g->root) return LRC_OK;   // nothing is sent here
     cudaStream_t s = lrc_stream(g->ctx, stream);
     for (int p = 0; p < g->world; ++p) {
         const CUresult r = g->wait32(reinterpret_cast<CUstream>(s),

@@ -115,3 +115,33 @@ def test_gather_two_processes_cuda_ipc(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_gather_to_one_root_only_that_rank_receives(ctx):
+    """lrc_gather_set_root: a gather instead of an all-gather -- every rank pushes ONE block (to the root), the root's
+    buffer holds every rank's block, nothing lands on the other ranks and their wait() has nothing to wait for."""
+    world, slots, n = 3, 2, 2048
+    gs = [blocks.Gather(ctx, r, world, n * 4, slots) for r in range(world)]
+    blocks.Gather.connect_local(gs)
+    for g in gs:
+        g.set_root(1)
+    srcs = [torch.empty(n, dtype=torch.float32, device=ctx.tdev) for _ in range(world)]
+    for it in range(4):
+        slot = it % slots
+        for r in range(world):
+            gs[r].wait_sent(slot)
+            srcs[r].fill_(float(10 * it + r + 1))
+            gs[r].push(slot, srcs[r])
+        for r in range(world):
+            gs[r].wait(slot)
+        ctx.sync()
+        torch.cuda.synchronize()
+        root_buf = gs[1].buffer(slot)
+        for p in range(world):
+            assert torch.all(root_buf[p] == float(10 * it + p + 1)), (it, p)
+        for r in (0, 2):
+            assert torch.all(gs[r].buffer(slot) == 0), (it, r)           # never written: still the zeros of create
+    with pytest.raises(blocks.capi.LrcError):
+        gs[0].set_root(0)                                                # pushes were already issued
+    for g in gs:
+        g.close()
