@@ -460,7 +460,7 @@ def run_ours(args):
     # the only exchange: every rank's output rows go to every peer.  Default: lrc_gather (copy engines over NVLink,
     # zero SMs, overlaps the next step's persistent kernel); fallback / --gather nccl: NCCL all-gather, whose kernel
     # cannot start while the chain kernel fills every SM and therefore serialises with it.
-    gather, gather_kind, gath, gather_all = None, "none (1 GPU)", None, None
+    gather, gather_kind, gath, gather_all, gather_rot = None, "none (1 GPU)", None, None, None
     if world > 1:
         ok = torch.zeros(1, device=dev)
         if args.gather == "ce":
@@ -468,7 +468,11 @@ def run_ours(args):
                 gather = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
                 if args.gather_to == "root":
                     gather.set_root(0)
-                    gather_all = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()   # diagnostics only
+                elif args.gather_to == "rotate":
+                    gather.set_root(-2)
+                # diagnostics only: the same loop with the other two placements of the receiver
+                gather_all = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
+                gather_rot = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed().set_root(-2)
                 ok += 1
             except Exception as e:                         # e.g. CUDA IPC not permitted in this container
                 print(f"bench.py rank {rank}: lrc_gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
@@ -477,9 +481,10 @@ def run_ours(args):
         if int(ok.item()) != world:
             if gather is not None:
                 gather.close()
-            if gather_all is not None:
-                gather_all.close()
-            gather = gather_all = None
+            for gx in (gather_all, gather_rot):
+                if gx is not None:
+                    gx.close()
+            gather = gather_all = gather_rot = None
         # bounded-time probe before the timed loop depends on it (every rank created and connected its Gather): one push +
         # arrival wait per slot on a side stream, polled from the host.  A peer whose flag write never arrives would
         # otherwise hang the bench inside a device-side wait; the probing stream can never drain in that case, so the
@@ -508,6 +513,8 @@ def run_ours(args):
         else:
             gather_kind = ("lrc_gather, root 0: copy-engine P2P push of every rank's output rows into rank 0's slot (CUDA IPC, 2 slots)"
                            if args.gather_to == "root" else
+                           "lrc_gather, rotating receiver: step n's rows of every rank land on rank (n - 1 + slot) % world"
+                           if args.gather_to == "rotate" else
                            "lrc_gather, all ranks: copy-engine P2P push of output rows into every peer's slot (CUDA IPC, 2 slots)")
 
     def step(i):
@@ -592,7 +599,11 @@ def run_ours(args):
             want = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(want, outs[b])
             got = gather.buffer(b).reshape(world * rows, NFFT)
-            if (args.gather_to == "all" or rank == 0) and not torch.equal(got, want):
+            w_ = max(args.warmup, 3)
+            last_push = 1 + (w_ + 1 - b) // 2 + (args.steps + 1 - b) // 2     # pushes of slot b so far: probe, warm-up, timed
+            mine = (args.gather_to == "all" or (args.gather_to == "root" and rank == 0) or
+                    (args.gather_to == "rotate" and rank == (last_push - 1 + b) % world))
+            if mine and not torch.equal(got, want):
                 raise SystemExit(f"bench.py rank {rank}: lrc_gather slot {b} differs from the NCCL all-gather")
     # ---- where a multi-GPU step's time goes (0.93 at 8 GPUs unexplained): every rank's own kernel time, the
     # same timed loop again WITHOUT the gather (no pushes, no arrival waits; max over ranks), and rank 0 alone
@@ -606,13 +617,18 @@ def run_ours(args):
         ng_ms, ng_kern = timed_loop(False)
         tn = torch.tensor([ng_ms, ng_kern], device=dev, dtype=torch.float64)
         dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-        ta = None
-        if gather_all is not None:                             # the same loop with the rows pushed to EVERY rank
+        ta = tr = None
+        if gather_all is not None:                             # the same loop with the rows pushed to EVERY rank ...
             dist.barrier()
             torch.cuda.synchronize()
             ag_ms, ag_kern = timed_loop(True, gather_all)
             ta = torch.tensor([ag_ms, ag_kern], device=dev, dtype=torch.float64)
             dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            dist.barrier()                                     # ... and with the receiver rotating from step to step
+            torch.cuda.synchronize()
+            rg_ms, rg_kern = timed_loop(True, gather_rot)
+            tr = torch.tensor([rg_ms, rg_kern], device=dev, dtype=torch.float64)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         # one rank alone (the others idle): is the kernel itself slower when its peers run (power, NVLink inbound writes)?
         solo = torch.zeros(2, device=dev, dtype=torch.float64)
         dist.barrier()
@@ -626,10 +642,14 @@ def run_ours(args):
                 "kernel_ms_without_gather_max_over_ranks": float(tn[1].item()),
                 "ms_per_step_all_gather_max_over_ranks": (float(ta[0].item()) / args.steps) if ta is not None else None,
                 "kernel_ms_all_gather_max_over_ranks": float(ta[1].item()) if ta is not None else None,
+                "ms_per_step_rotating_receiver_max_over_ranks": (float(tr[0].item()) / args.steps) if tr is not None else None,
+                "kernel_ms_rotating_receiver_max_over_ranks": float(tr[1].item()) if tr is not None else None,
                 "ms_per_step_rank0_alone_peers_idle": float(solo[0].item()),
                 "kernel_ms_rank0_alone_peers_idle": float(solo[1].item()),
-                "note": "ms_per_step - ms_per_step_without_gather = cost of the gather (pushes, arrival waits, final drain over "
-                        "`steps` steps); without_gather - rank0_alone = what running next to busy peers costs the kernel"}
+                "note": "kernel_ms_per_rank: only the RECEIVER of the gather runs a slower kernel (inbound P2P writes into an "
+                        "HBM-saturated GPU); ms_per_step - ms_per_step_without_gather = what the gather costs in all; the all-gather and "
+                        "rotating-receiver lines are the same loop with the receiver placed differently; without_gather - rank0_alone "
+                        "= what running next to busy peers costs"}
     clocks = None
     if sampler:
         # NVML refreshes its clock reading only every few tens of ms: when the timed region was too short
@@ -783,8 +803,9 @@ def run_ours(args):
         dist.barrier()
     if gather is not None:
         gather.close()
-    if gather_all is not None:
-        gather_all.close()
+    for gx in (gather_all, gather_rot):
+        if gx is not None:
+            gx.close()
     chain.close()
     ctx.close()
     if world > 1:
@@ -807,8 +828,9 @@ def main():
     ap.add_argument("--quick-extra", action="store_true", dest="quick_extra", help="extra block at 1/8 size (smoke runs)")
     ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
                     help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
-    ap.add_argument("--gather-to", default="root", choices=["root", "all"], dest="gather_to",
-                    help="N > 1: who receives the output rows: rank 0 only (a gather, default) or every rank (all-gather)")
+    ap.add_argument("--gather-to", default="root", choices=["root", "all", "rotate"], dest="gather_to",
+                    help="N > 1: who receives the output rows: rank 0 only (a gather, default), every rank (all-gather), or a "
+                         "receiver that rotates from step to step")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
                     help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()

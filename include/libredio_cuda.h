@@ -313,9 +313,12 @@ int lrc_ook_envelope_table(lrc_ctx *ctx, float *d_table, void *stream);
 typedef struct lrc_gather lrc_gather;
 int    lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, lrc_gather **g);
 int    lrc_gather_destroy(lrc_gather *g);
-/* root < 0 (default): every rank receives every rank's block (all-gather); root = r: only rank r receives (gather) --
- * pushes then send one block per rank instead of world-1, and lrc_gather_wait is a no-op on the other ranks.  Same root on
- * every rank, before the first push. */
+/* root = -1 (default): every rank receives every rank's block (all-gather); root = r: only rank r receives (gather) --
+ * pushes then send one block per rank instead of world-1, and lrc_gather_wait is a no-op on the other ranks;
+ * root = LRC_GATHER_ROTATE: the receiver rotates, push n (1-based) of slot s lands on rank (n - 1 + s) % world.
+ * Same value on every rank, before the first push. */
+#define LRC_GATHER_ALL (-1)
+#define LRC_GATHER_ROTATE (-2)
 int    lrc_gather_set_root(lrc_gather *g, int root);
 size_t lrc_gather_handle_bytes(void);
 int    lrc_gather_export(lrc_gather *g, void *h_handle, size_t cap);

@@ -24,7 +24,8 @@ typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct lrc_gather {
     lrc_ctx     *ctx;
     int          rank, world, slots;
-    int          root;                          // -1: every rank receives every block (all-gather); r: only rank r receives
+    int          root;                          // -1: every rank receives every block (all-gather); r: only rank r receives;
+                                                // -2: the receiver rotates, push n of slot s lands on rank (n - 1 + s) % world
     size_t       bytes_per_rank, block_stride, slot_stride, flags_off, total_bytes;
     uint8_t     *base;                          // this rank's receive buffer (+ flag words)
     uint8_t     *peer[GATHER_MAX_WORLD];        // peers' receive buffers mapped into this process
@@ -177,10 +178,12 @@ extern "C" int lrc_gather_connect_local(lrc_gather *g, lrc_gather *const *all)
 // push) or one rank only (a gather: one outbound block per rank, world - 1 inbound blocks at the root -- what a KPN graph
 // whose consumer lives on one device needs; measured at 8 GPUs the all-gather's copy-engine traffic slows the HBM-bound
 // chain kernel of EVERY rank by 4.2 %, profiles/r2_i_bench_n8.json).  SPMD: every rank sets the same root before its
-// first push.
+// first push.  root = -2 (LRC_GATHER_ROTATE): the receiver rotates -- push n of slot s lands on rank (n - 1 + s) % world -- for
+// graphs whose consumers are sharded like their producers: the same bytes cross NVLink, but every rank takes the inbound
+// writes of one step in `world` (it is the RECEIVER's kernel that inbound P2P writes slow down, by 4.7 % for 28 MB a step).
 extern "C" int lrc_gather_set_root(lrc_gather *g, int root)
 {
-    LRC_REQUIRE(g && root >= -1 && root < g->world, LRC_ERR_INVALID, "lrc_gather_set_root: need -1 <= root < world");
+    LRC_REQUIRE(g && root >= -2 && root < g->world, LRC_ERR_INVALID, "lrc_gather_set_root: need -2 <= root < world");
     for (int s = 0; s < g->slots; ++s)
         LRC_REQUIRE(g->seq[s] == 0, LRC_ERR_INVALID, "lrc_gather_set_root: pushes were already issued");
     g->root = root;
@@ -209,6 +212,7 @@ extern "C" int lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void 
     for (int i = 0; i < g->world; ++i) {
         const int p = (g->rank + 1 + i) % g->world;          // start at the right-hand neighbour: spreads the NVSwitch ports
         if (g->root >= 0 && p != g->root) continue;
+        if (g->root == -2 && p != (int)((seq - 1 + (uint32_t)slot) % (uint32_t)g->world)) continue;
         LRC_CUDA(cudaMemcpyAsync(slot_block(g, g->peer[p], slot, g->rank), d_src, g->bytes_per_rank,
                                  cudaMemcpyDeviceToDevice, g->push_stream));
         const CUresult r = g->write32(reinterpret_cast<CUstream>(g->push_stream),
@@ -231,6 +235,7 @@ extern "C" int lrc_gather_wait(lrc_gather *g, int slot, void *stream)
     const uint32_t seq = g->seq[slot];
     if (seq == 0) return LRC_OK;
     if (g->root >= 0 && g->rank != g->root) return LRC_OK;   // nothing is sent here
+    if (g->root == -2 && g->rank != (int)((seq - 1 + (uint32_t)slot) % (uint32_t)g->world)) return LRC_OK;
     cudaStream_t s = lrc_stream(g->ctx, stream);
     for (int p = 0; p < g->world; ++p) {
         const CUresult r = g->wait32(reinterpret_cast<CUstream>(s),
