@@ -294,53 +294,10 @@ struct WarpFFT1024 {
         }
     }
 
-    // The first radix-32 butterfly with a real window folded into its first level: the four products w x of a radix-4
-    // butterfly cost 2 FMUL2 + 4 FFMA2 inside its first four additions instead of 4 FMUL2 + 4 FADD2 in front of them
-    // (w0 x0 +- w2 x2 = fma(x2, +-w2, w0 x0)).  w[e] = window[lane + 32 e].
-    __device__ __forceinline__ static void first_pass_windowed(float2 *v, const float *w)
-    {
-        constexpr int R2 = 8;
-#pragma unroll
-        for (int b = 0; b < R2; ++b) {
-            float2 &a0 = v[b], &a1 = v[R2 + b], &a2 = v[2 * R2 + b], &a3 = v[3 * R2 + b];
-            const float w0 = w[b], w1 = w[R2 + b], w2 = w[2 * R2 + b], w3 = w[3 * R2 + b];
-            const float2 t0 = mul2(a0, make_float2(w0, w0)), t1 = mul2(a1, make_float2(w1, w1));
-            const float2 s02 = fma2(a2, make_float2(w2, w2), t0), d02 = fma2(a2, make_float2(-w2, -w2), t0);
-            const float2 s13 = fma2(a3, make_float2(w3, w3), t1), d13 = rot90<INV>(fma2(a3, make_float2(-w3, -w3), t1));
-            a0 = cadd(s02, s13);
-            a2 = csub(s02, s13);
-            a1 = cadd(d02, d13);
-            a3 = csub(d02, d13);
-        }
-#pragma unroll
-        for (int c = 1; c < 4; ++c)
-#pragma unroll
-            for (int b = 1; b < R2; ++b) v[R2 * c + b] = mul_w32<INV>(v[R2 * c + b], b * c);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) RegFFT<R2, INV>::run(v + R2 * c);
-        float2 tmp[32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int d = 0; d < R2; ++d) tmp[c + 4 * d] = v[R2 * c + d];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = tmp[i];
-    }
-
     // v[e] = x[lane + 32 e] on entry, X[lane + 32 e] on exit.  xb: this warp's SMEM_CPX float2 tile.
     __device__ __forceinline__ static void run(float2 *v, float2 *xb, const float2 *tws, int lane)
     {
         RegFFT<32, INV>::run(v);
-        second_half(v, xb, tws, lane);
-    }
-    // the same on w[e] v[e]
-    __device__ __forceinline__ static void run_windowed(float2 *v, const float *w, float2 *xb, const float2 *tws, int lane)
-    {
-        first_pass_windowed(v, w);
-        second_half(v, xb, tws, lane);
-    }
-    __device__ __forceinline__ static void second_half(float2 *v, float2 *xb, const float2 *tws, int lane)
-    {
         const float2 *twl = tws + lane;
 #pragma unroll
         for (int r = 1; r < 32; ++r) v[r] = cmulf(v[r], twl[32 * (r - 1)]);

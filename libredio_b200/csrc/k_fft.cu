@@ -569,73 +569,6 @@ psd1024_warp_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw
     }
 }
 
-// Variant with the |X|^2 accumulators in SHARED memory and the window folded into the first butterfly level.
-// ncu on psd1024_warp_kernel (profiles/r1_s6_psd1024_warp_ncu_keys.txt): FMA pipe 66-70 % active with 12 warps per SM -- it
-// is occupancy (156 registers: 64 for the frame, 32 for the accumulators) that leaves the pipe idle, while reaching the HBM
-// roofline needs ~80 % of it.  Here a warp adds each frame's |X|^2 into its own 4 KB of shared memory (red.shared.add.f32,
-// one per point: only this warp ever touches it, in frame order, so the sum stays deterministic) and the kernel fits
-// 16 warps per SM; the window multiply costs 16 packed instructions per frame instead of 32 (WarpFFT1024::run_windowed).
-template <int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-psd1024_warp_sacc_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, const float *__restrict__ win,
-                         float *__restrict__ partial, size_t k_avg, size_t fpi, size_t ipr, size_t n_items)
-{
-    using F = WarpFFT1024<false>;
-    constexpr int N = 1024;
-    extern __shared__ __align__(16) float2 psdw_sm[];
-    float2 *tws = psdw_sm + WARPS * F::SMEM_CPX;
-    float *wsm = reinterpret_cast<float *>(tws + F::TW_CPX);
-    float *accs = wsm + N;                                   // [WARPS][1024]
-    for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[i] = win[i];
-    F::fill_twiddles(tw, tws);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *xb = psdw_sm + warp * F::SMEM_CPX;
-    const float *wl = wsm + lane;
-    float *acc = accs + warp * N + lane;
-    const uint32_t acc_s = smem_u32(acc);
-    const size_t stride = (size_t)gridDim.x * WARPS;
-    for (size_t item = (size_t)blockIdx.x * WARPS + warp; item < n_items; item += stride) {
-        const size_t row = item / ipr, c = item % ipr;
-        const size_t f0 = row * k_avg + c * fpi;
-        size_t f1 = f0 + fpi;
-        if (f1 > (row + 1) * k_avg) f1 = (row + 1) * k_avg;
-        size_t fnext_item = 0;
-        const bool has_next = item + stride < n_items;
-        if (has_next) {
-            const size_t it2 = item + stride;
-            fnext_item = (it2 / ipr) * k_avg + (it2 % ipr) * fpi;
-        }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[32 * e] = 0.f;
-        for (size_t f = f0; f < f1; ++f) {
-            float2 v[32];
-            const float2 *src = in + f * N + lane;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __ldcs(src + 32 * e);
-            {   // next frame -> L2: 8 KB = 64 lines of 128 B, two per lane
-                const bool more = f + 1 < f1;
-                if (more || has_next) {
-                    const char *nx = reinterpret_cast<const char *>(in + (more ? f + 1 : fnext_item) * N) + lane * 256;
-                    prefetch_l2(nx); prefetch_l2(nx + 128);
-                }
-            }
-            float w[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) w[e] = wl[32 * e];
-            F::run_windowed(v, w, xb, tws, lane);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float m = fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
-                asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(acc_s + 128u * e), "f"(m) : "memory");
-            }
-        }
-        float *dst = partial + item * N + lane;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) dst[32 * e] = acc[32 * e];
-    }
-}
-
 // Same transform, frames double-buffered in REGISTERS: the 32 loads of the warp's next frame are issued before
 // the current frame is transformed, so a full frame of arithmetic (~760 issue slots) covers the HBM latency and
 // no warp ever sits in a pure load phase.  Costs 64 more registers (2 CTAs of 4 warps per SM instead of 3).
@@ -750,9 +683,8 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
             };
             if constexpr (LOG2N == 10) {
                 if (variant == 0 || variant >= 10) {
-                    auto launch_w = [&](auto kern, int warps = PSDW_WARPS, bool sacc = false) -> int {
-                        const int smem = (warps * WarpFFT1024<false>::SMEM_CPX + WarpFFT1024<false>::TW_CPX) * 8 + 1024 * 4 +
-                                         (sacc ? warps * 1024 * 4 : 0);
+                    auto launch_w = [&](auto kern, int warps = PSDW_WARPS) -> int {
+                        const int smem = (warps * WarpFFT1024<false>::SMEM_CPX + WarpFFT1024<false>::TW_CPX) * 8 + 1024 * 4;
                         LRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                         int occ = 1;
                         LRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
@@ -773,9 +705,6 @@ static int launch_psd(lrc_psd *p, const float2 *in, size_t k_avg, size_t fpi, si
                         case 14: return launch_w(psd1024_warp_db_kernel<2, 4>, 4);
                         case 15: return launch_w(psd1024_warp_db_kernel<1, 8>, 8);
                         case 16: return launch_w(psd1024_warp_db_kernel<3, 4>, 4);
-                        case 17: return launch_w(psd1024_warp_sacc_kernel<8, 2>, 8, true);
-                        case 18: return launch_w(psd1024_warp_sacc_kernel<4, 4>, 4, true);
-                        case 19: return launch_w(psd1024_warp_sacc_kernel<4, 3>, 4, true);
                         default: return launch_w(psd1024_warp_kernel<3, 1>);
                     }
                 }
