@@ -22,6 +22,7 @@
 //                          matcher A and B -> shaper_optional -> packed packets
 #include "common.cuh"
 #include "unpack.cuh"
+#include <cuda.h>
 #include <algorithm>
 #include <vector>
 
@@ -80,6 +81,40 @@ __device__ __forceinline__ void lut_load(float *s_lut, const float *__restrict__
     __syncthreads();
 }
 
+// ---- folded table (round 2, the block-sum kernel's default) -----------------------------------------------
+// ncu on the triangular lookup (profiles/r1_s3_ookA3_ncu_keys.txt): ALU pipe 89.5 %, 13.6 issued instructions per
+// sample of which 5.5 are ALU-pipe index work (PRMT x2, IMNMX x2, LEA) and ~4 are the cp.async slab bookkeeping.
+// The folded table needs no byte extraction and no per-byte max/min:
+//   * a 32-bit word holds two samples {b0, b1} {b2, b3}; ONE PRMT swaps the bytes of both halfwords and ONE
+//     VIMNMX.U16x2 (__vmaxu2) takes the per-halfword maximum  max(b0 | b1 << 8, b1 | b0 << 8) = hi << 8 | lo,
+//     the sorted pair as a 16-bit key -- two ALU instructions for two samples;
+//   * the triangle {lo <= hi} is folded into the 129 x 256 rectangle of rows 127..255: rows hi >= 128 stay where they
+//     are (columns 0..hi), a row hi <= 127 goes to row 254 - hi, columns 255 - lo (the free columns hi' + 1 .. 255 of
+//     that row): key2 = max(key, 65279 - key), one integer multiply-add (FMA pipe) and one signed max;
+//   * rows are skewed 8 banks apart like the triangular table's: index = key2 + (key2 >> 5) = 264 row + col + col / 32
+//     (one LEA.HI), injective because col + col / 32 <= 262 < 264.
+// 3.5 ALU-pipe instructions per sample instead of 5.5.  The table is filled by the same lr_envelope as before, so
+// table == formula for all 65536 pairs is still checked by the bit-exact block sums of every OOK test.
+constexpr uint32_t OOK_FOLD_C = 65279u;                                  // 254 * 256 + 255
+__host__ __device__ __forceinline__ uint32_t ook_fold_index(uint32_t key)   // key = hi << 8 | lo, lo <= hi
+{
+    const int alt = (int)OOK_FOLD_C - (int)key;                          // negative for hi = 255: loses the signed max
+    const uint32_t k2 = (uint32_t)(alt > (int)key ? alt : (int)key);
+    return k2 + (k2 >> 5);
+}
+constexpr uint32_t OOK_FOLD_MIN = 32640u + (32640u >> 5);                // smallest index in use (key2 >= 32640)
+constexpr uint32_t OOK_FOLD_MAX = 65535u + (65535u >> 5);
+constexpr int OOK_FLUT_N = (int)((OOK_FOLD_MAX - OOK_FOLD_MIN + 1 + 3) / 4 * 4);   // 33924 floats
+constexpr int OOK_FLUT_BYTES = OOK_FLUT_N * 4;
+
+__global__ void ook_build_flut_kernel(float *__restrict__ flut)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536u) return;
+    const uint32_t hi = i >> 8, lo = i & 0xffu;
+    if (lo <= hi) flut[ook_fold_index(i) - OOK_FOLD_MIN] = lr_envelope(hi, lo);
+}
+
 __global__ void ook_build_lut_kernel(float *__restrict__ lut)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,7 +138,9 @@ struct lrc_ook {
     unsigned long long *d_packets;    // [n_streams][2][max_packets] packets packed MSB-first
     uint32_t *d_npackets;             // [n_streams][2]
     uint32_t *d_runs_dbg;             // [n_streams][max_runs] (value << 31 | length), filled by K-D
-    float    *d_lut;                  // triangular envelope table, OOK_LUT_N floats
+    float    *d_lut;                  // triangular envelope table, OOK_LUT_N floats (LRC_OOK_KA=0 variant)
+    float    *d_flut;                 // folded envelope table, OOK_FLUT_N floats (default block-sum kernel)
+    void     *encode_tiled;           // cuTensorMapEncodeTiled (driver entry point, fetched once)
     uint16_t *d_rank;                 // [65536] rank of the pair's envelope among the distinct envelope values
     float    *d_uniq;                 // [n_uniq] the distinct envelope values, ascending
     uint32_t  n_uniq;
@@ -192,29 +229,235 @@ ook_block_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
 }
 
 // ---------------------------------------------------------------------------------------------
-// K-B: trigger state machine, one thread per stream (bitfount.rs:41-81, statement by statement)
+// K-A, round 2 (default): the same lane-owns-block walk with
+//   * the folded table above (3.5 instead of 5.5 ALU-pipe instructions per sample), and
+//   * the staging done by the TMA engine: the capture is described to it as a 3-D byte tensor
+//     [stream][block][1024 B]; ONE cp.async.bulk.tensor per slab (issued by lane 0) brings the box
+//     {64 B, 32 blocks, 1 stream} into a 2 KB stage with the 64-byte hardware swizzle, i.e. 16-byte chunk c of
+//     row r lands at chunk c ^ ((r >> 1) & 3).  Lane r then reads its row with four LDS.128 and the eight lanes of
+//     a quarter-warp phase hit eight distinct bank groups (4 r + (c ^ f(r)) mod 8 takes all values 0..7) -- the
+//     transposition costs no padding, no per-lane address arithmetic and no LDGSTS instructions (the cp.async
+//     version spent ~4 of its 13.6 instructions per sample on slab bookkeeping).  Blocks past the end of the
+//     capture are zero-filled by the TMA (out-of-bounds rows of the box).
+// Every warp runs its own ring of KA2_STAGES stages with one mbarrier per stage and treats all its (group, slab)
+// pairs as one flat sequence, so the prefetch runs across group boundaries.
 // ---------------------------------------------------------------------------------------------
-constexpr int KB_THREADS = 64;                // streams per CTA (static shared memory stays under 48 KB)
+constexpr int KA2_SLAB_BYTES = 64;
+constexpr int KA2_STAGE_BYTES = 32 * KA2_SLAB_BYTES;
+constexpr int KA2_SLABS = OOK_BLOCK * 2 / KA2_SLAB_BYTES;     // 16 slabs per block row
+
+template <int WARPS, int STAGES>
+struct Ka2Cfg {
+    static constexpr int STG_OFF = (OOK_FLUT_BYTES + 1023) / 1024 * 1024;
+    static constexpr int BAR_OFF = STG_OFF + WARPS * STAGES * KA2_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + WARPS * STAGES * 8 + 1024;     // + slack to align the base to 1024
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void tma_load_box3(uint32_t dst_s, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar_s)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst_s), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar_s) : "memory");
+}
+
+// envelope of one sorted 16-bit key through the folded table; flut_adj = shared address of the table minus
+// 4 OOK_FOLD_MIN.  Pipe balance is the point (the triangular lookup had 5.5 ALU-pipe instructions per sample): the
+// negation and the skew k2 + (k2 >> 5) are written so that ptxas keeps them on the FMA pipe -- the skew as
+// mad.hi by 2^27 + 1 (floor(k2 (2^27 + 1) / 2^32) = k2 >> 5 for k2 < 2^16; with the plain 2^27 ptxas turns it into
+// an ALU-pipe LEA.HI) -- which leaves the fused add-max (VIADDMNMX) and the address LEA on the ALU pipe.
+template <bool SKEW_FMA>
+__device__ __forceinline__ float flut_envelope(uint32_t flut_adj, uint32_t key)
+{
+    int alt;
+    asm("mad.lo.s32 %0, %1, -1, 65279;" : "=r"(alt) : "r"((int)key));
+    const uint32_t k2 = (uint32_t)max(alt, (int)key);
+    uint32_t idx;
+    if (SKEW_FMA) asm("mad.hi.u32 %0, %1, 134217729, %1;" : "=r"(idx) : "r"(k2));   // IMAD.HI (+ a zeroed pair register)
+    else idx = k2 + (k2 >> 5);                                                       // LEA.HI
+    float e;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(flut_adj + 4u * idx));
+    return e;
+}
+
+template <int WARPS, int STAGES, bool SKEW_FMA>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams, size_t n_blocks,
+                     const float *__restrict__ g_flut, float *__restrict__ d_sum, float *__restrict__ d_max)
+{
+    using Cfg = Ka2Cfg<WARPS, STAGES>;
+    extern __shared__ __align__(1024) uint8_t ka2_smem[];
+    // the 64-byte swizzle pattern is a function of the shared ADDRESS: stages must sit on 512-byte boundaries
+    const uint32_t base_s = (smem_u32(ka2_smem) + 1023u) & ~1023u;
+    uint8_t *base = ka2_smem + (base_s - smem_u32(ka2_smem));
+    float *flut = reinterpret_cast<float *>(base);
+    for (int i = threadIdx.x; i < OOK_FLUT_N / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(flut)[i] = __ldg(reinterpret_cast<const float4 *>(g_flut) + i);
+    // warp index through a shuffle: the compiler then knows it (and every stage, barrier and box coordinate derived
+    // from it) is warp-uniform and keeps the TMA operands in uniform registers
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const uint32_t stg_s = base_s + Cfg::STG_OFF + warp * (STAGES * KA2_STAGE_BYTES);
+    const uint32_t bar_s = base_s + Cfg::BAR_OFF + warp * (STAGES * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_s + 8 * s), "r"(1));
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t flut_adj = base_s - 4u * OOK_FOLD_MIN;
+    const size_t groups_per_stream = (n_blocks + 31) / 32;
+    const size_t n_groups = groups_per_stream * n_streams;
+    const size_t warps_total = (size_t)gridDim.x * WARPS;
+    size_t grp = (size_t)blockIdx.x * WARPS + warp;
+    if (grp >= n_groups) return;
+    // lane's read offsets inside a stage: row = lane, chunk q at (q ^ ((lane >> 1) & 3))
+    const uint32_t row_s = stg_s + lane * KA2_SLAB_BYTES;
+    const uint32_t f16 = ((uint32_t)(lane >> 1) & 3u) << 4;
+    // stage = slab % STAGES and parity = (slab / STAGES) & 1 come from the slab counter alone: a group has 16 slabs, a
+    // multiple of 2 STAGES, so every group starts with all barriers back in phase 0
+    static_assert(KA2_SLABS % (2 * STAGES) == 0, "phase bookkeeping");
+    auto issue = [&](int st, int b0, int slab) {                 // lane 0
+        const uint32_t bar = bar_s + 8 * (slab % STAGES);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(KA2_STAGE_BYTES) : "memory");
+        tma_load_box3(stg_s + (slab % STAGES) * KA2_STAGE_BYTES, &tmap, slab * KA2_SLAB_BYTES, b0, st, bar);
+    };
+    int st = (int)(grp / groups_per_stream), b0 = (int)(grp % groups_per_stream) * 32;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < STAGES - 1; ++k) issue(st, b0, k);
+    }
+    while (true) {
+        const size_t grp_n = grp + warps_total;
+        const bool has_n = grp_n < n_groups;
+        const int st_n = (int)(grp_n / groups_per_stream), b0_n = (int)(grp_n % groups_per_stream) * 32;
+        float s = 0.0f, mx = 0.0f;
+#pragma unroll 1
+        for (int so = 0; so < KA2_SLABS; so += STAGES) {
+            const uint32_t parity = (uint32_t)(so / STAGES) & 1u;
+#pragma unroll
+            for (int h = 0; h < STAGES; ++h) {
+                const int slab = so + h;
+                // the stage this issue overwrites was read one slab ago (closed by its __syncwarp)
+                {
+                    const int nx = slab + STAGES - 1;
+                    const bool wrap = nx >= KA2_SLABS;           // the prefetch runs into the warp's next group
+                    if (lane == 0 && (!wrap || has_n)) issue(wrap ? st_n : st, wrap ? b0_n : b0, wrap ? nx - KA2_SLABS : nx);
+                }
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "WAITA_%=:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra DONEA_%=;\n"
+                    "bra WAITA_%=;\n"
+                    "DONEA_%=:\n"
+                    "}\n" :: "r"(bar_s + 8 * h), "r"(parity) : "memory");
+                const uint32_t rs = row_s + h * KA2_STAGE_BYTES;
+#pragma unroll
+                for (int q = 0; q < KA2_SLAB_BYTES / 16; ++q) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(rs + (((uint32_t)q << 4) ^ f16)));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // both samples of the word at once: per halfword max(b0 | b1 << 8, b1 | b0 << 8) = hi << 8 | lo
+                        const uint32_t K = __vmaxu2(w[k], __byte_perm(w[k], 0, 0x2301));
+                        const float e0 = flut_envelope<SKEW_FMA>(flut_adj, K & 0xffffu);
+                        const float e1 = flut_envelope<SKEW_FMA>(flut_adj, __umulhi(K, 65536u));    // K >> 16 on the FMA pipe
+                        s = __fadd_rn(s, e0);                    // samples.iter().sum(): left to right from 0.0
+                        s = __fadd_rn(s, e1);
+                        mx = fmaxf(mx, fmaxf(e0, e1));
+                    }
+                }
+                __syncwarp();                                    // every lane is done with the stage
+            }
+        }
+        if ((size_t)b0 + lane < n_blocks) {
+            d_sum[(size_t)st * n_blocks + b0 + lane] = s;
+            d_max[(size_t)st * n_blocks + b0 + lane] = mx;
+        }
+        if (!has_n) break;
+        grp = grp_n; st = st_n; b0 = b0_n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K-B: trigger state machine, one thread per stream (bitfount.rs:41-81, statement by statement)
+//
+// The walk along a stream is one dependent chain (threshold -> compare -> trigger -> threshold ...): its length in
+// cycles IS the kernel's duration, whatever the number of streams.  Round 1 had every thread stage its tile, divide its
+// sums by 1000, walk, and write its tags back: ~2500 dependent-issue slots per 32-block tile on a warp that has an SM
+// sub-partition to itself (133 us for 500 blocks, 490 cycles per block).  Now a CTA is ONE walker warp (32 streams)
+// plus three helper warps that do everything that is not the chain, a tile ahead or behind the walker:
+//   helpers, iteration i : wait for the cp.async copies of tile i+1 (sums, maxima), q = s / 1000 (:63) for tile i+1,
+//                          tags of tile i-1 out to global memory (coalesced), cp.async of tile i+2
+//   walker,  iteration i : tile i from shared memory, eight blocks ahead into registers, the reference's statements
+//                          as selects (32 streams are in 32 different states: as branches every `if` would run both
+//                          sides one after the other), a branch only where a burst ends
+// one __syncthreads per tile.  A burst that is dropped (the OOM guard :52-54, or still open when the capture ends) keeps bit 0
+// of its flag clear and has its blocks un-tagged once all tags are in global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp
+constexpr int KB_HELPERS = 96;                // helper threads (three warps)
+constexpr int KB_THREADS = KB_STREAMS + KB_HELPERS;
 constexpr int KB_TILE = 32;                   // blocks per staged tile
-constexpr int KB_LD = KB_TILE + 1;
+constexpr int KB_LD = KB_TILE + 1;            // conflict-free both ways: helpers move rows, the walker reads columns
 
 __global__ void __launch_bounds__(KB_THREADS)
 ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_max, size_t n_streams,
                    size_t n_blocks, size_t max_bursts, int32_t *__restrict__ d_tag, float *__restrict__ d_half,
                    uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
 {
-    // The state machine is sequential per stream (one thread each); its inputs are not: the CTA stages
-    // tiles of [128 streams][32 blocks] sums and maxima through shared memory with coalesced row reads
-    // (a warp reads 32 consecutive floats of one stream), double-buffered so the next tile is in flight
-    // while this one is walked, and the tags leave the same way.
-    __shared__ float s_sum[2][KB_THREADS * KB_LD];
-    __shared__ float s_max[2][KB_THREADS * KB_LD];
-    __shared__ int32_t s_tag[KB_THREADS * KB_LD];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t st0 = (size_t)blockIdx.x * KB_THREADS;
+    __shared__ float s_sum[3][KB_STREAMS * KB_LD];
+    __shared__ float s_max[3][KB_STREAMS * KB_LD];
+    __shared__ float s_q[2][KB_STREAMS * KB_LD];
+    __shared__ int32_t s_tag[2][KB_STREAMS * KB_LD];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const size_t st0 = (size_t)blockIdx.x * KB_STREAMS;
+    const int n_tiles = (int)((n_blocks + KB_TILE - 1) / KB_TILE);
+    const bool walker = tid < KB_STREAMS;
+    const int ht = tid - KB_STREAMS, hwarp = ht >> 5;                  // helpers: 3 warps, warp w moves rows w, w + 3, ...
+    // cp.async (LDGSTS) of tile `tile` into its buffer: a helper warp moves 32 consecutive floats of one stream per step
+    auto stage = [&](int tile) {
+        if (tile < n_tiles) {
+            const int buf = tile % 3;
+            const size_t b = (size_t)tile * KB_TILE + lane;
+            for (int r = hwarp; r < KB_STREAMS; r += KB_HELPERS / 32) {
+                const size_t s = st0 + r;
+                float *ds = &s_sum[buf][r * KB_LD + lane], *dm = &s_max[buf][r * KB_LD + lane];
+                if (s < n_streams && b < n_blocks) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(ds)), "l"(d_sum + s * n_blocks + b) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dm)), "l"(d_max + s * n_blocks + b) : "memory");
+                } else {
+                    *ds = 0.0f; *dm = 0.0f;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // s / 1000 (:63) of tile `tile`, whose copies have landed: 1024 independent IEEE divisions over 96 threads
+    auto quotients = [&](int tile) {
+        if (tile >= n_tiles) return;
+        const float *src = s_sum[tile % 3];
+        float *dst = s_q[tile & 1];
+        for (int i = ht; i < KB_STREAMS * KB_TILE; i += KB_HELPERS) {
+            const int r = i >> 5, c = i & 31;
+            dst[r * KB_LD + c] = __fdiv_rn(src[r * KB_LD + c], 1000.0f);
+        }
+    };
+    auto tags_out = [&](int tile) {
+        if (tile < 0) return;
+        const int32_t *src = s_tag[tile & 1];
+        const size_t b = (size_t)tile * KB_TILE + lane;
+        for (int r = hwarp; r < KB_STREAMS; r += KB_HELPERS / 32) {
+            const size_t s = st0 + r;
+            if (s < n_streams && b < n_blocks) d_tag[s * n_blocks + b] = src[r * KB_LD + lane];
+        }
+    };
+    // walker state (one stream per lane)
     const size_t st = st0 + tid;
-    const bool live = st < n_streams;
-    int32_t *tag = d_tag + st * n_blocks;
+    const bool live = walker && st < n_streams;
     float *half = d_half + st * max_bursts;
     uint8_t *flags = d_bflags + st * max_bursts;
     int trigger = 0;                          // :41 (isize there; |trigger| <= n_blocks here)
@@ -223,99 +466,90 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     bool lead0 = true;                        // the buffer currently starts with that 0.0
     float cur_max = 0.0f;
     uint32_t burst = 0;                       // index of the burst being collected
-    size_t burst_first_block = 0;
-    bool burst_has_blocks = false;
-    const size_t n_tiles = (n_blocks + KB_TILE - 1) / KB_TILE;
-    // cp.async (LDGSTS) writes the staged tile straight into shared memory: the loads of tile t+1 are in
-    // flight while the state machine walks tile t, and nothing waits on a register
-    auto stage = [&](size_t tile, int buf) {
-        const size_t b = tile * KB_TILE + lane;
-#pragma unroll 4
-        for (int r = warp; r < KB_THREADS; r += KB_THREADS / 32) {
-            const size_t s = st0 + r;
-            float *ds = &s_sum[buf][r * KB_LD + lane], *dm = &s_max[buf][r * KB_LD + lane];
-            if (s < n_streams && b < n_blocks) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(ds)), "l"(d_sum + s * n_blocks + b) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dm)), "l"(d_max + s * n_blocks + b) : "memory");
-            } else {
-                *ds = 0.0f; *dm = 0.0f;
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0, 0);
-    for (size_t tile = 0; tile < n_tiles; ++tile) {
-        const int buf = (int)(tile & 1);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();                                   // tile `tile` is in shared memory for every thread
-        if (tile + 1 < n_tiles) stage(tile + 1, buf ^ 1);  // buffer buf^1 was last read two barriers ago
-        const size_t b0 = tile * KB_TILE;
-        const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
-        if (live) {
-            // s / 1000 (:63) for the whole tile first: 32 independent IEEE divisions pipeline, inside the
-            // state machine each would sit on the threshold's dependency chain.  s_tag doubles as the buffer.
-            float *s_q = reinterpret_cast<float *>(s_tag) + tid * KB_LD;
-#pragma unroll 8
-            for (int u = 0; u < KB_TILE; ++u) s_q[u] = __fdiv_rn(s_sum[buf][tid * KB_LD + u], 1000.0f);
-            for (int u = 0; u < nb; ++u) {
-                const size_t b = b0 + u;
-                trigger -= 1;                                                       // :46
-                const float s = s_sum[buf][tid * KB_LD + u];                       // :48
-                const float s_over_1000 = s_q[u];
-                // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps; no fixture reaches it).  KNOWN
-                // DEVIATION in one corner: when the guard fires with trigger == 1, the reference sends the reset buffer
-                // [0.0] at the next block (a burst of one 0 bit); here that burst has no tagged block and contributes no
-                // bit, so transition positions after it are one lower than the reference's.  DESIGN.md section 7.
-                if (buf_len > 1000u * OOK_TRIGGER_DURATION * OOK_BLOCK) {
-                    if (burst_has_blocks) {
-                        // blocks of this burst tagged in earlier tiles are already in global memory
-                        for (size_t k = burst_first_block; k < b0; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
-                        for (int k = 0; k < u; ++k) if (s_tag[tid * KB_LD + k] == (int32_t)burst) s_tag[tid * KB_LD + k] = -1;
+    uint32_t open_from = 0xffffffffu;         // first tagged block of the burst being collected (none yet)
+    bool dropped = false;                     // the OOM guard abandoned a burst of this stream
+    if (!walker) {
+        stage(0);
+        stage(1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");            // tile 0 has landed (this thread's part)
+        named_bar_sync(1, KB_HELPERS);
+        quotients(0);
+    }
+    __syncthreads();
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        if (!walker) {
+            asm volatile("cp.async.wait_all;" ::: "memory");            // tile + 1 (issued an iteration ago)
+            named_bar_sync(1, KB_HELPERS);                              // ... every helper's part of it
+            quotients(tile + 1);
+            tags_out(tile - 1);
+            stage(tile + 2);                                            // its buffer was last read in iteration tile - 1
+        } else if (live) {
+            const float *t_sum = s_sum[tile % 3] + tid * KB_LD, *t_max = s_max[tile % 3] + tid * KB_LD;
+            const float *t_q = s_q[tile & 1] + tid * KB_LD;
+            int32_t *t_tag = s_tag[tile & 1] + tid * KB_LD;
+            const size_t b0 = (size_t)tile * KB_TILE;
+            const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
+            for (int u0 = 0; u0 < nb; u0 += 8) {
+                // the block's inputs do not depend on the chain: eight blocks ahead into registers
+                float sr[8], qr[8], mr[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { sr[k] = t_sum[u0 + k]; qr[k] = t_q[u0 + k]; mr[k] = t_max[u0 + k]; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int u = u0 + k;
+                    if (u >= nb) break;
+                    trigger -= 1;                                                       // :46
+                    const float s = sr[k];                                              // :48
+                    // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps; no fixture reaches it): what
+                    // was collected is dropped -- the burst index is abandoned with its flag clear -- and collection goes on
+                    // in a fresh buffer [0.0].  KNOWN DEVIATION in one corner: when the guard fires with trigger == 1, the
+                    // reference sends the reset buffer [0.0] at the next block (a burst of one 0 bit); here that burst has no
+                    // tagged block and contributes no bit, so transition positions after it are one lower than the
+                    // reference's.  DESIGN.md section 7.
+                    if (buf_len > 1000u * OOK_TRIGGER_DURATION * OOK_BLOCK) {
+                        if (burst < max_bursts) flags[burst] = 0;
+                        burst += 1; dropped = true;
+                        buf_len = 1; lead0 = true; cur_max = 0.0f; open_from = 0xffffffffu;
                     }
-                    buf_len = 1; lead0 = true; cur_max = 0.0f; burst_has_blocks = false;
-                }
-                if (threshold == 0.0f) threshold = s;                               // :57-59
-                if (trigger < 0) {                                                  // :62-65
-                    threshold = __fadd_rn(threshold, s_over_1000);
-                    threshold = __fsub_rn(threshold, __fmul_rn(threshold, 0.002f));
-                }
-                if (s > __fmul_rn(threshold, 4.0f)) trigger = OOK_TRIGGER_DURATION; // :68-70
-                int32_t tg = -1;
-                if (trigger > 1) {                                                  // :73-75 push_all
-                    if (burst < max_bursts) {
-                        tg = (int32_t)burst;
-                        if (!burst_has_blocks) { burst_first_block = b; burst_has_blocks = true; }
+                    const float thr0 = threshold == 0.0f ? s : threshold;               // :57-59
+                    const float thr1 = __fadd_rn(thr0, qr[k]);                          // :62-65
+                    const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
+                    threshold = trigger < 0 ? thr2 : thr0;
+                    trigger = s > __fmul_rn(threshold, 4.0f) ? OOK_TRIGGER_DURATION : trigger;   // :68-70
+                    const bool collect = trigger > 1;                                   // :73-75 push_all
+                    buf_len += collect ? (uint32_t)OOK_BLOCK : 0u;
+                    cur_max = collect ? fmaxf(cur_max, mr[k]) : cur_max;
+                    const bool tagged = collect && burst < max_bursts;
+                    t_tag[u] = tagged ? (int32_t)burst : -1;
+                    open_from = tagged ? min(open_from, (uint32_t)(b0 + u)) : open_from;
+                    if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
+                        if (burst < max_bursts) {
+                            half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
+                            flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                        }
+                        burst += 1;
+                        buf_len = 0; lead0 = false; cur_max = 0.0f; open_from = 0xffffffffu;
                     }
-                    buf_len += OOK_BLOCK;
-                    cur_max = fmaxf(cur_max, s_max[buf][tid * KB_LD + u]);
                 }
-                s_tag[tid * KB_LD + u] = tg;
-                if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
-                    if (burst < max_bursts) {
-                        const float h = __fdiv_rn(cur_max, 2.0f);                   // discretize :90-91 max/2f32
-                        half[burst] = h;
-                        flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
-                    }
-                    burst += 1;
-                    buf_len = 0; lead0 = false; cur_max = 0.0f; burst_has_blocks = false;
-                }
-            }
-        }
-        __syncthreads();
-        // tags of this tile out, coalesced
-        {
-            const size_t b = b0 + lane;
-            for (int r = warp; r < KB_THREADS; r += KB_THREADS / 32) {
-                const size_t s = st0 + r;
-                if (s < n_streams && b < n_blocks) d_tag[s * n_blocks + b] = s_tag[r * KB_LD + lane];
             }
         }
         __syncthreads();
     }
+    if (!walker) tags_out(n_tiles - 1);
+    __syncthreads();                          // all tags are in global memory
     if (!live) return;
-    // a burst still open when the capture ends is never sent: un-tag its blocks
-    if (burst_has_blocks)
-        for (size_t k = burst_first_block; k < n_blocks; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
+    // a burst still open when the capture ends is never sent: its blocks (at most the tail of the capture) are un-tagged,
+    // and so are -- in one pass over the stream's tags, which only a capture that tripped the OOM guard pays for -- the
+    // blocks of the bursts the guard abandoned (flag bit 0 clear).  The slicer only ever sees blocks of bursts that were sent.
+    int32_t *tag = d_tag + st * n_blocks;
+    if (burst < max_bursts) flags[burst] = 0;
+    if (open_from != 0xffffffffu)
+        for (size_t k = open_from; k < n_blocks; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
+    if (dropped)
+        for (size_t k = 0; k < n_blocks; ++k) {
+            const int32_t tg = tag[k];
+            if (tg >= 0 && !(flags[tg] & 1u)) tag[k] = -1;
+        }
     d_nbursts[st] = burst;                    // may exceed max_bursts -> reported by fetch
 }
 
@@ -340,7 +574,15 @@ constexpr int OOK_RANK_PITCH = 264;                           // u16 entries per
 constexpr int OOK_RANK_N = 256 * OOK_RANK_PITCH;
 constexpr int OOK_RANK_BYTES = OOK_RANK_N * 2;                // 135 168
 static_assert(OOK_RANK_BYTES % 16 == 0, "table is copied as uint4");
-__host__ __device__ __forceinline__ uint32_t ook_rank_slot(uint32_t b0, uint32_t b1) { return b0 + OOK_RANK_PITCH * b1; }
+// slot of the byte pair (b0 = I, b1 = Q): with raw = b0 | b1 << 8 -- the sample's 16 bits as they sit in the capture --
+// raw + (raw >> 5) = 264 b1 + b0 + (b0 >> 5): the skewed row layout above, reached from the raw halfword with ONE LEA.HI
+// instead of two byte extractions and a multiply-add (b0 + (b0 >> 5) <= 262 < 264: injective)
+__host__ __device__ __forceinline__ uint32_t ook_rank_slot(uint32_t b0, uint32_t b1)
+{
+    const uint32_t raw = b0 | (b1 << 8);
+    return raw + (raw >> 5);
+}
+static_assert(65535 + (65535 >> 5) < OOK_RANK_N, "rank table covers every slot");
 
 // #{i : uniq[i] <= h} for ascending uniq[0..n): every lane probes one position per round
 __device__ __forceinline__ uint32_t warp_upper_bound(const float *__restrict__ uniq, uint32_t n, float h, int lane)
@@ -359,7 +601,9 @@ __device__ __forceinline__ uint32_t warp_upper_bound(const float *__restrict__ u
     return lo;
 }
 
-constexpr int KC_THREADS = 1024;             // 32 streams per CTA, one CTA per SM: 4736 warps cover 4096 streams in ONE wave
+constexpr int KC_THREADS = 1024;             // at most 32 streams per CTA, one CTA per SM (the table fills its shared memory).  The launch
+                                             // uses ceil(n_streams / n_sm) warps per CTA so that every SM gets the same number of streams
+                                             // (4096 streams: 147 CTAs of 28 warps instead of 128 CTAs of 32 with 20 SMs idle)
 
 __global__ void __launch_bounds__(KC_THREADS, 1)
 ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
@@ -403,12 +647,11 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         const uint32_t hm1 = h - 1u;                                         // rank >= h  <=>  (h - 1) - rank < 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            uint32_t a0, a1;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a0) : "r"(__byte_perm(w[i], 0, 0x4441)), "r"(2u * OOK_RANK_PITCH), "r"(rank_s));
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(__byte_perm(w[i], 0, 0x4443)), "r"(2u * OOK_RANK_PITCH), "r"(rank_s));
+            const uint32_t raw0 = w[i] & 0xffffu, raw1 = __umulhi(w[i], 65536u);        // w >> 16 on the FMA pipe
+            const uint32_t a0 = rank_s + 2u * (raw0 + (raw0 >> 5)), a1 = rank_s + 2u * (raw1 + (raw1 >> 5));
             unsigned short r0, r1;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r0) : "r"(a0 + 2u * __byte_perm(w[i], 0, 0x4440)));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r1) : "r"(a1 + 2u * __byte_perm(w[i], 0, 0x4442)));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r0) : "r"(a0));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r1) : "r"(a1));
             m = __funnelshift_l(hm1 - (uint32_t)r0, m, 1);                   // (x > max/2f32) as usize  :91
             m = __funnelshift_l(hm1 - (uint32_t)r1, m, 1);
         }
@@ -592,14 +835,32 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
     OOK_ALLOC(d_runs_dbg, n_streams * o->max_runs);
     OOK_ALLOC(d_lut, (size_t)OOK_LUT_N);
+    OOK_ALLOC(d_flut, (size_t)OOK_FLUT_N);
     OOK_ALLOC(d_rank, (size_t)OOK_RANK_N); OOK_ALLOC(d_uniq, (size_t)65536);
 #undef OOK_ALLOC
     if (e == cudaSuccess) {
         e = cudaMemsetAsync(o->d_lut, 0, OOK_LUT_BYTES, ctx->stream);           // the row padding is never read
         ook_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(o->d_lut);
         e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemsetAsync(o->d_flut, 0, OOK_FLUT_BYTES, ctx->stream);   // the row skew gaps are never read
+        if (e == cudaSuccess) {
+            ook_build_flut_kernel<<<256, 256, 0, ctx->stream>>>(o->d_flut);
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_tma_kernel<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ka2Cfg<16, 2>::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_tma_kernel<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ka2Cfg<16, 2>::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_block_tma_kernel<8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ka2Cfg<8, 4>::SMEM_BYTES);
+        if (e == cudaSuccess) {
+            cudaDriverEntryPointQueryResult qr;
+            e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &o->encode_tiled, cudaEnableDefault, &qr);
+            if (e == cudaSuccess && (qr != cudaDriverEntryPointSuccess || !o->encode_tiled)) {
+                lrc_set_error("lrc_ook_create: the driver does not export cuTensorMapEncodeTiled");
+                lrc_ook_destroy(o);
+                return LRC_ERR_UNSUPPORTED;
+            }
+        }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_RANK_BYTES);
     }
     if (e == cudaSuccess) {
@@ -638,7 +899,7 @@ extern "C" int lrc_ook_destroy(lrc_ook *o)
     cudaSetDevice(o->ctx->device);
     cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags);
     cudaFree(o->d_nbursts); cudaFree(o->d_trans); cudaFree(o->d_ntrans); cudaFree(o->d_nbits);
-    cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut);
+    cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut); cudaFree(o->d_flut);
     cudaFree(o->d_rank); cudaFree(o->d_uniq);
     delete o;
     return LRC_OK;
@@ -654,16 +915,58 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
                 "lrc_ook_decode: input and stream stride must be 16-byte aligned");
     cudaStream_t s = lrc_stream(o->ctx, stream);
     const size_t groups = ((o->n_blocks + 31) / 32) * o->n_streams;
-    size_t blocks = ceil_div(groups, (size_t)KA_WARPS);
     const size_t cap = (size_t)o->ctx->n_sm;           // one persistent CTA per SM (the table fills its shared memory)
-    if (blocks > cap) blocks = cap;
-    ook_block_kernel<<<(unsigned)blocks, KA_WARPS * 32, KA_SMEM_BYTES, s>>>(d_iq, stream_stride_bytes, o->n_streams,
-                                                                           o->n_blocks, o->d_lut, o->d_sum, o->d_max);
+    // LRC_OOK_KA: 0 = round-1 kernel (triangular table, cp.async slabs), 1 = folded table + TMA slabs 16 warps x 2 stages
+    // (default), 2 = the same with 8 warps x 4 stages, 3 = like 1 with the table skew on the ALU pipe (LEA.HI).  A/B knob; all produce
+    // identical bits.
+    static const int ka = getenv("LRC_OOK_KA") ? atoi(getenv("LRC_OOK_KA")) : 3;
+    if (ka == 0) {
+        size_t blocks = ceil_div(groups, (size_t)KA_WARPS);
+        if (blocks > cap) blocks = cap;
+        ook_block_kernel<<<(unsigned)blocks, KA_WARPS * 32, KA_SMEM_BYTES, s>>>(d_iq, stream_stride_bytes, o->n_streams,
+                                                                               o->n_blocks, o->d_lut, o->d_sum, o->d_max);
+    } else {
+        // the capture as a byte tensor [stream][block][1024]: one box = 64 bytes of 32 consecutive blocks of one stream
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        CUtensorMap tm;
+        const cuuint64_t dims[3] = {(cuuint64_t)OOK_BLOCK * 2, (cuuint64_t)o->n_blocks, (cuuint64_t)o->n_streams};
+        const cuuint64_t strides[2] = {(cuuint64_t)OOK_BLOCK * 2, (cuuint64_t)stream_stride_bytes};
+        const cuuint32_t box[3] = {KA2_SLAB_BYTES, 32, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult cr = reinterpret_cast<encode_fn>(o->encode_tiled)(
+            &tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(d_iq), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            lrc_set_error("lrc_ook_decode: cuTensorMapEncodeTiled -> CUresult %d (n_blocks %zu, n_streams %zu, stride %zu)",
+                          (int)cr, o->n_blocks, o->n_streams, stream_stride_bytes);
+            return LRC_ERR_CUDA;
+        }
+        if (ka == 2) {
+            size_t blocks = ceil_div(groups, (size_t)8);
+            if (blocks > cap) blocks = cap;
+            ook_block_tma_kernel<8, 4, true><<<(unsigned)blocks, 8 * 32, Ka2Cfg<8, 4>::SMEM_BYTES, s>>>(
+                tm, o->n_streams, o->n_blocks, o->d_flut, o->d_sum, o->d_max);
+        } else {
+            size_t blocks = ceil_div(groups, (size_t)16);
+            if (blocks > cap) blocks = cap;
+            if (ka == 3)
+                ook_block_tma_kernel<16, 2, false><<<(unsigned)blocks, 16 * 32, Ka2Cfg<16, 2>::SMEM_BYTES, s>>>(
+                    tm, o->n_streams, o->n_blocks, o->d_flut, o->d_sum, o->d_max);
+            else
+                ook_block_tma_kernel<16, 2, true><<<(unsigned)blocks, 16 * 32, Ka2Cfg<16, 2>::SMEM_BYTES, s>>>(
+                    tm, o->n_streams, o->n_blocks, o->d_flut, o->d_sum, o->d_max);
+        }
+    }
     LRC_CUDA(cudaGetLastError());
-    ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_THREADS), KB_THREADS, 0, s>>>(
+    ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_STREAMS), KB_THREADS, 0, s>>>(
         o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
     LRC_CUDA(cudaGetLastError());
-    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams * 32, (size_t)KC_THREADS), KC_THREADS, OOK_RANK_BYTES, s>>>(
+    size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
+    if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
+    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
         d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
         o->d_uniq, o->n_uniq, o->d_bflags, o->d_trans, o->d_ntrans, o->d_nbits);
     LRC_CUDA(cudaGetLastError());
