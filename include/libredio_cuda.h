@@ -175,6 +175,10 @@ int    lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, int decim,
                         lrc_chain **chain);
 int    lrc_chain_destroy(lrc_chain *chain);
 size_t lrc_chain_frames(const lrc_chain *chain, size_t n_in);       /* whole frames in n_in samples */
+/* which kernel the plan runs: 0 = unfused (FIR kernel -> HBM -> PSD kernel), 1 = the fused BASELINE instance
+ * (64 taps / 10 / 1024, cf32 and u8 input), 2 = a fused generic instance (ntaps <= 128, decim in {4,5,8,10,16},
+ * nfft in {512,1024,2048}, tile fits shared memory).  Results are the same chain either way (FIR to float rounding). */
+int    lrc_chain_kind(const lrc_chain *chain);
 int    lrc_chain_run(lrc_chain *chain, const float *d_in, size_t n_in, size_t k_avg, float *d_rows,
                      size_t *n_rows, void *stream);
 /* same with rtlsdr u8 I,Q on the DEVICE (2 bytes per sample; rtlsdr::data_to_samples, rtlsdr.rs:160-162, folded into the

@@ -273,6 +273,11 @@ class Chain:
     def frames(self, n_in: int) -> int:
         return int(self.ctx.lib.lrc_chain_frames(self.h, n_in))
 
+    @property
+    def kind(self) -> int:
+        """0 = unfused kernels, 1 = fused BASELINE instance, 2 = fused generic instance (lrc_chain_kind)"""
+        return int(self.ctx.lib.lrc_chain_kind(self.h))
+
     def run(self, x: torch.Tensor, k_avg: int, out: torch.Tensor | None = None) -> torch.Tensor:
         assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous() and x.dim() == 1
         rows = self.frames(x.numel()) // k_avg

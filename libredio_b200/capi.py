@@ -81,6 +81,7 @@ SIGNATURES = {
     "lrc_chain_create": (_i, [_vp, _fp, _i, _i, _i, _i, _pp]),
     "lrc_chain_destroy": (_i, [_vp]),
     "lrc_chain_frames": (_sz, [_vp, _sz]),
+    "lrc_chain_kind": (_i, [_vp]),
     "lrc_chain_run": (_i, [_vp, _fp, _sz, _sz, _fp, _szp, _vp]),
     "lrc_chain_run_u8": (_i, [_vp, _u8p, _sz, _sz, _fp, _szp, _vp]),
     "lrc_chain_run_host": (_i, [_vp, _fp, _sz, _sz, _fp, _szp]),

@@ -17,6 +17,7 @@
 #include "fir_core.cuh"
 #include "fft_core.cuh"
 #include "unpack.cuh"
+#include "chain_generic.cuh"
 #include <vector>
 #include <cmath>
 
@@ -32,7 +33,8 @@ int    lrc_psd_reduce(const float *d_partial, float *d_rows, int nfft, size_t ip
 struct lrc_chain {
     lrc_ctx *ctx;
     int      ntaps, decim, nfft, log2n, window;
-    bool     fused;
+    bool     fused;            // the BASELINE instance chain_kernel<64,10,10,7> (cf32 and u8 input)
+    bool     fused_generic;    // an instance of chain_gen_kernel (chain_generic.cuh): ntaps <= 128, decim in {4,5,8,10,16}, nfft in {512,1024,2048}
     std::vector<float> taps;
     float2  *d_tw;
     float   *d_win;
@@ -251,6 +253,17 @@ extern "C" int lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, in
     c->ctx = ctx; c->ntaps = ntaps; c->decim = decim; c->nfft = nfft; c->log2n = l2; c->window = window;
     c->taps.assign(h_taps, h_taps + ntaps);
     c->fused = (ntaps == 64 && decim == 10 && nfft == 1024);
+    c->fused_generic = false;
+    if (!c->fused && !getenv("LRC_CHAIN_NO_GENERIC")) {     // A/B knob: LRC_CHAIN_NO_GENERIC=1 forces the unfused path
+        switch (decim) {
+            case 4:  c->fused_generic = lrc_chaing_has_d4(ntaps, l2); break;
+            case 5:  c->fused_generic = lrc_chaing_has_d5(ntaps, l2); break;
+            case 8:  c->fused_generic = lrc_chaing_has_d8(ntaps, l2); break;
+            case 10: c->fused_generic = lrc_chaing_has_d10(ntaps, l2); break;
+            case 16: c->fused_generic = lrc_chaing_has_d16(ntaps, l2); break;
+            default: break;
+        }
+    }
     c->d_tw = nullptr; c->d_win = nullptr; c->d_partial = nullptr; c->partial_cap = 0;
     c->fir = nullptr; c->psd = nullptr; c->d_tmp = nullptr; c->tmp_cap = 0;
     c->d_ring[0] = c->d_ring[1] = nullptr; c->ring_cap = 0; c->d_rows = nullptr; c->rows_cap = 0;
@@ -300,6 +313,12 @@ extern "C" size_t lrc_chain_frames(const lrc_chain *c, size_t n_in)
     return (n_in - tile_in) / ((size_t)c->nfft * c->decim) + 1;
 }
 
+extern "C" int lrc_chain_kind(const lrc_chain *c)
+{
+    if (!c) return 0;
+    return c->fused ? 1 : (c->fused_generic ? 2 : 0);
+}
+
 template <bool IS_U8>
 static int chain_launch_fused(lrc_chain *c, const void *d_in, size_t k_local, size_t fpi, size_t ipr, size_t n_items, cudaStream_t s)
 {
@@ -339,6 +358,23 @@ static int chain_launch(lrc_chain *c, const void *d_in_any, int input_is_u8, siz
         return lrc_psd_reduce(c->d_partial, d_rows, c->nfft, ipr, rows_local, scale, accumulate, s);
     }
     LRC_REQUIRE(!input_is_u8, LRC_ERR_INVALID, "chain_launch: u8 input without a fused instance");
+    if (c->fused_generic) {
+        chaing::Args a;
+        a.in = (const float2 *)d_in_any; a.tw = c->d_tw; a.win = c->d_win; a.taps = c->taps.data(); a.partial = c->d_partial;
+        a.k_avg = k_local; a.fpi = fpi; a.ipr = ipr; a.n_items = n_items; a.ntaps = c->ntaps; a.n_sm = c->ctx->n_sm; a.stream = s;
+        int grc = -1;
+        switch (c->decim) {
+            case 4:  grc = lrc_chaing_launch_d4(a, c->log2n); break;
+            case 5:  grc = lrc_chaing_launch_d5(a, c->log2n); break;
+            case 8:  grc = lrc_chaing_launch_d8(a, c->log2n); break;
+            case 10: grc = lrc_chaing_launch_d10(a, c->log2n); break;
+            case 16: grc = lrc_chaing_launch_d16(a, c->log2n); break;
+            default: break;
+        }
+        if (grc > 0) return grc;
+        if (grc == 0) return lrc_psd_reduce(c->d_partial, d_rows, c->nfft, ipr, rows_local, scale, accumulate, s);
+        // grc < 0 cannot happen for a plan whose fused_generic is set; fall through to the unfused kernels
+    }
     // unfused fallback: FIR into a scratch signal, then the PSD kernel
     const size_t n_frames = rows_local * k_local;
     const size_t n_dec = n_frames * (size_t)c->nfft;

@@ -89,6 +89,7 @@ extern "C" {
                             chain: *mut *mut lrc_chain) -> c_int;
     pub fn lrc_chain_destroy(chain: *mut lrc_chain) -> c_int;
     pub fn lrc_chain_frames(chain: *const lrc_chain, n_in: size_t) -> size_t;
+    pub fn lrc_chain_kind(chain: *const lrc_chain) -> c_int;
     pub fn lrc_chain_run(chain: *mut lrc_chain, d_in: *const c_float, n_in: size_t, k_avg: size_t, d_rows: *mut c_float,
                          n_rows: *mut size_t, stream: *mut c_void) -> c_int;
     pub fn lrc_chain_run_u8(chain: *mut lrc_chain, d_iq: *const u8, n_in: size_t, k_avg: size_t, d_rows: *mut c_float,

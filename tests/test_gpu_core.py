@@ -436,6 +436,68 @@ def test_chain_generic_shape_falls_back_to_unfused(ctx):
     ch.close()
 
 
+# the generic fused instances (chain_generic.cuh): ntaps <= 128 (run-time, zero-padded to 64 / 128), decim in {4,5,8,10,16},
+# nfft in {512,1024,2048}.  Odd ntaps exercise the hand-copied last sample of a tile, decim 4/8/16 the padded chunk layout.
+GENERIC_SHAPES = [(33, 4, 512), (64, 4, 1024), (128, 4, 2048), (17, 5, 512), (64, 5, 1024), (97, 5, 2048),
+                  (64, 8, 512), (128, 8, 1024), (31, 8, 2048), (48, 10, 512), (63, 10, 1024), (128, 10, 1024),
+                  (64, 10, 2048), (5, 16, 512), (64, 16, 1024), (127, 16, 1024)]
+
+
+@pytest.mark.parametrize("ntaps,decim,nfft", GENERIC_SHAPES)
+def test_chain_generic_shape_runs_a_fused_instance(ctx, ntaps, decim, nfft):
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(ntaps * 1000 + decim * 10 + nfft)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    frames, k = 21, 3
+    n = (frames - 1) * nfft * decim + (nfft - 1) * decim + ntaps          # exactly what lrc_chain_frames asks for
+    x = synth.cf32_noise_tones(n, seed=ntaps + decim)
+    ch = blocks.Chain(ctx, taps, decim, nfft)
+    assert ch.kind == 2, "no fused generic instance for this shape"
+    assert ch.frames(n) == frames and ch.frames(n - 1) == frames - 1
+    # the input ends exactly where the last frame ends: a kernel that reads one sample further faults or reads the guard
+    xd = torch.full((n + 64,), float("nan"), dtype=torch.complex64, device=ctx.tdev)
+    xd[:n] = dev(x, ctx)
+    got = ch.run(xd[:n], k).cpu().numpy()
+    ref = chain_ref(x, taps, decim, nfft, k)
+    assert got.shape == ref.shape == (frames // k, nfft)
+    assert np.isfinite(got).all()
+    assert np.max(np.abs(got - ref)) <= TOL * np.sqrt(np.mean(ref ** 2))
+    ch.close()
+
+
+@pytest.mark.parametrize("ntaps,decim,nfft", [(64, 4, 1024), (100, 8, 2048), (64, 16, 1024), (33, 5, 512)])
+def test_chain_generic_fused_equals_unfused_kernels_at_size(ctx, ntaps, decim, nfft, monkeypatch):
+    """many CTAs, many items per CTA, rows of several work items: fused generic == FIR kernel -> PSD kernel to float rounding"""
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(7)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    frames, k = 1500, 50
+    n = (frames - 1) * nfft * decim + (nfft - 1) * decim + ntaps
+    g = torch.Generator(device=ctx.tdev).manual_seed(3)
+    x = torch.view_as_complex(torch.randn(n, 2, device=ctx.tdev, generator=g))
+    fused = blocks.Chain(ctx, taps, decim, nfft)
+    monkeypatch.setenv("LRC_CHAIN_NO_GENERIC", "1")
+    unfused = blocks.Chain(ctx, taps, decim, nfft)
+    monkeypatch.delenv("LRC_CHAIN_NO_GENERIC")
+    assert fused.kind == 2 and unfused.kind == 0
+    a, b = fused.run(x, k), unfused.run(x, k)
+    assert a.shape == b.shape == (frames // k, nfft)
+    assert (a - b).abs().max().item() <= 1e-5 * b.pow(2).mean().sqrt().item()
+    fused.close(); unfused.close()
+
+
+def test_chain_shapes_without_an_instance_stay_unfused(ctx):
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    for ntaps, decim, nfft in [(64, 16, 2048), (64, 3, 1024), (64, 10, 256), (129, 10, 1024)]:
+        ch = blocks.Chain(ctx, np.resize(taps, ntaps), decim, nfft)
+        assert ch.kind == 0
+        ch.close()
+    ch = blocks.Chain(ctx, taps, 10, 1024)
+    assert ch.kind == 1
+    ch.close()
+
+
 @pytest.mark.parametrize("frames,k", [(100, 10), (900, 900), (1000, 64), (37, 1)])
 def test_chain_host_ring_matches_device_path(ctx, frames, k):
     """the HOST-buffer entry point (pinned ring, chunked H2D overlapped with the kernel) must give the

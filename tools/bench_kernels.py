@@ -204,6 +204,36 @@ def main():
             ff.close()
         del x
 
+    if want("chaing"):
+        # generic fused chain instances (chain_generic.cuh) beside the unfused FIR -> HBM -> PSD path, ~2.7 GB of cf32 each
+        os_env = os.environ
+        for ntaps, decim, nfft in [(64, 10, 1024), (64, 4, 1024), (128, 4, 1024), (64, 5, 1024), (64, 8, 1024), (128, 8, 2048),
+                                   (128, 10, 1024), (64, 10, 2048), (64, 10, 512), (64, 16, 1024), (64, 16, 512), (64, 4, 512)]:
+            tp = synth.lpf_taps(ntaps, 0.4 / decim)
+            k = 64
+            frames = max(k, ((1 << 25) // q // (nfft * decim)) // k * k * 10)
+            n = (frames - 1) * nfft * decim + (nfft - 1) * decim + ntaps
+            x = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
+            res = {}
+            for label, env in (("fused", None), ("unfused", "1")):
+                if env: os_env["LRC_CHAIN_NO_GENERIC"] = env
+                ch = blocks.Chain(ctx, tp, decim, nfft)
+                os_env.pop("LRC_CHAIN_NO_GENERIC", None)
+                if label == "unfused" and (ntaps, decim, nfft) == (64, 10, 1024):
+                    ch.close(); continue
+                out = torch.empty((frames // k, nfft), dtype=torch.float32, device=dev)
+                ms, _ = timeit(lambda: ch.run(x, k, out))
+                res[label] = (ms, ch.kind)
+                ch.close()
+            ms, kind = res["fused"]
+            extra = {"kind": kind, "flop_per_sample": 2.0 * 2 * ntaps / decim + 55.0 / decim}
+            extra["TFLOP/s"] = n * extra["flop_per_sample"] / (ms * 1e-3) / 1e12
+            if "unfused" in res:
+                extra["unfused_ms"] = res["unfused"][0]
+                extra["speedup_vs_unfused"] = res["unfused"][0] / ms
+            report(f"chain {ntaps}/{decim}/{nfft} fused (kind {kind})", n, n * 8.0 + frames // k * nfft * 4, ms, extra)
+            del x
+
     if want("ook"):
         n_streams, n_blocks = 4096 // q, 500
         caps = [synth.ook_capture_u8(n_blocks, seed=4 + s, n_packets=2)[0] for s in range(32)]
