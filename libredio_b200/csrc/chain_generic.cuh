@@ -17,8 +17,8 @@
 //    offsets after unrolling.  FIR thread t issues the bulk copy of chunk t, so the 70-300 copies of a tile are issued
 //    in parallel, all completing on one mbarrier.
 //
-//  * N in {512, 1024, 2048}; shapes whose tile does not fit 227 KB (N DECIM > ~25 k samples) have no instance and run
-//    unfused (FIR kernel -> HBM -> PSD kernel).
+//  * N in {512, 1024, 2048}; a frame is produced in 1, 2 or 4 sub-tiles (GenCfg below), so every one of the 30 shapes fits
+//    shared memory and the ones that only fit one CTA per SM overlap their own loads through a two-stage tile ring.
 #pragma once
 #include "fir_core.cuh"
 #include "fft_core.cuh"
@@ -55,34 +55,58 @@ struct GenTile {
     }
 };
 
-template <int NTAPS, int DECIM, int LOG2N, int R>
-struct GenCfg {
+// sub-tiling: a frame's N outputs are produced in SUBT sub-tiles of NS = N / SUBT outputs, each from its own TMA tile.
+//   SUBT = 1, one tile buffer : the whole frame from one tile (the BASELINE instance's scheme; with two or more CTAs per SM the
+//                               TMA of one CTA overlaps the arithmetic of the others);
+//   SUBT = 2 or 4, two buffers: a two-stage ring of half- or quarter-frame tiles: sub-tile g + 2 is on its way while g + 1 is
+//                               filtered.  This is how 2048 x 16 (a 262 KB frame tile) fits at all.
+template <int NTAPS, int DECIM, int LOG2N, int R, int SUBT_>
+struct GenLayout {
     using Tile = GenTile<NTAPS, DECIM, R>;
     using FFT = CtaFFT<LOG2N, false>;
-    static constexpr int N = 1 << LOG2N;
-    static constexpr int FRAME_ADV = N * DECIM;
-    static constexpr int TILE_IN_MAX = (N - 1) * DECIM + NTAPS;
-    static constexpr int NFIR = (N + R - 1) / R;
-    static constexpr int NFIR_T = (NFIR + 31) / 32 * 32;
-    static constexpr int NFFT_T = FFT::T;
-    static constexpr int NT = NFIR_T + NFFT_T;
+    static constexpr int N = 1 << LOG2N, SUBT = SUBT_, NBUF = SUBT == 1 ? 1 : 2;
+    static constexpr int NS = N / SUBT;                                  // outputs per sub-tile
+    static constexpr int TILE_IN_MAX = (NS - 1) * DECIM + NTAPS;
+    static constexpr int NFIR = (NS + R - 1) / R;
     static constexpr int N_CHUNKS_MAX = (TILE_IN_MAX + Tile::STEP - 1) / Tile::STEP;
     static constexpr int WIN_END = (NFIR - 1) * Tile::PITCH + Tile::off(Tile::WINL - 1) + 16;   // last byte a FIR thread reads
     static constexpr int CHUNK_END = N_CHUNKS_MAX * Tile::PITCH;
     static constexpr int TILE_BYTES = ((WIN_END > CHUNK_END ? WIN_END : CHUNK_END) + 127) / 128 * 128;
-    static constexpr int OFF_HAND = TILE_BYTES;
+    static constexpr int SMEM_BYTES = NBUF * TILE_BYTES + 2 * FFT::SMEM_CPX * 8 + 32;
+};
+
+template <int NTAPS, int DECIM, int LOG2N, int R>
+struct GenCfg {
+    using L1 = GenLayout<NTAPS, DECIM, LOG2N, R, 1>;
+    using L2 = GenLayout<NTAPS, DECIM, LOG2N, R, 2>;
+    // Measured (profiles/r2_p_chain_generic.jsonl): for shapes that fit ONE CTA per SM the two-stage ring with half-frame
+    // sub-tiles is slower than the whole-frame tile (64/16/1024: 0.71 vs 0.89 of HBM, 64/10/2048: 0.63 vs 0.74) -- half the
+    // producer threads, and only one 66-82 KB sub-tile in flight while the other is filtered, where the whole-frame load
+    // keeps 130-160 KB in flight.  So sub-tiling is used only where the whole-frame tile does not fit at all (2048 x 16).
+    static constexpr int SUBT = (L1::SMEM_BYTES + 1024 <= 227 * 1024) ? 1 : (L2::SMEM_BYTES <= 227 * 1024 ? 2 : 4);
+    using L = GenLayout<NTAPS, DECIM, LOG2N, R, SUBT>;
+    using Tile = typename L::Tile;
+    using FFT = typename L::FFT;
+    static constexpr int N = L::N, NS = L::NS, NBUF = L::NBUF;
+    static constexpr int FRAME_ADV = N * DECIM;
+    static constexpr int SUB_ADV = NS * DECIM;                           // input samples between sub-tiles
+    static constexpr int NFIR = L::NFIR;
+    static constexpr int NFIR_T = (NFIR + 31) / 32 * 32;
+    static constexpr int NFFT_T = FFT::T;
+    static constexpr int NT = NFIR_T + NFFT_T;
+    static constexpr int TILE_BYTES = L::TILE_BYTES;
+    static constexpr int OFF_HAND = NBUF * TILE_BYTES;
     static constexpr int OFF_XCHG = OFF_HAND + FFT::SMEM_CPX * 8;
     static constexpr int OFF_BAR = OFF_XCHG + FFT::SMEM_CPX * 8;
-    static constexpr int SMEM_BYTES = OFF_BAR + 16;
+    static constexpr int SMEM_BYTES = OFF_BAR + 32;
     static constexpr bool FITS = SMEM_BYTES <= 227 * 1024 && NT <= 1024;
-    // two CTAs per SM whenever shared memory allows it (the register budget then follows from the launch bounds): the TMA
-    // of one CTA overlaps the arithmetic of the other, as in the BASELINE instance
-    // (at 128 registers per thread, which the 16-point-per-thread FFT needs)
+    // as many CTAs per SM as shared memory and a 128-register thread (the 16-point-per-thread FFT needs that) allow
     static constexpr int BY_SMEM = (227 * 1024) / (SMEM_BYTES + 1024), BY_REGS = 65536 / (NT * 128);
     static constexpr int MIN_CTAS_RAW = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
     static constexpr int MIN_CTAS = MIN_CTAS_RAW < 1 ? 1 : (MIN_CTAS_RAW > 8 ? 8 : MIN_CTAS_RAW);
-    static_assert((FRAME_ADV * 8) % 16 == 0 && (Tile::STEP * 8) % 16 == 0, "TMA alignment");
+    static_assert((FRAME_ADV * 8) % 16 == 0 && (SUB_ADV * 8) % 16 == 0 && (Tile::STEP * 8) % 16 == 0, "TMA alignment");
     static_assert(NFFT_T % 32 == 0, "FFT threads must be whole warps");
+    static_assert(N % SUBT == 0, "whole sub-tiles");
 };
 
 enum { BAR_FULL = 1, BAR_EMPTY = 2, BAR_TILE = 3, BAR_FFT = 4 };
@@ -96,17 +120,20 @@ chain_gen_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, c
     using Cfg = GenCfg<NTAPS, DECIM, LOG2N, R>;
     using Tile = typename Cfg::Tile;
     using FFT = typename Cfg::FFT;
-    constexpr int N = Cfg::N, E = FFT::E, T = FFT::T;
+    constexpr int N = Cfg::N, E = FFT::E, T = FFT::T, SUBT = Cfg::SUBT, NBUF = Cfg::NBUF, NS = Cfg::NS;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *tile = smem;
     float2 *hand = reinterpret_cast<float2 *>(smem + Cfg::OFF_HAND);
     float2 *xchg = reinterpret_cast<float2 *>(smem + Cfg::OFF_XCHG);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BAR);
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    // the padded taps (ntaps_rt..NTAPS-1 are zero) must only ever meet finite values: zero the tile once
-    for (int i = tid; i < Cfg::TILE_BYTES / 16; i += Cfg::NT) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_proxy_async();                                   // ... before the TMA (async proxy) writes over it
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) mbar_init(bar + i, 1);
+        mbar_fence_init();
+    }
+    // the padded taps (ntaps_rt..NTAPS-1 are zero) must only ever meet finite values: zero the tiles once
+    for (int i = tid; i < NBUF * Cfg::TILE_BYTES / 16; i += Cfg::NT) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();                                   // ... before the TMA (async proxy) writes over them
     __syncthreads();
     if ((size_t)blockIdx.x >= n_items) return;
 
@@ -119,58 +146,71 @@ chain_gen_kernel(const float2 *__restrict__ in, const float2 *__restrict__ tw, c
 
     if (tid < Cfg::NFIR_T) {
         // ================= FIR producers =================
-        const int tile_in = (N - 1) * DECIM + ntaps_rt;                 // samples of a frame that exist in the input
+        const int tile_in = (NS - 1) * DECIM + ntaps_rt;                // samples of a sub-tile that exist in the input
         const int n_chunks = (tile_in + Tile::STEP - 1) / Tile::STEP;
         const int tma_samples = tile_in & ~1;                           // bulk copies move whole 16-byte units ...
-        uint32_t phase = 0;
-        bool first = true;
-        size_t item = blockIdx.x, f0, f1;
-        item_range(item, f0, f1);
-        size_t f = f0;
-        auto load_frame = [&](size_t fr) {                              // every producer thread: its chunk(s)
-            const float2 *src = in + fr * (size_t)Cfg::FRAME_ADV;
-            if (tid == 0) mbar_expect_tx(bar, (uint32_t)tma_samples * 8u);
-            for (int c = tid; c < n_chunks; c += Cfg::NFIR_T) {
-                const int s0 = c * Tile::STEP;
+        // the CTA's schedule as a cursor over (item, frame, sub-tile); two cursors walk it: `cur` (being filtered) and
+        // `ld` (being loaded, NBUF sub-tiles ahead)
+        struct Cursor { size_t item, f, f1; int s; bool ok; };
+        auto start = [&]() { Cursor c; c.item = blockIdx.x; size_t f0; item_range(c.item, f0, c.f1); c.f = f0; c.s = 0; c.ok = true; return c; };
+        auto advance = [&](Cursor &c) {
+            if (++c.s < SUBT) return;
+            c.s = 0;
+            if (++c.f < c.f1) return;
+            c.item += gridDim.x;
+            if (c.item < n_items) { size_t f0; item_range(c.item, f0, c.f1); c.f = f0; }
+            else c.ok = false;
+        };
+        auto load_sub = [&](const Cursor &c, int buf) {                 // every producer thread: its chunk(s)
+            const float2 *src = in + c.f * (size_t)Cfg::FRAME_ADV + (size_t)c.s * Cfg::SUB_ADV;
+            uint8_t *tile = smem + (size_t)buf * Cfg::TILE_BYTES;
+            if (tid == 0) mbar_expect_tx(bar + buf, (uint32_t)tma_samples * 8u);
+            for (int ch = tid; ch < n_chunks; ch += Cfg::NFIR_T) {
+                const int s0 = ch * Tile::STEP;
                 int ns = tma_samples - s0;
                 if (ns > Tile::STEP) ns = Tile::STEP;
-                if (ns > 0) tma_load_1d_evict_first(tile + (size_t)c * Tile::PITCH, src + s0, (uint32_t)ns * 8u, bar);
-                // ... and an odd last sample goes by hand (its owner stores it before it arrives on BAR_TILE)
+                if (ns > 0) tma_load_1d_evict_first(tile + (size_t)ch * Tile::PITCH, src + s0, (uint32_t)ns * 8u, bar + buf);
+                // ... and an odd last sample goes by hand; a BAR_TILE barrier lies between this store and the sub-tile's use
                 if ((tile_in & 1) && s0 + Tile::STEP >= tile_in && s0 < tile_in)
-                    *reinterpret_cast<float2 *>(tile + (size_t)c * Tile::PITCH + (size_t)(tile_in - 1 - s0) * 8) = __ldg(src + tile_in - 1);
+                    *reinterpret_cast<float2 *>(tile + (size_t)ch * Tile::PITCH + (size_t)(tile_in - 1 - s0) * 8) = __ldg(src + tile_in - 1);
             }
         };
-        load_frame(f);
-        // the hand-copied sample must be visible to the thread whose window holds it
-        named_bar_sync(BAR_TILE, Cfg::NFIR_T);
+        Cursor cur = start(), ld = cur;
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i)
+            if (ld.ok) { load_sub(ld, i); advance(ld); }
+        named_bar_sync(BAR_TILE, Cfg::NFIR_T);                          // hand-copied samples of the first sub-tiles
+        uint32_t g = 0;                                                  // sub-tiles done by this CTA
+        bool first = true;
         while (true) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            const int buf = (int)(g % NBUF);
+            mbar_wait(bar + buf, (g / NBUF) & 1u);
             float2 acc[R];
-            if (tid < Cfg::NFIR) Tile::run(tile + (size_t)tid * Tile::PITCH, taps, acc);
-            size_t nf = f + 1, nitem = item, nf1 = f1;
-            if (nf == f1) {
-                nitem = item + gridDim.x;
-                if (nitem < n_items) item_range(nitem, nf, nf1);
-            }
-            const bool has_next = nitem < n_items;
-            // every FIR thread is done with the tile -> the chunks of the next frame
+            if (tid < Cfg::NFIR) Tile::run(smem + (size_t)buf * Cfg::TILE_BYTES + (size_t)tid * Tile::PITCH, taps, acc);
+            // every FIR thread is done with the tile -> the chunks of the sub-tile NBUF ahead go into it
             named_bar_sync(BAR_TILE, Cfg::NFIR_T);
-            if (has_next) load_frame(nf);
-            if (!first) named_bar_sync(BAR_EMPTY, Cfg::NT);
-            first = false;
+            if (ld.ok) { load_sub(ld, buf); advance(ld); }
+            // a new frame starts: is the hand-over buffer free? (the FFT warps arrive on EMPTY once they hold the previous frame)
+            if (cur.s == 0) {
+                if (!first) named_bar_sync(BAR_EMPTY, Cfg::NT);
+                first = false;
+            }
             if (tid < Cfg::NFIR) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int o = tid * R + r;
-                    if (o < N) hand[FFT::pad(o)] = acc[r];
+                    if (o < NS) hand[FFT::pad(cur.s * NS + o)] = acc[r];
                 }
             }
-            __threadfence_block();
-            named_bar_arrive(BAR_FULL, Cfg::NT);
-            if (!has_next) break;
-            if (tile_in & 1) named_bar_sync(BAR_TILE, Cfg::NFIR_T);    // the hand-copied last sample (see load_frame)
-            item = nitem; f = nf; f1 = nf1;
+            const bool frame_done = cur.s == SUBT - 1;
+            advance(cur);
+            if (frame_done) {
+                __threadfence_block();
+                named_bar_arrive(BAR_FULL, Cfg::NT);
+            }
+            if (!cur.ok) break;
+            if (NBUF == 1 && (tile_in & 1)) named_bar_sync(BAR_TILE, Cfg::NFIR_T);   // the hand-copied sample, single buffer
+            ++g;
         }
     } else {
         // ================= FFT consumers =================

@@ -440,7 +440,7 @@ def test_chain_generic_shape_falls_back_to_unfused(ctx):
 # nfft in {512,1024,2048}.  Odd ntaps exercise the hand-copied last sample of a tile, decim 4/8/16 the padded chunk layout.
 GENERIC_SHAPES = [(33, 4, 512), (64, 4, 1024), (128, 4, 2048), (17, 5, 512), (64, 5, 1024), (97, 5, 2048),
                   (64, 8, 512), (128, 8, 1024), (31, 8, 2048), (48, 10, 512), (63, 10, 1024), (128, 10, 1024),
-                  (64, 10, 2048), (5, 16, 512), (64, 16, 1024), (127, 16, 1024)]
+                  (64, 10, 2048), (5, 16, 512), (64, 16, 1024), (127, 16, 1024), (64, 16, 2048), (128, 16, 2048), (77, 10, 2048)]
 
 
 @pytest.mark.parametrize("ntaps,decim,nfft", GENERIC_SHAPES)
@@ -465,7 +465,7 @@ def test_chain_generic_shape_runs_a_fused_instance(ctx, ntaps, decim, nfft):
     ch.close()
 
 
-@pytest.mark.parametrize("ntaps,decim,nfft", [(64, 4, 1024), (100, 8, 2048), (64, 16, 1024), (33, 5, 512)])
+@pytest.mark.parametrize("ntaps,decim,nfft", [(64, 4, 1024), (100, 8, 2048), (64, 16, 1024), (33, 5, 512), (64, 16, 2048), (64, 10, 2048)])
 def test_chain_generic_fused_equals_unfused_kernels_at_size(ctx, ntaps, decim, nfft, monkeypatch):
     """many CTAs, many items per CTA, rows of several work items: fused generic == FIR kernel -> PSD kernel to float rounding"""
     from libredio_b200 import blocks
@@ -489,7 +489,7 @@ def test_chain_generic_fused_equals_unfused_kernels_at_size(ctx, ntaps, decim, n
 def test_chain_shapes_without_an_instance_stay_unfused(ctx):
     from libredio_b200 import blocks
     taps = synth.lpf_taps(64, 0.04)
-    for ntaps, decim, nfft in [(64, 16, 2048), (64, 3, 1024), (64, 10, 256), (129, 10, 1024)]:
+    for ntaps, decim, nfft in [(64, 3, 1024), (64, 10, 256), (129, 10, 1024), (64, 10, 4096)]:
         ch = blocks.Chain(ctx, np.resize(taps, ntaps), decim, nfft)
         assert ch.kind == 0
         ch.close()

@@ -208,7 +208,7 @@ def main():
         # generic fused chain instances (chain_generic.cuh) beside the unfused FIR -> HBM -> PSD path, ~2.7 GB of cf32 each
         os_env = os.environ
         for ntaps, decim, nfft in [(64, 10, 1024), (64, 4, 1024), (128, 4, 1024), (64, 5, 1024), (64, 8, 1024), (128, 8, 2048),
-                                   (128, 10, 1024), (64, 10, 2048), (64, 10, 512), (64, 16, 1024), (64, 16, 512), (64, 4, 512)]:
+                                   (128, 10, 1024), (64, 10, 2048), (64, 10, 512), (64, 16, 1024), (64, 16, 512), (64, 4, 512), (64, 16, 2048), (64, 5, 2048)]:
             tp = synth.lpf_taps(ntaps, 0.4 / decim)
             k = 64
             frames = max(k, ((1 << 25) // q // (nfft * decim)) // k * k * 10)
