@@ -40,13 +40,15 @@ struct RsTaps { float g[NT_]; };
 // The window loop, unrolled by template recursion (a `#pragma unroll` over ~175 iterations of packed builtins is
 // not honoured by the compiler, and thousands of inline-asm statements in one block take minutes to compile):
 // step J loads samples J, J+1 of both tiles with one LDS.128 and feeds the accumulators they belong to.
-template <int M, int R, int TPP, int J, int JEND>
+// PADP pairs of padding follow every STEPP pairs of the buffer (STEPP = a thread's window advance, so a window starts
+// at a multiple of STEPP and sample J sits at J + PADP (J / STEPP) from it: compile-time offsets).  PADP = 0: dense.
+template <int M, int R, int TPP, int J, int JEND, int STEPP = 1 << 30, int PADP = 0>
 struct RsDec2Steps {
     template <class Taps>
     __device__ __forceinline__ static void run(const float2 *sx, const Taps &taps, float2 *acc)
     {
         if constexpr (J < JEND) {
-            const float4 x = *reinterpret_cast<const float4 *>(sx + J);
+            const float4 x = *reinterpret_cast<const float4 *>(sx + J + PADP * (J / STEPP));
             const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -54,8 +56,7 @@ struct RsDec2Steps {
                 if (k0 >= 0 && k0 < TPP) acc[r] = __ffma2_rn(x0, make_float2(taps.g[k0], taps.g[k0]), acc[r]);
                 if (k1 >= 0 && k1 < TPP) acc[r] = __ffma2_rn(x1, make_float2(taps.g[k1], taps.g[k1]), acc[r]);
             }
-            RsDec2Steps<M, R, TPP, J + 2, JEND>::run(sx, taps, acc);
+            RsDec2Steps<M, R, TPP, J + 2, JEND, STEPP, PADP>::run(sx, taps, acc);
         }
     }
 };
-

@@ -32,6 +32,10 @@ constexpr int RF = 5;                                     // FIR outputs per thr
 constexpr int ROUND_Z = RF * HALF;                        // 640 baseband samples per channel and round
 constexpr int ROUNDS = 4;
 constexpr int TILE_D = ROUND_Z * ROUNDS;                  // 2560 new discriminator samples per tile
+// Measured and rejected (round 2, profiles/r2_r_fmrx_r2x8_ncu.txt): the resampler phase with R2 = 8 outputs on 64 threads and a
+// padded ring (RsDec2Steps' STEPP/PADP form) -- 3.7x fewer shared-memory wavefronts in the phase, but six of the CTA's eight warps
+// then wait at the barrier behind two (barrier stall 0.59 -> 3.2 per issue, instruction-fetch stalls on the 3 k-instruction
+// straight-line block): 0.382 ms against 0.321 ms.  The kernel is issue-bound by its FIR phase (158 M of 218 M warp-instructions).
 constexpr int R2 = 2;                                     // audio outputs per thread and tile (per channel)
 constexpr int TILE_A = TILE_D / M;                        // 512
 static_assert(TILE_A == R2 * NT, "every thread resamples");
