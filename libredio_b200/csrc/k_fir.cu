@@ -4,9 +4,14 @@
 //
 // Two code paths, same arithmetic order (j ascending, fused multiply-add):
 //   * fir_tile_kernel<64,10,...>: TMA-staged shared-memory tile, register-blocked (fir_core.cuh)
-//   * fir_generic_kernel: any (ntaps, decim), one thread per output straight from global/L1
+//   * fir_gentile_kernel (k_fir_gentile.cu): cf32, ntaps <= 128, decim in {4,5,8,10,16}: padded-chunk TMA tile, packed FFMA2
+//   * fir_generic_kernel: any other (ntaps, decim) and u8 input of those, one thread per output straight from global/L1
 #include "fir_core.cuh"
 #include <vector>
+
+bool lrc_fir_gentile_has(int ntaps, int decim);
+int  lrc_fir_gentile_launch(int n_sm, const float *h_taps, int ntaps, int decim, const float *d_in, size_t n_ch, size_t n_in,
+                            size_t in_stride, float *d_out, size_t n_out, size_t out_stride, cudaStream_t s);
 
 struct lrc_fir {
     lrc_ctx *ctx;
@@ -206,6 +211,10 @@ static int fir_launch(lrc_fir *f, const void *d_in, size_t n_ch, size_t n_in, si
         for (int i = 0; i < 64; ++i) taps.h[i] = IS_U8 ? (float)((double)f->taps[i] / 127.0) : f->taps[i];
         kern<<<(unsigned)blocks, NT, Cfg::SMEM_BYTES, s>>>((const uint8_t *)d_in, n_ch, n_in, in_stride,
                                                           (float2 *)d_out, n_out, out_stride, use_tma, taps);
+    } else if (!IS_U8 && lrc_fir_gentile_has(f->ntaps, f->decim) && !getenv("LRC_FIR_NO_GENTILE")) {
+        // cf32, ntaps <= 128, decim in {4,5,8,10,16}: the generic tile kernel (k_fir_gentile.cu); LRC_FIR_NO_GENTILE=1 is the A/B knob
+        return lrc_fir_gentile_launch(f->ctx->n_sm, f->taps.data(), f->ntaps, f->decim, (const float *)d_in, n_ch, n_in, in_stride,
+                                      d_out, n_out, out_stride, s);
     } else {
         size_t blocks = ceil_div(n_ch * n_out, 256);
         const size_t cap = (size_t)f->ctx->n_sm * 8;

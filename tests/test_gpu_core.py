@@ -123,6 +123,50 @@ def test_fir_generic_shapes_vs_oracle(ctx, ntaps, decim, n):
     fir.close()
 
 
+@pytest.mark.parametrize("ntaps,decim", [(64, 4), (33, 4), (128, 5), (17, 5), (64, 8), (127, 8), (31, 10), (128, 10), (64, 16), (100, 16), (2, 16)])
+def test_fir_tile_shapes_multichannel_vs_oracle(ctx, ntaps, decim, monkeypatch):
+    """cf32, ntaps <= 128, decim in {4,5,8,10,16}: the padded-chunk tile kernel (k_fir_gentile.cu).  Several tiles per channel, a
+    ragged last tile, even stride (TMA path) and odd stride (cooperative-copy path), and the same bits as the one-thread-per-output
+    kernel it replaces (same ascending-tap fma chain per lane)."""
+    from libredio_b200 import blocks
+    rng = np.random.default_rng(ntaps * 100 + decim)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    n_ch = 3
+    for n in (decim * 2600 + ntaps + 3, decim * 1024 + ntaps - 1, ntaps, 20_001):
+        x = np.stack([synth.cf32_noise_tones(n, seed=50 + c) for c in range(n_ch)])
+        fir = blocks.Fir(ctx, taps, decim)
+        got = fir.run(dev(x, ctx))
+        monkeypatch.setenv("LRC_FIR_NO_GENTILE", "1")
+        old = fir.run(dev(x, ctx))
+        monkeypatch.delenv("LRC_FIR_NO_GENTILE")
+        assert torch.equal(got.view(torch.float32), old.view(torch.float32))
+        got = got.cpu().numpy()
+        for c in range(n_ch):
+            ref = oracle.fir_decimate(x[c], taps, decim)
+            assert got[c].shape == ref.shape
+            assert_close_rms(got[c], ref)
+        fir.close()
+
+
+@pytest.mark.parametrize("chunks", [[5000], [63, 1, 1, 700, 4235], [4096, 4096, 13], [16] * 40 + [4500]])
+def test_fir_stream_tile_shape_is_seam_exact(ctx, chunks):
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(96, 0.05)
+    n, n_ch = sum(chunks), 3
+    x = np.stack([synth.cf32_noise_tones(n, seed=c) for c in range(n_ch)])
+    fir = blocks.Fir(ctx, taps, 8)
+    whole = fir.run(dev(x, ctx)).cpu().numpy()
+    st = blocks.FirStream(fir, n_ch, max(chunks), u8=False)
+    outs, pos = [], 0
+    for c in chunks:
+        outs.append(st.push(dev(x[:, pos:pos + c], ctx)).cpu().numpy())
+        pos += c
+    got = np.concatenate(outs, axis=1)
+    assert got.shape == whole.shape
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    st.close(); fir.close()
+
+
 def test_fir_matches_reference_convolve_on_real_planes(ctx):
     """dsputils::convolve is real-only: the cf32 kernel must equal convolve() on each plane."""
     from libredio_b200 import blocks

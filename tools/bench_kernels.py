@@ -204,6 +204,24 @@ def main():
             ff.close()
         del x
 
+    if want("firg"):
+        # stand-alone FIR for shapes without a dedicated instance: the padded-chunk tile kernel vs the one-thread-per-output kernel
+        for ntaps, decim in [(64, 4), (128, 4), (64, 5), (64, 8), (128, 8), (128, 10), (64, 16), (128, 16)]:
+            tp = synth.lpf_taps(ntaps, 0.4 / decim)
+            n_ch, n = 256 // q, 1_000_000
+            x = torch.view_as_complex(torch.randn(n_ch, n, 2, device=dev, generator=g))
+            fir = blocks.Fir(ctx, tp, decim)
+            ms, _ = timeit(lambda: fir.run(x))
+            os.environ["LRC_FIR_NO_GENTILE"] = "1"
+            ms_old, _ = timeit(lambda: fir.run(x), iters=3, warm=1)
+            os.environ.pop("LRC_FIR_NO_GENTILE")
+            no = (n - ntaps) // decim + 1
+            report(f"FIR{ntaps}/{decim} cf32 (tile, generic shapes)", n_ch * n, n_ch * (n * 8.0 + no * 8.0), ms,
+                   {"n_ch": n_ch, "flop_per_sample": 4.0 * ntaps / decim, "TFLOP/s": n_ch * n * 4.0 * ntaps / decim / (ms * 1e-3) / 1e12,
+                    "one_thread_per_output_ms": ms_old, "speedup": ms_old / ms})
+            fir.close()
+            del x
+
     if want("chaing"):
         # generic fused chain instances (chain_generic.cuh) beside the unfused FIR -> HBM -> PSD path, ~2.7 GB of cf32 each
         os_env = os.environ
