@@ -292,23 +292,14 @@ template <> struct RFor<8>  { static constexpr int R = 7; };
 template <> struct RFor<10> { static constexpr int R = 7; };
 template <> struct RFor<16> { static constexpr int R = 4; };
 
-template <int DECIM>
-static int launch_decim(const Args &a, int log2n)
+template <int NTAPS, int DECIM>
+static int launch_decim_n(const Args &a, int log2n)
 {
     constexpr int R = RFor<DECIM>::R;
-    if (a.ntaps < 1 || a.ntaps > 128) return -1;
-    if (a.ntaps <= 64) {
-        switch (log2n) {
-            case 9:  return launch_one<64, DECIM, 9, R>(a);
-            case 10: return launch_one<64, DECIM, 10, R>(a);
-            case 11: return launch_one<64, DECIM, 11, R>(a);
-            default: return -1;
-        }
-    }
     switch (log2n) {
-        case 9:  return launch_one<128, DECIM, 9, R>(a);
-        case 10: return launch_one<128, DECIM, 10, R>(a);
-        case 11: return launch_one<128, DECIM, 11, R>(a);
+        case 9:  return launch_one<NTAPS, DECIM, 9, R>(a);
+        case 10: return launch_one<NTAPS, DECIM, 10, R>(a);
+        case 11: return launch_one<NTAPS, DECIM, 11, R>(a);
         default: return -1;
     }
 }
@@ -324,14 +315,16 @@ static bool has_decim(int ntaps, int log2n)
 
 }  // namespace chaing
 
-// one translation unit per decimation (k_chaing_d*.cu), so the 28 instances compile in parallel
-int  lrc_chaing_launch_d4(const chaing::Args &a, int log2n);
-int  lrc_chaing_launch_d5(const chaing::Args &a, int log2n);
-int  lrc_chaing_launch_d8(const chaing::Args &a, int log2n);
-int  lrc_chaing_launch_d10(const chaing::Args &a, int log2n);
-int  lrc_chaing_launch_d16(const chaing::Args &a, int log2n);
-bool lrc_chaing_has_d4(int ntaps, int log2n);
-bool lrc_chaing_has_d5(int ntaps, int log2n);
-bool lrc_chaing_has_d8(int ntaps, int log2n);
-bool lrc_chaing_has_d10(int ntaps, int log2n);
-bool lrc_chaing_has_d16(int ntaps, int log2n);
+// Translation units: the three nfft instances of a (decimation, 64-tap) pair share one (k_chaing_d*_n64.cu); a 128-tap instance
+// is a minute or more of compilation on its own, so each has its own (k_chaing_d*_n128_l*.cu) -- a fresh build is then bounded by
+// the core count, not by one file.
+#define LRC_CHAING_DECL(D_, NT_) int lrc_chaing_launch_d##D_##_n##NT_(const chaing::Args &a, int log2n)
+#define LRC_CHAING_DEFINE(D_, NT_) LRC_CHAING_DECL(D_, NT_) { return chaing::launch_decim_n<NT_, D_>(a, log2n); }
+#define LRC_CHAING_DECL1(D_, NT_, L_) int lrc_chaing_launch_d##D_##_n##NT_##_l##L_(const chaing::Args &a)
+#define LRC_CHAING_DEFINE1(D_, NT_, L_) \
+    LRC_CHAING_DECL1(D_, NT_, L_) { return chaing::launch_one<NT_, D_, L_, chaing::RFor<D_>::R>(a); }
+LRC_CHAING_DECL(4, 64); LRC_CHAING_DECL(5, 64); LRC_CHAING_DECL(8, 64); LRC_CHAING_DECL(10, 64); LRC_CHAING_DECL(16, 64);
+#define LRC_CHAING_DECL3(D_) LRC_CHAING_DECL1(D_, 128, 9); LRC_CHAING_DECL1(D_, 128, 10); LRC_CHAING_DECL1(D_, 128, 11)
+LRC_CHAING_DECL3(4); LRC_CHAING_DECL3(5); LRC_CHAING_DECL3(8); LRC_CHAING_DECL3(10); LRC_CHAING_DECL3(16);
+int  lrc_chaing_launch(const chaing::Args &a, int decim, int log2n);     // k_chaing.cu: dispatch
+bool lrc_chaing_has(int ntaps, int decim, int log2n);

@@ -255,14 +255,7 @@ extern "C" int lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, in
     c->fused = (ntaps == 64 && decim == 10 && nfft == 1024);
     c->fused_generic = false;
     if (!c->fused && !getenv("LRC_CHAIN_NO_GENERIC")) {     // A/B knob: LRC_CHAIN_NO_GENERIC=1 forces the unfused path
-        switch (decim) {
-            case 4:  c->fused_generic = lrc_chaing_has_d4(ntaps, l2); break;
-            case 5:  c->fused_generic = lrc_chaing_has_d5(ntaps, l2); break;
-            case 8:  c->fused_generic = lrc_chaing_has_d8(ntaps, l2); break;
-            case 10: c->fused_generic = lrc_chaing_has_d10(ntaps, l2); break;
-            case 16: c->fused_generic = lrc_chaing_has_d16(ntaps, l2); break;
-            default: break;
-        }
+        c->fused_generic = lrc_chaing_has(ntaps, decim, l2);
     }
     c->d_tw = nullptr; c->d_win = nullptr; c->d_partial = nullptr; c->partial_cap = 0;
     c->fir = nullptr; c->psd = nullptr; c->d_tmp = nullptr; c->tmp_cap = 0;
@@ -362,15 +355,7 @@ static int chain_launch(lrc_chain *c, const void *d_in_any, int input_is_u8, siz
         chaing::Args a;
         a.in = (const float2 *)d_in_any; a.tw = c->d_tw; a.win = c->d_win; a.taps = c->taps.data(); a.partial = c->d_partial;
         a.k_avg = k_local; a.fpi = fpi; a.ipr = ipr; a.n_items = n_items; a.ntaps = c->ntaps; a.n_sm = c->ctx->n_sm; a.stream = s;
-        int grc = -1;
-        switch (c->decim) {
-            case 4:  grc = lrc_chaing_launch_d4(a, c->log2n); break;
-            case 5:  grc = lrc_chaing_launch_d5(a, c->log2n); break;
-            case 8:  grc = lrc_chaing_launch_d8(a, c->log2n); break;
-            case 10: grc = lrc_chaing_launch_d10(a, c->log2n); break;
-            case 16: grc = lrc_chaing_launch_d16(a, c->log2n); break;
-            default: break;
-        }
+        const int grc = lrc_chaing_launch(a, c->decim, c->log2n);
         if (grc > 0) return grc;
         if (grc == 0) return lrc_psd_reduce(c->d_partial, d_rows, c->nfft, ipr, rows_local, scale, accumulate, s);
         // grc < 0 cannot happen for a plan whose fused_generic is set; fall through to the unfused kernels

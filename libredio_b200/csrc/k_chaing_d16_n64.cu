@@ -1,0 +1,4 @@
+// k_chaing_d16_n64.cu -- chain_gen_kernel<64, 16, 9|10|11, R> (chain_generic.cuh): the instances of one (decimation, NTAPS) pair
+#include "chain_generic.cuh"
+
+LRC_CHAING_DEFINE(16, 64)

@@ -1,0 +1,4 @@
+// k_chaing_d4_n128_l9.cu -- chain_gen_kernel<128, 4, 9, R> (chain_generic.cuh): one instance per translation unit
+#include "chain_generic.cuh"
+
+LRC_CHAING_DEFINE1(4, 128, 9)

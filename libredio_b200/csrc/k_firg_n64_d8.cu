@@ -1,0 +1,4 @@
+// k_firg_n64_d8.cu -- fir_gentile_kernel<64, 8, R, 128> (fir_gentile.cuh): one instance per translation unit
+#include "fir_gentile.cuh"
+
+LRC_FIRG_DEFINE(64, 8)
