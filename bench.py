@@ -637,7 +637,39 @@ def run_ours(args):
             solo[0], solo[1] = a_ms / args.steps, a_kern
         dist.barrier()
         dist.all_reduce(solo)
-        diag = {"kernel_ms_per_rank": [float(v) for v in kall.tolist()],
+        # Isolation of the receiver's slow-down: rank 0 runs the kernel-only loop while its peers run NO kernel that touches HBM --
+        # a spin kernel paces them to one push of their (stale) rows per step time, into rank 0's slot.  Same inbound bytes per
+        # step as the real loop, no peer compute, no peer power draw to speak of: what is left is the inbound traffic itself.
+        # Second pass: only ONE peer pushes (1/7 of the bytes).
+        iso = [None, None]
+        if gather is not None and args.gather_to == "root":
+            try:
+                clk_hz = torch.cuda.clock_rate() * 1e6 if hasattr(torch.cuda, "clock_rate") else 1.6e9    # MHz -> Hz
+            except Exception:
+                clk_hz = 1.6e9
+            spin = int(0.78e-3 * clk_hz)                           # torch.cuda._sleep counts SM cycles
+            for pi, pushers in enumerate((range(1, world), (1,))):
+                dist.barrier()
+                torch.cuda.synchronize()
+                res = torch.zeros(1, device=dev, dtype=torch.float64)
+                if rank == 0:
+                    _, k_iso = timed_loop(False)
+                    res[0] = k_iso
+                elif rank in pushers:
+                    for i in range(args.steps + 6):                # a little longer than rank 0's loop
+                        b = i & 1
+                        gather.wait_sent(b)
+                        torch.cuda._sleep(spin)
+                        gather.push(b, outs[b])
+                    torch.cuda.synchronize()
+                dist.barrier()
+                dist.all_reduce(res)
+                iso[pi] = float(res[0].item())
+            if rank == 0:                                           # leave the slots consistent: nothing reads them after this
+                torch.cuda.synchronize()
+        diag = {"kernel_ms_rank0_while_idle_peers_only_push": iso[0],
+                "kernel_ms_rank0_while_ONE_idle_peer_pushes": iso[1],
+                "kernel_ms_per_rank": [float(v) for v in kall.tolist()],
                 "ms_per_step_without_gather_max_over_ranks": float(tn[0].item()) / args.steps,
                 "kernel_ms_without_gather_max_over_ranks": float(tn[1].item()),
                 "ms_per_step_all_gather_max_over_ranks": (float(ta[0].item()) / args.steps) if ta is not None else None,

@@ -511,11 +511,16 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                         burst += 1; dropped = true;
                         buf_len = 1; lead0 = true; cur_max = 0.0f; open_from = 0xffffffffu;
                     }
-                    const float thr0 = threshold == 0.0f ? s : threshold;               // :57-59
-                    const float thr1 = __fadd_rn(thr0, qr[k]);                          // :62-65
+                    // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
+                    // candidate sums exist before the select -- and the fire test s > threshold * 4 (:68-70) is made as
+                    // s / 4 > threshold with s / 4 taken off the chain: both scalings by a power of two are exact (s is 0 or
+                    // >= 0.0078, the smallest non-zero envelope), so the comparison is the same one
+                    const bool unset = threshold == 0.0f;                               // :57-59
+                    const float thr0 = unset ? s : threshold;
+                    const float thr1 = unset ? __fadd_rn(s, qr[k]) : __fadd_rn(threshold, qr[k]);   // :62-65
                     const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
                     threshold = trigger < 0 ? thr2 : thr0;
-                    trigger = s > __fmul_rn(threshold, 4.0f) ? OOK_TRIGGER_DURATION : trigger;   // :68-70
+                    trigger = __fmul_rn(s, 0.25f) > threshold ? OOK_TRIGGER_DURATION : trigger;  // :68-70
                     const bool collect = trigger > 1;                                   // :73-75 push_all
                     buf_len += collect ? (uint32_t)OOK_BLOCK : 0u;
                     cur_max = collect ? fmaxf(cur_max, mr[k]) : cur_max;
@@ -662,22 +667,26 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         if (lane == 0) pb = prev;
         uint32_t tm = (m ^ ((m << 1) | pb)) & 0xffffu;                       // bit i set: sample i differs from i-1
         if (!has_prev) tm &= ~1u;                                            // very first bit of the stream
-        const uint32_t cnt = __popc(tm);
-        uint32_t off = cnt;                                                  // inclusive warp scan
+        // most collected blocks are the noise that follows a burst (the trigger holds for 49 blocks) or the inside of a long
+        // pulse: no transition anywhere in the block, nothing to scan or append
+        if (__ballot_sync(0xffffffffu, tm != 0u) != 0u) {
+            const uint32_t cnt = __popc(tm);
+            uint32_t off = cnt;                                              // inclusive warp scan
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
-            if (lane >= d) off += v;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
+                if (lane >= d) off += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
+            uint32_t o = ntr + off - cnt;
+            while (tm) {
+                const int i = __ffs(tm) - 1;
+                tm &= tm - 1;
+                if (o < max_runs) trans[o] = pos + lane * 16 + i;
+                ++o;
+            }
+            ntr += total;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
-        uint32_t o = ntr + off - cnt;
-        while (tm) {
-            const int i = __ffs(tm) - 1;
-            tm &= tm - 1;
-            if (o < max_runs) trans[o] = pos + lane * 16 + i;
-            ++o;
-        }
-        ntr += total;
         prev = __shfl_sync(0xffffffffu, m >> 15, 31) & 1u;
         pos += OOK_BLOCK;
     };

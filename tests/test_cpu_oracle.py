@@ -412,6 +412,54 @@ def test_fastfir16k_design_model_is_an_exact_overlap_save():
     assert np.max(np.abs(y - ref)) <= 1e-12 * np.sqrt(np.mean(np.abs(ref) ** 2))
 
 
+def test_round2_index_models_exhaustive():
+    """the integer arithmetic the round-2 kernels rely on (tools/models/index_models.py restates it index for index)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models"))
+    import index_models as im
+    # folded envelope table: every sorted pair has its own slot inside the table, whatever the order of the two bytes
+    seen = {}
+    for hi in range(256):
+        for lo in range(hi + 1):
+            idx = im.ook_fold_index(hi << 8 | lo)
+            assert im.OOK_FOLD_MIN <= idx <= im.OOK_FOLD_MAX and idx not in seen
+            seen[idx] = (hi, lo)
+    assert len(seen) == 256 * 257 // 2
+    rng = np.random.default_rng(0)
+    for w in rng.integers(0, 1 << 32, 20000, dtype=np.uint64).tolist() + [0, 0xFFFFFFFF, 0x00FF00FF, 0xFF00FF00, 0x7F7F7F7F]:
+        b = [(w >> (8 * i)) & 255 for i in range(4)]
+        k0, k1 = im.sorted_key_pair(w)
+        assert k0 == max(b[0], b[1]) << 8 | min(b[0], b[1]) and k1 == max(b[2], b[3]) << 8 | min(b[2], b[3])
+    # rows of both tables start 8 banks apart (4-byte / 2-byte entries: 264 entries per row)
+    assert im.ook_fold_index(200 << 8) - im.ook_fold_index(199 << 8) == 264
+    slots = {im.ook_rank_slot(raw) for raw in range(65536)}
+    assert len(slots) == 65536 and max(slots) < 256 * 264
+    # padded-chunk tile: windows never straddle a pad inside a 16-byte pair load, thread windows start an odd number of
+    # 16-byte units apart, and every sample a (zero-padded) tap can reach is either copied or lies behind the copied extent
+    for ntaps_max in (64, 128):
+        for decim, r in ((4, 8), (5, 8), (8, 7), (10, 7), (16, 4)):
+            step, win, winl, padb, pitch = im.gen_tile(ntaps_max, decim, r)
+            offs = im.gen_tile_offsets(ntaps_max, decim, r)
+            assert pitch % 16 == 0 and (pitch // 16) % 2 == 1
+            assert all(o % 8 == 0 for o in offs) and all(offs[j + 1] == offs[j] + 8 for j in range(0, winl, 2))
+            assert all(offs[j] % 16 == 0 for j in range(0, winl, 2))
+            for t in (0, 1, 5):                                  # window of thread t = the same samples seen from chunk t
+                for j in range(winl):
+                    i = t * step + j                             # tile sample index
+                    assert t * pitch + offs[j] == (i // step) * pitch + (i % step) * 8
+            for n in (512, 1024):
+                for ntaps in (1, 2, 17, 63, ntaps_max - 1, ntaps_max):
+                    tile_in = (n - 1) * decim + ntaps
+                    covered = np.zeros(tile_in, bool)
+                    for c, s0, ns, hand in im.chunk_plan(tile_in, step):
+                        assert ns % 2 == 0 and (s0 * 8) % 16 == 0
+                        covered[s0:s0 + ns] = True
+                        if hand is not None:
+                            assert s0 <= hand < s0 + step and not covered[hand]
+                            covered[hand] = True
+                    assert covered.all()
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3

@@ -111,6 +111,16 @@ def test_ook_edge_cases_match_oracle(ctx, case):
     check_against_oracle(caps, pk, dbg)
 
 
+@pytest.mark.parametrize("n_blocks", [1, 5, 31, 32, 33, 65])
+def test_ook_captures_shorter_than_a_warp_group(ctx, n_blocks):
+    """the block-sum kernel's TMA box is 32 blocks tall: captures with fewer blocks (and a ragged second group) rely on the
+    out-of-bounds rows being zero-filled and never stored; every stage must still equal the oracle"""
+    rng = np.random.default_rng(n_blocks)
+    caps = [np.clip(np.rint(127 + (2 + 40 * (s % 2)) * rng.standard_normal(n_blocks * 1024)), 0, 255).astype(np.uint8) for s in range(3)]
+    pk, dbg = run_ook(ctx, caps, max_runs=1 << 17)
+    check_against_oracle(caps, pk, dbg)
+
+
 def test_ook_run_capacity_overflow_is_reported(ctx):
     caps = [noisy_burst_capture(70)]
     assert oracle.ook_decode(caps[0])["run_val"].size > 64

@@ -1,0 +1,64 @@
+"""Index models of the round-2 kernels, restated index for index in Python so that the arithmetic the kernels rely on can be
+checked exhaustively on the CPU (tests/test_cpu_oracle.py):
+
+* `ook_fold_index` / `sorted_key_pair` -- the block-sum kernel's folded envelope table (k_ook.cu): one PRMT + VIMNMX.U16x2 sort
+  the byte pairs of two samples, `max(key, 65279 - key)` folds the triangle {lo <= hi} into rows 127..255, `k2 + (k2 >> 5)` skews
+  the rows 8 banks apart; the skew is computed as mad.hi by 2^27 + 1.
+* `ook_rank_slot` -- the slicer's rank table indexed from the raw halfword.
+* `gen_tile_offsets` / `chunk_plan` -- the padded-chunk tile of the generic fused chain and FIR tile kernel
+  (chain_generic.cuh: GenTile, load_sub): where sample j of a thread window lives, which bulk copies a tile takes, and that
+  every sample a tap can reach was either copied or lies in the zeroed tail.
+"""
+import numpy as np
+
+OOK_FOLD_C = 65279
+OOK_FOLD_MIN = 32640 + (32640 >> 5)
+OOK_FOLD_MAX = 65535 + (65535 >> 5)
+
+
+def sorted_key_pair(w: int) -> tuple[int, int]:
+    """w = b0 | b1 << 8 | b2 << 16 | b3 << 24 (two samples): (key0, key1) with key = hi << 8 | lo of each sample's byte pair"""
+    swapped = ((w & 0x00FF00FF) << 8) | ((w >> 8) & 0x00FF00FF)          # PRMT 0x2301
+    lo = max(w & 0xFFFF, swapped & 0xFFFF)                                # VIMNMX.U16x2
+    hi = max(w >> 16, swapped >> 16)
+    return lo, hi
+
+
+def ook_fold_index(key: int) -> int:
+    alt = OOK_FOLD_C - key                                               # negative for hi = 255: loses the SIGNED max
+    k2 = max(alt, key)
+    skew = (k2 * ((1 << 27) + 1)) >> 32                                  # mad.hi.u32 by 2^27 + 1
+    assert skew == k2 >> 5
+    return k2 + skew
+
+
+def ook_rank_slot(raw: int) -> int:
+    return raw + (raw >> 5)
+
+
+def gen_tile(ntaps_max: int, decim: int, r: int):
+    step = r * decim
+    win = (r - 1) * decim + ntaps_max
+    winl = (win + 1) & ~1
+    padb = 16 if (step // 2) % 2 == 0 else 0
+    pitch = step * 8 + padb
+    return step, win, winl, padb, pitch
+
+
+def gen_tile_offsets(ntaps_max: int, decim: int, r: int):
+    """byte offset of sample j of a thread window, from the window start"""
+    step, win, winl, padb, pitch = gen_tile(ntaps_max, decim, r)
+    return [j * 8 + padb * (j // step) for j in range(winl)]
+
+
+def chunk_plan(tile_in: int, step: int):
+    """(chunk, first sample, samples by bulk copy, hand-copied sample or None) as load_sub issues them"""
+    n_chunks = (tile_in + step - 1) // step
+    tma = tile_in & ~1
+    out = []
+    for c in range(n_chunks):
+        s0 = c * step
+        ns = min(step, tma - s0)
+        hand = tile_in - 1 if (tile_in & 1) and s0 + step >= tile_in and s0 < tile_in else None
+        out.append((c, s0, max(ns, 0), hand))
+    return out
