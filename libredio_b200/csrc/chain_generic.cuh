@@ -304,13 +304,33 @@ static int launch_decim_n(const Args &a, int log2n)
     }
 }
 
+// Which shapes a plan runs fused.  Every instance FITS; whether it is the faster path was measured against the unfused one
+// (FIR tile kernel -> HBM -> PSD kernel, itself at 0.8 of the HBM roofline since the FIR got tile instances for these shapes too,
+// profiles/r2_w_chain_generic_vs_unfused.txt): fused wins 1.03-1.22x when two or more CTAs fit an SM (the TMA of one overlaps the
+// arithmetic of the other) and the shape is not FP32-bound in the producers (decim >= 8, or nfft 512 where the FFT is cheap);
+// it ties or loses (1.01-0.74x) for the one-CTA shapes (whole-frame tile: load and filter serialise) and for decim 4 / 5 at
+// nfft >= 1024 (the producers share 162-register threads with the FFT warps: 12 warps per SM against the stand-alone FIR's 24).
+// all = true (LRC_CHAIN_GENERIC_ALL=1, what the parity tests use) selects every fitting instance.
+template <int NTAPS, int DECIM, int LOG2N>
+static constexpr bool prefer_fused()
+{
+    using C = GenCfg<NTAPS, DECIM, LOG2N, RFor<DECIM>::R>;
+    return C::FITS && C::BY_SMEM >= 2 && (DECIM >= 8 || LOG2N <= 9);
+}
+
 template <int DECIM>
-static bool has_decim(int ntaps, int log2n)
+static bool has_decim(int ntaps, int log2n, bool all)
 {
     constexpr int R = RFor<DECIM>::R;
     if (ntaps < 1 || ntaps > 128 || log2n < 9 || log2n > 11) return false;
-    if (ntaps <= 64) return log2n == 9 ? GenCfg<64, DECIM, 9, R>::FITS : log2n == 10 ? GenCfg<64, DECIM, 10, R>::FITS : GenCfg<64, DECIM, 11, R>::FITS;
-    return log2n == 9 ? GenCfg<128, DECIM, 9, R>::FITS : log2n == 10 ? GenCfg<128, DECIM, 10, R>::FITS : GenCfg<128, DECIM, 11, R>::FITS;
+    if (ntaps <= 64) {
+        if (log2n == 9)  return GenCfg<64, DECIM, 9, R>::FITS && (all || prefer_fused<64, DECIM, 9>());
+        if (log2n == 10) return GenCfg<64, DECIM, 10, R>::FITS && (all || prefer_fused<64, DECIM, 10>());
+        return GenCfg<64, DECIM, 11, R>::FITS && (all || prefer_fused<64, DECIM, 11>());
+    }
+    if (log2n == 9)  return GenCfg<128, DECIM, 9, R>::FITS && (all || prefer_fused<128, DECIM, 9>());
+    if (log2n == 10) return GenCfg<128, DECIM, 10, R>::FITS && (all || prefer_fused<128, DECIM, 10>());
+    return GenCfg<128, DECIM, 11, R>::FITS && (all || prefer_fused<128, DECIM, 11>());
 }
 
 }  // namespace chaing
@@ -327,4 +347,4 @@ LRC_CHAING_DECL(4, 64); LRC_CHAING_DECL(5, 64); LRC_CHAING_DECL(8, 64); LRC_CHAI
 #define LRC_CHAING_DECL3(D_) LRC_CHAING_DECL1(D_, 128, 9); LRC_CHAING_DECL1(D_, 128, 10); LRC_CHAING_DECL1(D_, 128, 11)
 LRC_CHAING_DECL3(4); LRC_CHAING_DECL3(5); LRC_CHAING_DECL3(8); LRC_CHAING_DECL3(10); LRC_CHAING_DECL3(16);
 int  lrc_chaing_launch(const chaing::Args &a, int decim, int log2n);     // k_chaing.cu: dispatch
-bool lrc_chaing_has(int ntaps, int decim, int log2n);
+bool lrc_chaing_has(int ntaps, int decim, int log2n, bool all);

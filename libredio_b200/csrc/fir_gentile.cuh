@@ -99,7 +99,8 @@ static int launch(int n_sm, const float *h_taps, int ntaps, const float *d_in, s
     static const size_t gm = lrc_grid_mult("LRC_FIR_GRID", 1024);
     size_t blocks = (size_t)n_sm * occ * gm;
     if (blocks > n_tiles) blocks = n_tiles;
-    const int use_tma = (((uintptr_t)d_in & 15) == 0) && (in_stride % 2 == 0);
+    // TMA needs 16-byte aligned sources: base, and the channel stride when there is more than one channel row
+    const int use_tma = (((uintptr_t)d_in & 15) == 0) && (n_ch == 1 || in_stride % 2 == 0);
     FirTaps<NTAPS> taps;
     for (int i = 0; i < NTAPS; ++i) taps.h[i] = i < ntaps ? h_taps[i] : 0.0f;
     kern<<<(unsigned)blocks, NT, C::SMEM_BYTES, s>>>((const float2 *)d_in, n_ch, n_in, in_stride, (float2 *)d_out, n_out,

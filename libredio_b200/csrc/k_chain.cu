@@ -254,8 +254,10 @@ extern "C" int lrc_chain_create(lrc_ctx *ctx, const float *h_taps, int ntaps, in
     c->taps.assign(h_taps, h_taps + ntaps);
     c->fused = (ntaps == 64 && decim == 10 && nfft == 1024);
     c->fused_generic = false;
-    if (!c->fused && !getenv("LRC_CHAIN_NO_GENERIC")) {     // A/B knob: LRC_CHAIN_NO_GENERIC=1 forces the unfused path
-        c->fused_generic = lrc_chaing_has(ntaps, decim, l2);
+    // A/B knobs: LRC_CHAIN_NO_GENERIC=1 forces the unfused path, LRC_CHAIN_GENERIC_ALL=1 the fused instance for every shape that
+    // has one (by default only where it measured faster than the unfused kernels, chain_generic.cuh: prefer_fused)
+    if (!c->fused && !getenv("LRC_CHAIN_NO_GENERIC")) {
+        c->fused_generic = lrc_chaing_has(ntaps, decim, l2, getenv("LRC_CHAIN_GENERIC_ALL") != nullptr);
     }
     c->d_tw = nullptr; c->d_win = nullptr; c->d_partial = nullptr; c->partial_cap = 0;
     c->fir = nullptr; c->psd = nullptr; c->d_tmp = nullptr; c->tmp_cap = 0;

@@ -1,14 +1,14 @@
 // k_chaing.cu -- dispatch of the generic fused chain (chain_generic.cuh; instances in k_chaing_d*_n*.cu)
 #include "chain_generic.cuh"
 
-bool lrc_chaing_has(int ntaps, int decim, int log2n)
+bool lrc_chaing_has(int ntaps, int decim, int log2n, bool all)
 {
     switch (decim) {
-        case 4:  return chaing::has_decim<4>(ntaps, log2n);
-        case 5:  return chaing::has_decim<5>(ntaps, log2n);
-        case 8:  return chaing::has_decim<8>(ntaps, log2n);
-        case 10: return chaing::has_decim<10>(ntaps, log2n);
-        case 16: return chaing::has_decim<16>(ntaps, log2n);
+        case 4:  return chaing::has_decim<4>(ntaps, log2n, all);
+        case 5:  return chaing::has_decim<5>(ntaps, log2n, all);
+        case 8:  return chaing::has_decim<8>(ntaps, log2n, all);
+        case 10: return chaing::has_decim<10>(ntaps, log2n, all);
+        case 16: return chaing::has_decim<16>(ntaps, log2n, all);
         default: return false;
     }
 }

@@ -206,7 +206,7 @@ static int fir_launch(lrc_fir *f, const void *d_in, size_t n_ch, size_t n_in, si
         size_t blocks = (size_t)f->ctx->n_sm * occ * gm;
         if (blocks > n_tiles) blocks = n_tiles;
         // TMA needs 16-byte aligned sources: base, channel stride and (always true) tile stride
-        const int use_tma = (((uintptr_t)d_in & 15) == 0) && ((in_stride * ES) % 16 == 0);
+        const int use_tma = (((uintptr_t)d_in & 15) == 0) && (n_ch == 1 || (in_stride * ES) % 16 == 0);
         FirTaps<64> taps;
         for (int i = 0; i < 64; ++i) taps.h[i] = IS_U8 ? (float)((double)f->taps[i] / 127.0) : f->taps[i];
         kern<<<(unsigned)blocks, NT, Cfg::SMEM_BYTES, s>>>((const uint8_t *)d_in, n_ch, n_in, in_stride,

@@ -488,8 +488,9 @@ GENERIC_SHAPES = [(33, 4, 512), (64, 4, 1024), (128, 4, 2048), (17, 5, 512), (64
 
 
 @pytest.mark.parametrize("ntaps,decim,nfft", GENERIC_SHAPES)
-def test_chain_generic_shape_runs_a_fused_instance(ctx, ntaps, decim, nfft):
+def test_chain_generic_shape_runs_a_fused_instance(ctx, ntaps, decim, nfft, monkeypatch):
     from libredio_b200 import blocks
+    monkeypatch.setenv("LRC_CHAIN_GENERIC_ALL", "1")         # every instance, not only the ones the default policy prefers
     rng = np.random.default_rng(ntaps * 1000 + decim * 10 + nfft)
     taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
     frames, k = 21, 3
@@ -519,7 +520,9 @@ def test_chain_generic_fused_equals_unfused_kernels_at_size(ctx, ntaps, decim, n
     n = (frames - 1) * nfft * decim + (nfft - 1) * decim + ntaps
     g = torch.Generator(device=ctx.tdev).manual_seed(3)
     x = torch.view_as_complex(torch.randn(n, 2, device=ctx.tdev, generator=g))
+    monkeypatch.setenv("LRC_CHAIN_GENERIC_ALL", "1")
     fused = blocks.Chain(ctx, taps, decim, nfft)
+    monkeypatch.delenv("LRC_CHAIN_GENERIC_ALL")
     monkeypatch.setenv("LRC_CHAIN_NO_GENERIC", "1")
     unfused = blocks.Chain(ctx, taps, decim, nfft)
     monkeypatch.delenv("LRC_CHAIN_NO_GENERIC")
@@ -528,6 +531,18 @@ def test_chain_generic_fused_equals_unfused_kernels_at_size(ctx, ntaps, decim, n
     assert a.shape == b.shape == (frames // k, nfft)
     assert (a - b).abs().max().item() <= 1e-5 * b.pow(2).mean().sqrt().item()
     fused.close(); unfused.close()
+
+
+def test_chain_default_policy_fuses_where_it_measured_faster(ctx):
+    """prefer_fused (chain_generic.cuh): two or more CTAs per SM and not FP32-bound in the producers"""
+    from libredio_b200 import blocks
+    taps = synth.lpf_taps(64, 0.04)
+    for (ntaps, decim, nfft), kind in {(64, 8, 1024): 2, (128, 10, 1024): 2, (64, 16, 512): 2, (64, 4, 512): 2, (64, 10, 512): 2,
+                                       (64, 5, 1024): 0, (64, 5, 2048): 0, (64, 4, 1024): 0, (64, 10, 2048): 0,
+                                       (64, 16, 2048): 0, (128, 8, 2048): 0, (64, 16, 1024): 0}.items():
+        ch = blocks.Chain(ctx, np.resize(taps, ntaps), decim, nfft)
+        assert ch.kind == kind, (ntaps, decim, nfft, ch.kind)
+        ch.close()
 
 
 def test_chain_shapes_without_an_instance_stay_unfused(ctx):

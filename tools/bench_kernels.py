@@ -234,9 +234,9 @@ def main():
             x = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
             res = {}
             for label, env in (("fused", None), ("unfused", "1")):
-                if env: os_env["LRC_CHAIN_NO_GENERIC"] = env
+                os_env["LRC_CHAIN_NO_GENERIC" if env else "LRC_CHAIN_GENERIC_ALL"] = "1"
                 ch = blocks.Chain(ctx, tp, decim, nfft)
-                os_env.pop("LRC_CHAIN_NO_GENERIC", None)
+                os_env.pop("LRC_CHAIN_NO_GENERIC", None); os_env.pop("LRC_CHAIN_GENERIC_ALL", None)
                 if label == "unfused" and (ntaps, decim, nfft) == (64, 10, 1024):
                     ch.close(); continue
                 out = torch.empty((frames // k, nfft), dtype=torch.float32, device=dev)
