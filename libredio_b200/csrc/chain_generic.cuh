@@ -101,7 +101,11 @@ struct GenCfg {
     static constexpr int SMEM_BYTES = OFF_BAR + 32;
     static constexpr bool FITS = SMEM_BYTES <= 227 * 1024 && NT <= 1024;
     // as many CTAs per SM as shared memory and a 128-register thread (the 16-point-per-thread FFT needs that) allow
-    static constexpr int BY_SMEM = (227 * 1024) / (SMEM_BYTES + 1024), BY_REGS = 65536 / (NT * 128);
+    // (decim 4 / 5 are FP32-bound in the FIR producers, which need ~40 registers: there the budget is 96 registers -- the FFT warps
+    // still fit without spilling and the producers get a third CTA per SM: 64/4/1024 0.835 -> 0.716 ms, 64/5/1024 0.752 -> 0.607;
+    // 80 registers, four CTAs and 56 bytes of spill measured the same)
+    static constexpr int REG_BUDGET = DECIM <= 5 ? 96 : 128;
+    static constexpr int BY_SMEM = (227 * 1024) / (SMEM_BYTES + 1024), BY_REGS = 65536 / (NT * REG_BUDGET);
     static constexpr int MIN_CTAS_RAW = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
     static constexpr int MIN_CTAS = MIN_CTAS_RAW < 1 ? 1 : (MIN_CTAS_RAW > 8 ? 8 : MIN_CTAS_RAW);
     static_assert((FRAME_ADV * 8) % 16 == 0 && (SUB_ADV * 8) % 16 == 0 && (Tile::STEP * 8) % 16 == 0, "TMA alignment");
@@ -307,15 +311,15 @@ static int launch_decim_n(const Args &a, int log2n)
 // Which shapes a plan runs fused.  Every instance FITS; whether it is the faster path was measured against the unfused one
 // (FIR tile kernel -> HBM -> PSD kernel, itself at 0.8 of the HBM roofline since the FIR got tile instances for these shapes too,
 // profiles/r2_w_chain_generic_vs_unfused.txt): fused wins 1.03-1.22x when two or more CTAs fit an SM (the TMA of one overlaps the
-// arithmetic of the other) and the shape is not FP32-bound in the producers (decim >= 8, or nfft 512 where the FFT is cheap);
-// it ties or loses (1.01-0.74x) for the one-CTA shapes (whole-frame tile: load and filter serialise) and for decim 4 / 5 at
-// nfft >= 1024 (the producers share 162-register threads with the FFT warps: 12 warps per SM against the stand-alone FIR's 24).
+// arithmetic of the other) and the producers are not starved (decim >= 8; decim 4 / 5 up to 64 taps and nfft 1024, where the
+// 96-register budget gives them a third CTA); it ties or loses (1.01-0.74x) for the one-CTA shapes (whole-frame tile: load and
+// filter serialise) and for 128 taps at decim 4 / 5 (FP32-bound producers with 18 warps per SM against the stand-alone FIR's 24).
 // all = true (LRC_CHAIN_GENERIC_ALL=1, what the parity tests use) selects every fitting instance.
 template <int NTAPS, int DECIM, int LOG2N>
 static constexpr bool prefer_fused()
 {
     using C = GenCfg<NTAPS, DECIM, LOG2N, RFor<DECIM>::R>;
-    return C::FITS && C::BY_SMEM >= 2 && (DECIM >= 8 || LOG2N <= 9);
+    return C::FITS && C::BY_SMEM >= 2 && (DECIM >= 8 || LOG2N <= 9 || (LOG2N == 10 && NTAPS <= 64));
 }
 
 template <int DECIM>

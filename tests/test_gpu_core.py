@@ -538,7 +538,7 @@ def test_chain_default_policy_fuses_where_it_measured_faster(ctx):
     from libredio_b200 import blocks
     taps = synth.lpf_taps(64, 0.04)
     for (ntaps, decim, nfft), kind in {(64, 8, 1024): 2, (128, 10, 1024): 2, (64, 16, 512): 2, (64, 4, 512): 2, (64, 10, 512): 2,
-                                       (64, 5, 1024): 0, (64, 5, 2048): 0, (64, 4, 1024): 0, (64, 10, 2048): 0,
+                                       (64, 5, 1024): 2, (64, 4, 1024): 2, (128, 4, 1024): 0, (64, 5, 2048): 0, (64, 10, 2048): 0,
                                        (64, 16, 2048): 0, (128, 8, 2048): 0, (64, 16, 1024): 0}.items():
         ch = blocks.Chain(ctx, np.resize(taps, ntaps), decim, nfft)
         assert ch.kind == kind, (ntaps, decim, nfft, ch.kind)
