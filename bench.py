@@ -460,12 +460,18 @@ def run_ours(args):
     # the only exchange: every rank's output rows go to every peer.  Default: lrc_gather (copy engines over NVLink,
     # zero SMs, overlaps the next step's persistent kernel); fallback / --gather nccl: NCCL all-gather, whose kernel
     # cannot start while the chain kernel fills every SM and therefore serialises with it.
-    gather, gather_kind, gath, gather_all, gather_rot = None, "none (1 GPU)", None, None, None
+    gather, gather_kind, gath, gather_all, gather_rot, gather_host, gather_p2p = None, "none (1 GPU)", None, None, None, None, None
     if world > 1:
         ok = torch.zeros(1, device=dev)
         if args.gather == "ce":
             try:
-                gather = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
+                # the node's shared-memory segment for the host gather: one name for all ranks
+                shm = [f"/lrc_bench_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}" if rank == 0 else None]
+                dist.broadcast_object_list(shm, src=0)
+                gather_host = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2, host_shm=shm[0], root=0)
+                dist.barrier()
+                gather_p2p = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
+                gather = gather_host if args.gather_to == "host" else gather_p2p
                 if args.gather_to == "root":
                     gather.set_root(0)
                 elif args.gather_to == "rotate":
@@ -481,10 +487,10 @@ def run_ours(args):
         if int(ok.item()) != world:
             if gather is not None:
                 gather.close()
-            for gx in (gather_all, gather_rot):
-                if gx is not None:
+            for gx in (gather_all, gather_rot, gather_host, gather_p2p):
+                if gx is not None and gx is not gather:
                     gx.close()
-            gather = gather_all = gather_rot = None
+            gather = gather_all = gather_rot = gather_host = gather_p2p = None
         # bounded-time probe before the timed loop depends on it (every rank created and connected its Gather): one push +
         # arrival wait per slot on a side stream, polled from the host.  A peer whose flag write never arrives would
         # otherwise hang the bench inside a device-side wait; the probing stream can never drain in that case, so the
@@ -511,7 +517,10 @@ def run_ours(args):
             gath = [torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
             gather_kind = "NCCL all_gather_into_tensor of output rows (async, 2 slots)"
         else:
-            gather_kind = ("lrc_gather, root 0: copy-engine P2P push of every rank's output rows into rank 0's slot (CUDA IPC, 2 slots)"
+            gather_kind = ("lrc_gather to HOST memory: every rank copies its output rows D2H over its own PCIe link into one page-locked "
+                           "shared-memory segment of the node, rank 0 (where the consumer block runs on the CPU) orders on the flags"
+                           if args.gather_to == "host" else
+                           "lrc_gather, root 0: copy-engine P2P push of every rank's output rows into rank 0's slot (CUDA IPC, 2 slots)"
                            if args.gather_to == "root" else
                            "lrc_gather, rotating receiver: step n's rows of every rank land on rank (n - 1 + slot) % world"
                            if args.gather_to == "rotate" else
@@ -598,6 +607,13 @@ def run_ours(args):
         for b in range(2):
             want = torch.empty((world * rows, NFFT), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(want, outs[b])
+            if args.gather_to == "host":
+                if rank == 0:
+                    gather.wait(b)
+                    torch.cuda.synchronize()
+                    if not torch.equal(gather.buffer(b).reshape(world * rows, NFFT), want.cpu()):
+                        raise SystemExit(f"bench.py rank {rank}: host gather slot {b} differs from the NCCL all-gather")
+                continue
             got = gather.buffer(b).reshape(world * rows, NFFT)
             w_ = max(args.warmup, 3)
             last_push = 1 + (w_ + 1 - b) // 2 + (args.steps + 1 - b) // 2     # pushes of slot b so far: probe, warm-up, timed
@@ -629,6 +645,13 @@ def run_ours(args):
             rg_ms, rg_kern = timed_loop(True, gather_rot)
             tr = torch.tensor([rg_ms, rg_kern], device=dev, dtype=torch.float64)
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        th = None
+        if gather_host is not None:                            # ... and with the rows gathered into the node's HOST memory
+            dist.barrier()
+            torch.cuda.synchronize()
+            hg_ms, hg_kern = timed_loop(True, gather_host)
+            th = torch.tensor([hg_ms, hg_kern], device=dev, dtype=torch.float64)
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
         # one rank alone (the others idle): is the kernel itself slower when its peers run (power, NVLink inbound writes)?
         solo = torch.zeros(2, device=dev, dtype=torch.float64)
         dist.barrier()
@@ -667,7 +690,9 @@ def run_ours(args):
                 iso[pi] = float(res[0].item())
             if rank == 0:                                           # leave the slots consistent: nothing reads them after this
                 torch.cuda.synchronize()
-        diag = {"kernel_ms_rank0_while_idle_peers_only_push": iso[0],
+        diag = {"ms_per_step_host_gather_max_over_ranks": (float(th[0].item()) / args.steps) if th is not None else None,
+                "kernel_ms_host_gather_max_over_ranks": float(th[1].item()) if th is not None else None,
+                "kernel_ms_rank0_while_idle_peers_only_push": iso[0],
                 "kernel_ms_rank0_while_ONE_idle_peer_pushes": iso[1],
                 "kernel_ms_per_rank": [float(v) for v in kall.tolist()],
                 "ms_per_step_without_gather_max_over_ranks": float(tn[0].item()) / args.steps,
@@ -835,8 +860,8 @@ def run_ours(args):
         dist.barrier()
     if gather is not None:
         gather.close()
-    for gx in (gather_all, gather_rot):
-        if gx is not None:
+    for gx in (gather_all, gather_rot, gather_host, gather_p2p):
+        if gx is not None and gx is not gather:
             gx.close()
     chain.close()
     ctx.close()
@@ -860,9 +885,9 @@ def main():
     ap.add_argument("--quick-extra", action="store_true", dest="quick_extra", help="extra block at 1/8 size (smoke runs)")
     ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
                     help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
-    ap.add_argument("--gather-to", default="root", choices=["root", "all", "rotate"], dest="gather_to",
-                    help="N > 1: who receives the output rows: rank 0 only (a gather, default), every rank (all-gather), or a "
-                         "receiver that rotates from step to step")
+    ap.add_argument("--gather-to", default="root", choices=["root", "all", "rotate", "host"], dest="gather_to",
+                    help="N > 1: who receives the output rows: rank 0's GPU (a gather, default), every rank (all-gather), a "
+                         "receiver that rotates from step to step, or the node's host memory (a CPU consumer on rank 0)")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
                     help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()

@@ -316,6 +316,14 @@ int lrc_ook_envelope_table(lrc_ctx *ctx, float *d_table, void *stream);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct lrc_gather lrc_gather;
 int    lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, lrc_gather **g);
+/* the same gather into HOST memory shared by the ranks of one node: POSIX shared memory `shm_name` ("/name"), created by rank
+ * `root` and opened by the others (they retry for up to 30 s), page-locked and mapped by every rank.  A push is one D2H copy over
+ * the pushing GPU's own PCIe link plus the flag write; lrc_gather_wait on the root orders a stream behind the arrival flags;
+ * lrc_gather_buffer returns a HOST pointer.  For graphs whose consumer block runs on the CPU (the reference's vidsink / psdpng):
+ * no GPU's HBM or NVLink port sees another rank's rows (inbound peer writes cost a bandwidth-bound kernel 4.7 % at 8 GPUs).
+ * export / connect / set_root do not apply. */
+int    lrc_gather_create_host(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, const char *shm_name,
+                              int root, lrc_gather **g);
 int    lrc_gather_destroy(lrc_gather *g);
 /* root = -1 (default): every rank receives every rank's block (all-gather); root = r: only rank r receives (gather) --
  * pushes then send one block per rank instead of world-1, and lrc_gather_wait is a no-op on the other ranks;

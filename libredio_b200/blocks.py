@@ -528,10 +528,18 @@ class Gather:
     `Gather(ctx, rank, world, nbytes, slots).connect_distributed()`; several contexts in one process:
     `Gather.connect_local([g0, g1, ...])`."""
 
-    def __init__(self, ctx: Context, rank: int, world: int, bytes_per_rank: int, slots: int = 2):
+    def __init__(self, ctx: Context, rank: int, world: int, bytes_per_rank: int, slots: int = 2, host_shm: str | None = None,
+                 root: int = 0):
+        """host_shm = "/name": gather into page-locked POSIX shared memory of the node instead of a GPU (lrc_gather_create_host;
+        rank `root` creates the segment, the others open it) -- for consumers that run on the CPU."""
         self.ctx, self.rank, self.world, self.bytes_per_rank, self.slots = ctx, rank, world, bytes_per_rank, slots
+        self.is_host = host_shm is not None
         self.h = C.c_void_p()
-        check(ctx.lib.lrc_gather_create(ctx.h, rank, world, bytes_per_rank, slots, C.byref(self.h)), "lrc_gather_create")
+        if self.is_host:
+            check(ctx.lib.lrc_gather_create_host(ctx.h, rank, world, bytes_per_rank, slots, host_shm.encode(), root, C.byref(self.h)),
+                  "lrc_gather_create_host")
+        else:
+            check(ctx.lib.lrc_gather_create(ctx.h, rank, world, bytes_per_rank, slots, C.byref(self.h)), "lrc_gather_create")
 
     def set_root(self, root: int):
         """root >= 0: only that rank receives (a gather); -1: every rank receives everything (the default)"""
@@ -581,6 +589,13 @@ class Gather:
         check(self.ctx.lib.lrc_gather_buffer(self.h, slot, C.byref(ptr), C.byref(stride)), "lrc_gather_buffer")
         es = torch.empty(0, dtype=dtype).element_size()
         assert stride.value % es == 0 and self.bytes_per_rank % es == 0
+        if self.is_host:
+            # host gather: the segment as a CPU tensor [world, elems_per_rank] (a view of the shared memory, no copy)
+            npdt = np.dtype(torch.empty(0, dtype=dtype).numpy().dtype)
+            raw = (C.c_uint8 * (self.world * stride.value)).from_address(ptr.value)
+            arr = np.frombuffer(raw, dtype=npdt).reshape(self.world, stride.value // es)
+            self._keep = raw
+            return torch.from_numpy(arr)[:, : self.bytes_per_rank // es]
         iface = {"shape": (self.world, stride.value // es), "typestr": np.dtype(torch.empty(0, dtype=dtype).numpy().dtype).str,
                  "data": (ptr.value, False), "version": 3}
         holder = type("_Buf", (), {"__cuda_array_interface__": iface})()

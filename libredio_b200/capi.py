@@ -113,6 +113,7 @@ SIGNATURES = {
     "lrc_eat": (_i, [_vp, _sz, _vp, _sz, _vp]),
     "lrc_ook_envelope_table": (_i, [_vp, _fp, _vp]),
     "lrc_gather_create": (_i, [_vp, _i, _i, _sz, _i, _pp]),
+    "lrc_gather_create_host": (_i, [_vp, _i, _i, _sz, _i, C.c_char_p, _i, _pp]),
     "lrc_gather_destroy": (_i, [_vp]),
     "lrc_gather_set_root": (_i, [_vp, _i]),
     "lrc_gather_handle_bytes": (_sz, []),

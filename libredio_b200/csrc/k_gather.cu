@@ -14,6 +14,11 @@
 // stream behind it with cuStreamWaitValue32 -- no host round trip, no collective.
 #include "common.cuh"
 #include <cuda.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <string>
 
 constexpr int GATHER_MAX_WORLD = 64;
 constexpr size_t GATHER_ALIGN = 256;
@@ -37,6 +42,12 @@ struct lrc_gather {
     uint32_t    *seq;                           // per slot: pushes issued so far
     write32_fn   write32;
     wait32_fn    wait32;
+    // host mode (lrc_gather_create_host): `base` is then the DEVICE alias of a page-locked POSIX shared-memory segment that
+    // every rank of the node maps; pushes are D2H copies into it
+    bool         is_host;
+    uint8_t     *host_base;                     // this process's mapping of the segment
+    std::string  shm_name;
+    bool         shm_owner;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -61,6 +72,7 @@ extern "C" int lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes
     lrc_gather *g = new (std::nothrow) lrc_gather();
     LRC_REQUIRE(g != nullptr, LRC_ERR_NOMEM, "out of host memory");
     g->ctx = ctx; g->rank = rank; g->world = world; g->slots = slots; g->root = -1;
+    g->is_host = false; g->host_base = nullptr; g->shm_owner = false;
     g->bytes_per_rank = bytes_per_rank;
     g->block_stride = align_up(bytes_per_rank, GATHER_ALIGN);
     g->slot_stride = g->block_stride * world;
@@ -105,6 +117,101 @@ extern "C" int lrc_gather_create(lrc_ctx *ctx, int rank, int world, size_t bytes
     return LRC_OK;
 }
 
+// Gather into HOST memory.  Measured at 8 GPUs (profiles/r2_u_bench_n8.json): rows pushed INTO a GPU that is running a
+// bandwidth-bound kernel cost that kernel 4.7 % -- 13 us as soon as anything arrives plus the NVLink time of every 4 MB burst,
+// with the peers idle, so it is the inbound traffic itself.  When the consumer of the rows is a CPU block anyway (the reference's
+// PSD rows end in vidsink / psdpng, kpn blocks on the host), the rows need not visit another GPU at all: every rank copies its
+// block D2H over ITS OWN PCIe link into one page-locked POSIX shared-memory segment [slot][src_rank][bytes] that all ranks of the
+// node map, and raises its flag word there with the same stream-ordered 32-bit write; the root orders a stream behind the flags
+// (lrc_gather_wait) or reads them from the CPU.  No GPU's HBM or NVLink port sees another rank's rows.
+// Rank `root` creates the segment (an existing one of that name is replaced), the others open it (retrying for up to 30 s).
+extern "C" int lrc_gather_create_host(lrc_ctx *ctx, int rank, int world, size_t bytes_per_rank, int slots, const char *shm_name,
+                                      int root, lrc_gather **out)
+{
+    LRC_BIND(ctx);
+    LRC_REQUIRE(out && shm_name && shm_name[0] == '/', LRC_ERR_INVALID, "lrc_gather_create_host: need out and a POSIX shm name \"/...\"");
+    LRC_REQUIRE(world >= 1 && world <= GATHER_MAX_WORLD && rank >= 0 && rank < world && root >= 0 && root < world, LRC_ERR_INVALID,
+                "lrc_gather_create_host: need 0 <= rank, root < world <= 64");
+    LRC_REQUIRE(slots >= 1 && slots <= 64 && bytes_per_rank > 0, LRC_ERR_INVALID,
+                "lrc_gather_create_host: need 1 <= slots <= 64 and bytes_per_rank > 0");
+    lrc_gather *g = new (std::nothrow) lrc_gather();
+    LRC_REQUIRE(g != nullptr, LRC_ERR_NOMEM, "out of host memory");
+    g->ctx = ctx; g->rank = rank; g->world = world; g->slots = slots; g->root = root;
+    g->is_host = true; g->host_base = nullptr; g->shm_name = shm_name; g->shm_owner = false; g->base = nullptr;
+    g->bytes_per_rank = bytes_per_rank;
+    g->block_stride = align_up(bytes_per_rank, GATHER_ALIGN);
+    g->slot_stride = g->block_stride * world;
+    g->flags_off = g->slot_stride * slots;
+    g->total_bytes = align_up(g->flags_off + align_up((size_t)slots * world * sizeof(uint32_t), GATHER_ALIGN), 4096);
+    g->connected = false;
+    for (int i = 0; i < GATHER_MAX_WORLD; ++i) { g->peer[i] = nullptr; g->opened[i] = false; }
+    g->push_stream = nullptr; g->ev_src = nullptr;
+    g->ev_sent = new cudaEvent_t[slots]();
+    g->seq = new uint32_t[slots]();
+    void *fw = nullptr, *fq = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &fw, cudaEnableDefault, &qr);
+    if (e == cudaSuccess) e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fq, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || !fw || !fq) {
+        lrc_gather_destroy(g);
+        lrc_set_error("lrc_gather_create_host: the driver does not export cuStreamWriteValue32/cuStreamWaitValue32");
+        return LRC_ERR_UNSUPPORTED;
+    }
+    g->write32 = reinterpret_cast<write32_fn>(fw);
+    g->wait32 = reinterpret_cast<wait32_fn>(fq);
+    int fd = -1;
+    if (rank == root) {
+        shm_unlink(shm_name);
+        fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, (off_t)g->total_bytes) != 0) { close(fd); fd = -1; shm_unlink(shm_name); }
+        g->shm_owner = fd >= 0;
+    } else {
+        for (int tries = 0; tries < 3000 && fd < 0; ++tries) {                 // the root may not have created it yet
+            fd = shm_open(shm_name, O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                if (fstat(fd, &st) != 0 || (size_t)st.st_size != g->total_bytes) { close(fd); fd = -1; }
+            }
+            if (fd < 0) usleep(10000);
+        }
+    }
+    if (fd < 0) {
+        lrc_set_error("lrc_gather_create_host: cannot %s shared memory %s (%zu bytes)", rank == root ? "create" : "open", shm_name, g->total_bytes);
+        lrc_gather_destroy(g);
+        return LRC_ERR_UNSUPPORTED;
+    }
+    void *m = mmap(nullptr, g->total_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+        lrc_set_error("lrc_gather_create_host: mmap of %s failed", shm_name);
+        lrc_gather_destroy(g);
+        return LRC_ERR_NOMEM;
+    }
+    g->host_base = static_cast<uint8_t *>(m);
+    if (rank == root) memset(g->host_base, 0, g->total_bytes);                 // flags start at 0 (ftruncate zero-fills; be explicit)
+    e = cudaHostRegister(g->host_base, g->total_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    void *dp = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dp, g->host_base, 0);
+    if (e != cudaSuccess) {
+        munmap(g->host_base, g->total_bytes); g->host_base = nullptr;          // never registered: destroy must not unregister
+        lrc_set_error("lrc_gather_create_host: cudaHostRegister -> %s", cudaGetErrorString(e));
+        lrc_gather_destroy(g);
+        return LRC_ERR_CUDA;
+    }
+    g->base = static_cast<uint8_t *>(dp);
+    e = cudaStreamCreateWithFlags(&g->push_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_src, cudaEventDisableTiming);
+    for (int s = 0; s < slots && e == cudaSuccess; ++s) e = cudaEventCreateWithFlags(&g->ev_sent[s], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        lrc_set_error("lrc_gather_create_host: %s", cudaGetErrorString(e));
+        lrc_gather_destroy(g);
+        return LRC_ERR_CUDA;
+    }
+    g->connected = true;                                                       // nothing to map: the segment IS the connection
+    *out = g;
+    return LRC_OK;
+}
+
 extern "C" int lrc_gather_destroy(lrc_gather *g)
 {
     if (!g) return LRC_OK;
@@ -115,7 +222,15 @@ extern "C" int lrc_gather_destroy(lrc_gather *g)
     for (int s = 0; s < g->slots; ++s) if (g->ev_sent && g->ev_sent[s]) cudaEventDestroy(g->ev_sent[s]);
     if (g->ev_src) cudaEventDestroy(g->ev_src);
     if (g->push_stream) cudaStreamDestroy(g->push_stream);
-    cudaFree(g->base);
+    if (g->is_host) {
+        if (g->host_base) {
+            cudaHostUnregister(g->host_base);
+            munmap(g->host_base, g->total_bytes);
+        }
+        if (g->shm_owner) shm_unlink(g->shm_name.c_str());
+    } else {
+        cudaFree(g->base);
+    }
     delete[] g->ev_sent;
     delete[] g->seq;
     delete g;
@@ -129,6 +244,7 @@ extern "C" int lrc_gather_export(lrc_gather *g, void *h_handle, size_t cap)
     LRC_REQUIRE(g && h_handle, LRC_ERR_INVALID, "lrc_gather_export: null argument");
     LRC_BIND(g->ctx);
     LRC_REQUIRE(cap >= sizeof(cudaIpcMemHandle_t), LRC_ERR_CAPACITY, "lrc_gather_export: handle buffer too small");
+    LRC_REQUIRE(!g->is_host, LRC_ERR_INVALID, "lrc_gather_export: a host gather has nothing to export (the shared-memory name is the handle)");
     cudaIpcMemHandle_t h;
     LRC_CUDA(cudaIpcGetMemHandle(&h, g->base));
     memcpy(h_handle, &h, sizeof(h));
@@ -184,6 +300,7 @@ extern "C" int lrc_gather_connect_local(lrc_gather *g, lrc_gather *const *all)
 extern "C" int lrc_gather_set_root(lrc_gather *g, int root)
 {
     LRC_REQUIRE(g && root >= -2 && root < g->world, LRC_ERR_INVALID, "lrc_gather_set_root: need -2 <= root < world");
+    LRC_REQUIRE(!g->is_host, LRC_ERR_INVALID, "lrc_gather_set_root: a host gather's receiver is fixed at creation");
     for (int s = 0; s < g->slots; ++s)
         LRC_REQUIRE(g->seq[s] == 0, LRC_ERR_INVALID, "lrc_gather_set_root: pushes were already issued");
     g->root = root;
@@ -209,6 +326,19 @@ extern "C" int lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void 
     const uint32_t seq = ++g->seq[slot];
     LRC_CUDA(cudaEventRecord(g->ev_src, lrc_stream(g->ctx, stream)));
     LRC_CUDA(cudaStreamWaitEvent(g->push_stream, g->ev_src, 0));
+    if (g->is_host) {
+        // one D2H copy over this GPU's own PCIe link into the shared segment, then the flag (both through the device alias)
+        LRC_CUDA(cudaMemcpyAsync(slot_block(g, g->host_base, slot, g->rank), d_src, g->bytes_per_rank, cudaMemcpyDeviceToHost,
+                                 g->push_stream));
+        const CUresult r = g->write32(reinterpret_cast<CUstream>(g->push_stream),
+                                      reinterpret_cast<CUdeviceptr>(flag_word(g, g->base, slot, g->rank)), seq, 0);
+        if (r != CUDA_SUCCESS) {
+            lrc_set_error("lrc_gather_push: cuStreamWriteValue32 to the host segment -> CUresult %d", (int)r);
+            return LRC_ERR_CUDA;
+        }
+        LRC_CUDA(cudaEventRecord(g->ev_sent[slot], g->push_stream));
+        return LRC_OK;
+    }
     for (int i = 0; i < g->world; ++i) {
         const int p = (g->rank + 1 + i) % g->world;          // start at the right-hand neighbour: spreads the NVSwitch ports
         if (g->root >= 0 && p != g->root) continue;
@@ -252,7 +382,7 @@ extern "C" int lrc_gather_wait(lrc_gather *g, int slot, void *stream)
 extern "C" int lrc_gather_buffer(lrc_gather *g, int slot, void **d_ptr, size_t *block_stride)
 {
     LRC_REQUIRE(g && d_ptr && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_buffer: bad argument");
-    *d_ptr = g->base + (size_t)slot * g->slot_stride;
+    *d_ptr = (g->is_host ? g->host_base : g->base) + (size_t)slot * g->slot_stride;     // host mode: a HOST pointer
     if (block_stride) *block_stride = g->block_stride;
     return LRC_OK;
 }

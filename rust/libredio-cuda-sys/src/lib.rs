@@ -145,6 +145,8 @@ extern "C" {
     // are sharded over several devices
     pub fn lrc_gather_create(ctx: *mut lrc_ctx, rank: c_int, world: c_int, bytes_per_rank: size_t, slots: c_int,
                              g: *mut *mut lrc_gather) -> c_int;
+    pub fn lrc_gather_create_host(ctx: *mut lrc_ctx, rank: c_int, world: c_int, bytes_per_rank: size_t, slots: c_int,
+                                  shm_name: *const c_char, root: c_int, g: *mut *mut lrc_gather) -> c_int;
     pub fn lrc_gather_destroy(g: *mut lrc_gather) -> c_int;
     pub fn lrc_gather_set_root(g: *mut lrc_gather, root: c_int) -> c_int;
     pub fn lrc_gather_handle_bytes() -> size_t;

@@ -145,3 +145,50 @@ def test_gather_to_one_root_only_that_rank_receives(ctx):
         gs[0].set_root(0)                                                # pushes were already issued
     for g in gs:
         g.close()
+
+
+def _host_gather_worker(rank, world, name, nbytes, q):
+    """one process per rank, all on cuda:0: the host gather needs no peer access, only the shared-memory segment"""
+    import numpy as np
+    import torch
+    from libredio_b200 import blocks
+    ctx = blocks.Context(0)
+    g = blocks.Gather(ctx, rank, world, nbytes, slots=2, host_shm=name, root=0)
+    n = nbytes // 4
+    for step in range(5):
+        b = step & 1
+        src = torch.full((n,), float(100 * step + rank), dtype=torch.float32, device=ctx.tdev)
+        g.wait_sent(b)
+        g.push(b, src)
+    if rank == 0:
+        for b in (0, 1):
+            g.wait(b)                                    # orders the current stream behind every rank's latest push of the slot
+        torch.cuda.synchronize()
+        last = {0: 4, 1: 3}                              # last step that pushed each slot
+        ok = all(bool((g.buffer(b)[r] == float(100 * last[b] + r)).all()) for b in (0, 1) for r in range(world))
+        q.put(ok)
+    else:
+        torch.cuda.synchronize()
+        q.put(True)
+    import time
+    time.sleep(0.5 if rank == 0 else 0.0)                # the root owns the segment: let the others finish first
+    g.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_gather_to_host_shared_memory_two_processes():
+    """lrc_gather_create_host: every rank copies its block D2H into one page-locked POSIX shared-memory segment and raises its
+    flag there; the root orders a stream behind the flags and reads all blocks from host memory"""
+    import multiprocessing as mp
+    import os
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    name = f"/lrc_test_gather_{os.getpid()}"
+    world, nbytes = 3, 1 << 20
+    ps = [mpc.Process(target=_host_gather_worker, args=(r, world, name, nbytes, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(res) and all(p.exitcode == 0 for p in ps)
