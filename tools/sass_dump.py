@@ -30,7 +30,7 @@ def main():
         if m:
             hist[m.group(1)] += 1
     with open(out, "w") as f:
-        f.write(f"// {name}\n// SASS of sm_100a build (cuobjdump -sass), round 1 session 8. Opcode histogram: "
+        f.write(f"// {name}\n// SASS of sm_100a build (cuobjdump -sass), Opcode histogram: "
                 + ", ".join(f"{k}:{v}" for k, v in hist.most_common(16)) + "\n")
         f.write("\n".join(keep) + "\n")
     print(out, len(keep), "instructions")
