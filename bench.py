@@ -464,12 +464,25 @@ def run_ours(args):
     if world > 1:
         ok = torch.zeros(1, device=dev)
         if args.gather == "ce":
+            # the host gather (diagnostic line, or the gather itself with --gather-to host) is set up on its own: a node without
+            # usable POSIX shared memory must not cost the run its NVLink gather.  Every collective below is reached by all ranks.
+            shm = [f"/lrc_bench_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}" if rank == 0 else None]
+            dist.broadcast_object_list(shm, src=0)
+            hok = torch.zeros(1, device=dev)
             try:
-                # the node's shared-memory segment for the host gather: one name for all ranks
-                shm = [f"/lrc_bench_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}" if rank == 0 else None]
-                dist.broadcast_object_list(shm, src=0)
                 gather_host = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2, host_shm=shm[0], root=0)
-                dist.barrier()
+                hok += 1
+            except Exception as e:
+                print(f"bench.py rank {rank}: host gather unavailable ({e})", file=sys.stderr)
+                gather_host = None
+            dist.all_reduce(hok)
+            if int(hok.item()) != world:
+                if gather_host is not None:
+                    gather_host.close()
+                gather_host = None
+                if args.gather_to == "host":
+                    args.gather_to = "root"
+            try:
                 gather_p2p = blocks.Gather(ctx, rank, world, rows * NFFT * 4, slots=2).connect_distributed()
                 gather = gather_host if args.gather_to == "host" else gather_p2p
                 if args.gather_to == "root":
@@ -690,7 +703,16 @@ def run_ours(args):
                 iso[pi] = float(res[0].item())
             if rank == 0:                                           # leave the slots consistent: nothing reads them after this
                 torch.cuda.synchronize()
-        diag = {"ms_per_step_host_gather_max_over_ranks": (float(th[0].item()) / args.steps) if th is not None else None,
+        # the loops above ran one after the other on GPUs held at their power cap: later loops run a little slower whatever they do
+        # (the clocks sag as the run goes on).  The main loop once more, last, shows how much of a difference is just that.
+        dist.barrier()
+        torch.cuda.synchronize()
+        rp_ms, rp_kern = timed_loop(True)
+        trp = torch.tensor([rp_ms, rp_kern], device=dev, dtype=torch.float64)
+        dist.all_reduce(trp, op=dist.ReduceOp.MAX)
+        diag = {"ms_per_step_main_loop_again_after_the_diagnostics": float(trp[0].item()) / args.steps,
+                "kernel_ms_main_loop_again_after_the_diagnostics": float(trp[1].item()),
+                "ms_per_step_host_gather_max_over_ranks": (float(th[0].item()) / args.steps) if th is not None else None,
                 "kernel_ms_host_gather_max_over_ranks": float(th[1].item()) if th is not None else None,
                 "kernel_ms_rank0_while_idle_peers_only_push": iso[0],
                 "kernel_ms_rank0_while_ONE_idle_peer_pushes": iso[1],
@@ -703,7 +725,10 @@ def run_ours(args):
                 "kernel_ms_rotating_receiver_max_over_ranks": float(tr[1].item()) if tr is not None else None,
                 "ms_per_step_rank0_alone_peers_idle": float(solo[0].item()),
                 "kernel_ms_rank0_alone_peers_idle": float(solo[1].item()),
-                "note": "kernel_ms_per_rank: only the RECEIVER of the gather runs a slower kernel (inbound P2P writes into an "
+                "note": "ORDER MATTERS: these loops run one after the other and the later ones are slower whatever they do (power-capped "
+                        "clocks sag during the run: compare main_loop_again with the bench line's ms_per_step); A/B claims come from "
+                        "separate bench.py runs with the mode under test as the main loop (profiles/r2_z_gather_ab_n8.txt).  "
+                        "kernel_ms_per_rank: only the RECEIVER of the gather runs a slower kernel (inbound P2P writes into an "
                         "HBM-saturated GPU); ms_per_step - ms_per_step_without_gather = what the gather costs in all; the all-gather and "
                         "rotating-receiver lines are the same loop with the receiver placed differently; without_gather - rank0_alone "
                         "= what running next to busy peers costs"}
@@ -885,9 +910,10 @@ def main():
     ap.add_argument("--quick-extra", action="store_true", dest="quick_extra", help="extra block at 1/8 size (smoke runs)")
     ap.add_argument("--gather-probe-s", type=float, default=30.0, dest="gather_probe_s",
                     help="N > 1: seconds the lrc_gather connectivity probe may take before falling back to NCCL")
-    ap.add_argument("--gather-to", default="root", choices=["root", "all", "rotate", "host"], dest="gather_to",
-                    help="N > 1: who receives the output rows: rank 0's GPU (a gather, default), every rank (all-gather), a "
-                         "receiver that rotates from step to step, or the node's host memory (a CPU consumer on rank 0)")
+    ap.add_argument("--gather-to", default="host", choices=["host", "root", "all", "rotate"], dest="gather_to",
+                    help="N > 1: who receives the output rows: the node's host memory (default: the consumer of PSD rows is a CPU "
+                         "block in the reference -- vidsink / psdpng -- and rows pushed into a computing GPU cost its kernel 4.7 %%), "
+                         "rank 0's GPU (a gather over NVLink), every rank (all-gather), or a receiver that rotates from step to step")
     ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
                     help="N > 1: output gather by lrc_gather (copy engines over NVLink, default) or NCCL all-gather")
     args = ap.parse_args()
