@@ -345,6 +345,9 @@ int    lrc_gather_push(lrc_gather *g, int slot, const void *d_src, void *stream)
 int    lrc_gather_wait_sent(lrc_gather *g, int slot, void *stream);
 /* order `stream` behind the ARRIVAL of every rank's latest push into this rank's `slot` */
 int    lrc_gather_wait(lrc_gather *g, int slot, void *stream);
+/* host gather only: block the calling CPU thread until every rank's latest push into `slot` has arrived, at most timeout_ms
+ * (LRC_ERR_CAPACITY on timeout) -- for consumer blocks that run on the CPU and have no stream to order behind the flags */
+int    lrc_gather_wait_host(lrc_gather *g, int slot, unsigned timeout_ms);
 int    lrc_gather_buffer(lrc_gather *g, int slot, void **d_ptr, size_t *block_stride);
 
 #ifdef __cplusplus

@@ -583,6 +583,10 @@ class Gather:
     def wait(self, slot: int):
         check(self.ctx.lib.lrc_gather_wait(self.h, slot, _stream()), "lrc_gather_wait")
 
+    def wait_host(self, slot: int, timeout_ms: int = 10000):
+        """host gather: block this CPU thread until every rank's latest push into the slot has arrived"""
+        check(self.ctx.lib.lrc_gather_wait_host(self.h, slot, timeout_ms), "lrc_gather_wait_host")
+
     def buffer(self, slot: int, dtype=torch.float32) -> torch.Tensor:
         """The slot's receive buffer as a [world, elems_per_rank] tensor view (no copy)."""
         ptr, stride = C.c_void_p(), C.c_size_t()

@@ -115,6 +115,7 @@ SIGNATURES = {
     "lrc_gather_create": (_i, [_vp, _i, _i, _sz, _i, _pp]),
     "lrc_gather_create_host": (_i, [_vp, _i, _i, _sz, _i, C.c_char_p, _i, _pp]),
     "lrc_gather_destroy": (_i, [_vp]),
+    "lrc_gather_wait_host": (_i, [_vp, _i, C.c_uint]),
     "lrc_gather_set_root": (_i, [_vp, _i]),
     "lrc_gather_handle_bytes": (_sz, []),
     "lrc_gather_export": (_i, [_vp, _vp, _sz]),

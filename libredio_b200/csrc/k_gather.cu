@@ -18,6 +18,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <time.h>
 #include <string>
 
 constexpr int GATHER_MAX_WORLD = 64;
@@ -377,6 +378,36 @@ extern "C" int lrc_gather_wait(lrc_gather *g, int slot, void *stream)
         }
     }
     return LRC_OK;
+}
+
+// Host gather only: block the CALLING CPU THREAD until every rank's latest push into `slot` has arrived (the flag words live in
+// the shared host segment; a push writes its flag after its copy in stream order), or until timeout_ms have passed
+// (LRC_ERR_CAPACITY then: nothing is wrong yet, the rows are just not there).  For consumer blocks that run on the CPU and have
+// no CUDA stream to order behind the flags.
+extern "C" int lrc_gather_wait_host(lrc_gather *g, int slot, unsigned timeout_ms)
+{
+    LRC_REQUIRE(g && slot >= 0 && slot < g->slots, LRC_ERR_INVALID, "lrc_gather_wait_host: bad slot");
+    LRC_REQUIRE(g->is_host, LRC_ERR_INVALID, "lrc_gather_wait_host: not a host gather");
+    const uint32_t seq = g->seq[slot];
+    if (seq == 0) return LRC_OK;
+    const volatile uint32_t *flags = reinterpret_cast<const volatile uint32_t *>(flag_word(g, g->host_base, slot, 0));
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned spins = 0;; ++spins) {
+        bool all = true;
+        for (int p = 0; p < g->world; ++p) all = all && (int32_t)(flags[p] - seq) >= 0;
+        if (all) { __sync_synchronize(); return LRC_OK; }
+        if ((spins & 1023u) == 1023u) {
+            struct timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+            if (ms > (double)timeout_ms) {
+                lrc_set_error("lrc_gather_wait_host: slot %d: not every rank's push %u arrived within %u ms", slot, seq, timeout_ms);
+                return LRC_ERR_CAPACITY;
+            }
+            usleep(50);
+        }
+    }
 }
 
 extern "C" int lrc_gather_buffer(lrc_gather *g, int slot, void **d_ptr, size_t *block_stride)

@@ -148,6 +148,7 @@ extern "C" {
     pub fn lrc_gather_create_host(ctx: *mut lrc_ctx, rank: c_int, world: c_int, bytes_per_rank: size_t, slots: c_int,
                                   shm_name: *const c_char, root: c_int, g: *mut *mut lrc_gather) -> c_int;
     pub fn lrc_gather_destroy(g: *mut lrc_gather) -> c_int;
+    pub fn lrc_gather_wait_host(g: *mut lrc_gather, slot: c_int, timeout_ms: c_uint) -> c_int;
     pub fn lrc_gather_set_root(g: *mut lrc_gather, root: c_int) -> c_int;
     pub fn lrc_gather_handle_bytes() -> size_t;
     pub fn lrc_gather_export(g: *mut lrc_gather, h_handle: *mut c_void, cap: size_t) -> c_int;

@@ -161,9 +161,9 @@ def _host_gather_worker(rank, world, name, nbytes, q):
         g.wait_sent(b)
         g.push(b, src)
     if rank == 0:
-        for b in (0, 1):
-            g.wait(b)                                    # orders the current stream behind every rank's latest push of the slot
+        g.wait(0)                                        # slot 0: order the current stream behind every rank's latest push ...
         torch.cuda.synchronize()
+        g.wait_host(1, 20000)                            # ... slot 1: a CPU consumer polls the flag words in the shared segment
         last = {0: 4, 1: 3}                              # last step that pushed each slot
         ok = all(bool((g.buffer(b)[r] == float(100 * last[b] + r)).all()) for b in (0, 1) for r in range(world))
         q.put(ok)
