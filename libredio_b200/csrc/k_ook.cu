@@ -261,10 +261,11 @@ __device__ __forceinline__ void tma_load_box3(uint32_t dst_s, const CUtensorMap 
 }
 
 // envelope of one sorted 16-bit key through the folded table; flut_adj = shared address of the table minus
-// 4 OOK_FOLD_MIN.  Pipe balance is the point (the triangular lookup had 5.5 ALU-pipe instructions per sample): the
-// negation and the skew k2 + (k2 >> 5) are written so that ptxas keeps them on the FMA pipe -- the skew as
-// mad.hi by 2^27 + 1 (floor(k2 (2^27 + 1) / 2^32) = k2 >> 5 for k2 < 2^16; with the plain 2^27 ptxas turns it into
-// an ALU-pipe LEA.HI) -- which leaves the fused add-max (VIADDMNMX) and the address LEA on the ALU pipe.
+// 4 OOK_FOLD_MIN.  The negation runs on the FMA pipe (IMAD.MOV), the fused add-max (VIADDMNMX) and the address LEA on the ALU
+// pipe.  The skew k2 + (k2 >> 5) has two forms: SKEW_FMA writes it as mad.hi by 2^27 + 1 (floor(k2 (2^27 + 1) / 2^32) = k2 >> 5
+// for k2 < 2^16; with the plain 2^27 ptxas turns it into an LEA.HI) to keep it on the FMA pipe, but IMAD.HI adds into a 64-bit
+// register pair whose low half has to be zeroed for every use -- one more instruction per sample, and the kernel is bound by
+// issue slots (81 % busy), not by the ALU pipe alone: the plain LEA.HI form measured 10 % faster and is the default.
 template <bool SKEW_FMA>
 __device__ __forceinline__ float flut_envelope(uint32_t flut_adj, uint32_t key)
 {
@@ -925,9 +926,9 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     cudaStream_t s = lrc_stream(o->ctx, stream);
     const size_t groups = ((o->n_blocks + 31) / 32) * o->n_streams;
     const size_t cap = (size_t)o->ctx->n_sm;           // one persistent CTA per SM (the table fills its shared memory)
-    // LRC_OOK_KA: 0 = round-1 kernel (triangular table, cp.async slabs), 1 = folded table + TMA slabs 16 warps x 2 stages
-    // (default), 2 = the same with 8 warps x 4 stages, 3 = like 1 with the table skew on the ALU pipe (LEA.HI).  A/B knob; all produce
-    // identical bits.
+    // LRC_OOK_KA: 3 (default) = folded table + TMA slabs, 16 warps x 2 stages, table skew as one LEA.HI (ALU pipe): 0.825 ms for the
+    // whole chain; 1 = the same with the skew as IMAD.HI (FMA pipe, needs a zeroed pair register per use: 0.913 ms); 2 = like 1 with
+    // 8 warps x 4 stages (1.001 ms); 0 = the round-1 kernel (triangular table, cp.async slabs: 0.893 ms).  A/B knob; identical bits.
     static const int ka = getenv("LRC_OOK_KA") ? atoi(getenv("LRC_OOK_KA")) : 3;
     if (ka == 0) {
         size_t blocks = ceil_div(groups, (size_t)KA_WARPS);
