@@ -467,7 +467,6 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     bool lead0 = true;                        // the buffer currently starts with that 0.0
     float cur_max = 0.0f;
     uint32_t burst = 0;                       // index of the burst being collected
-    uint32_t open_from = 0xffffffffu;         // first tagged block of the burst being collected (none yet)
     bool dropped = false;                     // the OOM guard abandoned a burst of this stream
     if (!walker) {
         stage(0);
@@ -510,7 +509,7 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                     if (buf_len > 1000u * OOK_TRIGGER_DURATION * OOK_BLOCK) {
                         if (burst < max_bursts) flags[burst] = 0;
                         burst += 1; dropped = true;
-                        buf_len = 1; lead0 = true; cur_max = 0.0f; open_from = 0xffffffffu;
+                        buf_len = 1; lead0 = true; cur_max = 0.0f;
                     }
                     // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
                     // candidate sums exist before the select -- and the fire test s > threshold * 4 (:68-70) is made as
@@ -525,16 +524,14 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                     const bool collect = trigger > 1;                                   // :73-75 push_all
                     buf_len += collect ? (uint32_t)OOK_BLOCK : 0u;
                     cur_max = collect ? fmaxf(cur_max, mr[k]) : cur_max;
-                    const bool tagged = collect && burst < max_bursts;
-                    t_tag[u] = tagged ? (int32_t)burst : -1;
-                    open_from = tagged ? min(open_from, (uint32_t)(b0 + u)) : open_from;
+                    t_tag[u] = (collect && burst < max_bursts) ? (int32_t)burst : -1;
                     if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
                         if (burst < max_bursts) {
                             half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
                             flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
                         }
                         burst += 1;
-                        buf_len = 0; lead0 = false; cur_max = 0.0f; open_from = 0xffffffffu;
+                        buf_len = 0; lead0 = false; cur_max = 0.0f;
                     }
                 }
             }
@@ -542,21 +539,76 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
         __syncthreads();
     }
     if (!walker) tags_out(n_tiles - 1);
-    __syncthreads();                          // all tags are in global memory
-    if (!live) return;
-    // a burst still open when the capture ends is never sent: its blocks (at most the tail of the capture) are un-tagged,
-    // and so are -- in one pass over the stream's tags, which only a capture that tripped the OOM guard pays for -- the
-    // blocks of the bursts the guard abandoned (flag bit 0 clear).  The slicer only ever sees blocks of bursts that were sent.
-    int32_t *tag = d_tag + st * n_blocks;
-    if (burst < max_bursts) flags[burst] = 0;
-    if (open_from != 0xffffffffu)
-        for (size_t k = open_from; k < n_blocks; ++k) if (tag[k] == (int32_t)burst) tag[k] = -1;
-    if (dropped)
-        for (size_t k = 0; k < n_blocks; ++k) {
-            const int32_t tg = tag[k];
-            if (tg >= 0 && !(flags[tg] & 1u)) tag[k] = -1;
+    // a burst still open when the capture ends is never sent: its blocks (at most the tail of the capture) are un-tagged, and so
+    // are -- in one pass over the stream's tags, which only a capture that tripped the OOM guard pays for -- the blocks of the
+    // bursts the guard abandoned (flag bit 0 clear).  The slicer only ever sees blocks of bursts that were sent.  The whole CTA
+    // does it, a stream at a time with coalesced accesses, and it simply looks for the index of the burst that was never sent (the
+    // walk itself carries no "first block of this burst" bookkeeping: every instruction in it is latency on the chain).
+    uint32_t *s_open = reinterpret_cast<uint32_t *>(s_q[0]);         // [32] 1 = live stream, [32] index of its unsent burst,
+    if (live) {                                                       // [32] guard fired -- s_q is free after the last tile
+        if (burst < max_bursts) flags[burst] = 0;
+        d_nbursts[st] = burst;                // may exceed max_bursts -> reported by fetch
+    }
+    __syncthreads();                          // all tags are in global memory, s_q is no longer read
+    if (walker) {
+        s_open[tid] = live ? 1u : 0u;
+        s_open[32 + tid] = burst;
+        s_open[64 + tid] = live && dropped ? 1u : 0u;
+    }
+    __syncthreads();
+    // The unsent burst's blocks end within the last two blocks of the capture (it is still being collected, or the counter just
+    // reached 1) and lie at most one block apart.  Each warp takes eight streams: the last 64 tags of all eight are loaded first
+    // (independent loads, one latency), matched and cleared; a run longer than that (rare) is followed backwards chunk by chunk.
+    {
+        const int w = tid >> 5;
+        int32_t t0[8], t1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = w * 8 + j;
+            const size_t s = st0 + r;
+            const long long k0 = (long long)n_blocks - 1 - lane, k1 = k0 - 32;
+            const bool on = s < n_streams && s_open[r];
+            t0[j] = on && k0 >= 0 ? d_tag[s * n_blocks + k0] : -1;
+            t1[j] = on && k1 >= 0 ? d_tag[s * n_blocks + k1] : -1;
         }
-    d_nbursts[st] = burst;                    // may exceed max_bursts -> reported by fetch
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = w * 8 + j;
+            const size_t s = st0 + r;
+            if (s >= n_streams || !s_open[r]) continue;               // warp-uniform
+            int32_t *tag = d_tag + s * n_blocks;
+            const int32_t bidx = (int32_t)s_open[32 + r];
+            const long long k0 = (long long)n_blocks - 1 - lane, k1 = k0 - 32;
+            const bool m0 = t0[j] == bidx, m1 = t1[j] == bidx;
+            if (m0) tag[k0] = -1;
+            if (m1) tag[k1] = -1;
+            // the burst reaches past the 64 tags: keep going while a chunk of 32 still holds one of its blocks (a burst may skip
+            // single blocks -- the block at counter 1 is not collected, a re-fire on the next one continues the burst -- so a
+            // chunk without any of its blocks is the end)
+            long long k = k1 - 32;
+            bool more = __any_sync(0xffffffffu, m1);
+            while (more && __any_sync(0xffffffffu, k >= 0)) {
+                const bool m = k >= 0 && tag[k] == bidx;
+                if (m) tag[k] = -1;
+                more = __any_sync(0xffffffffu, m);
+                k -= 32;
+            }
+        }
+    }
+    // bursts the OOM guard abandoned: one pass over the stream's tags, which only a capture that tripped the guard pays for
+    for (int r = 0; r < KB_STREAMS; ++r) {
+        const size_t s = st0 + r;
+        if (s >= n_streams) break;
+        if (s_open[64 + r]) {
+            __syncthreads();                  // uniform: s_open is the same for every thread
+            int32_t *tag = d_tag + s * n_blocks;
+            const uint8_t *fl = d_bflags + s * max_bursts;
+            for (size_t k = tid; k < n_blocks; k += KB_THREADS) {
+                const int32_t tg = tag[k];
+                if (tg >= 0 && !(fl[tg] & 1u)) tag[k] = -1;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -90,7 +90,8 @@ def test_ook_decodes_known_packets_bit_exact(ctx):
     assert sum(len(x) for x in sent) == len(pk) > 16
 
 
-@pytest.mark.parametrize("case", ["noise_only", "loud_noise", "ragged_blocks", "all_zero", "saturated", "burst_at_end"])
+@pytest.mark.parametrize("case", ["noise_only", "loud_noise", "ragged_blocks", "all_zero", "saturated", "burst_at_end",
+                                  "long_gapped_burst_at_end", "gapped_bursts_sent"])
 def test_ook_edge_cases_match_oracle(ctx, case):
     rng = np.random.default_rng(hash(case) % 1000)
     if case == "noise_only":
@@ -103,6 +104,25 @@ def test_ook_edge_cases_match_oracle(ctx, case):
         caps = [np.zeros(64 * 1024, np.uint8), np.full(64 * 1024, 127, np.uint8)]
     elif case == "saturated":
         caps = [np.full(200 * 1024, 255, np.uint8), rng.integers(0, 256, 200 * 1024, dtype=np.uint8)]
+    elif case in ("long_gapped_burst_at_end", "gapped_bursts_sent"):
+        # one loud block every 50: the counter reaches 1 (that block is NOT collected) and the next block re-fires, so the burst
+        # goes on with single-block holes in it (bitfount.rs:68-75).  Open at the end of the capture: 250+ blocks to un-tag,
+        # with holes; or followed by silence: the same bursts are sent and sliced.
+        def quiet(n):
+            return np.clip(np.rint(127 + 1.5 * rng.standard_normal(n * 1024)), 0, 255).astype(np.uint8)
+        def loud(n):
+            return np.clip(np.rint(127 + 60 * rng.standard_normal(n * 1024)), 0, 255).astype(np.uint8)
+        caps = []
+        for s in range(3):
+            parts = [quiet(100 + s)]
+            for _ in range(5 + s):
+                parts += [loud(1), quiet(49)]
+            parts += [loud(1), quiet(20 if case == "long_gapped_burst_at_end" else 120)]
+            caps.append(np.concatenate(parts))
+        n = min(c.size for c in caps) // 1024 * 1024
+        caps = [c[:n] for c in caps]
+        r0 = oracle.ook_decode(caps[0])                       # the construction does what it says: nothing sent / one holed burst
+        assert (r0["bits"].size == 0) if case == "long_gapped_burst_at_end" else (r0["n_bursts"] == 1 and r0["bits"].size == 294 * 512 + 1)
     else:                           # a burst still open when the capture ends is never sent (bitfount.rs:78-81)
         iq, _ = synth.ook_capture_u8(500, seed=90, n_packets=1)
         iq = iq.copy(); iq[-40 * 1024:] = np.clip(np.rint(127 + 90 * rng.standard_normal(40 * 1024)), 0, 255).astype(np.uint8)
