@@ -127,6 +127,7 @@ struct lrc_ook {
     lrc_ctx *ctx;
     size_t   n_streams, n_blocks, max_runs, max_packets, max_bursts;
     unsigned sample_rate;
+    uint32_t guard_samples;           // bitfount.rs:52 1000 * trigger_duration * block_size (LRC_OOK_TEST_GUARD_BLOCKS: a test hook)
     float    *d_sum, *d_max;          // [n_streams][n_blocks]
     int32_t  *d_tag;                  // [n_streams][n_blocks] burst index the block is collected into, -1 = none
     float    *d_half;                 // [n_streams][max_bursts]  max/2 of the burst
@@ -407,8 +408,8 @@ constexpr int KB_LD = KB_TILE + 1;            // conflict-free both ways: helper
 
 __global__ void __launch_bounds__(KB_THREADS)
 ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_max, size_t n_streams,
-                   size_t n_blocks, size_t max_bursts, int32_t *__restrict__ d_tag, float *__restrict__ d_half,
-                   uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
+                   size_t n_blocks, size_t max_bursts, uint32_t guard_samples, int32_t *__restrict__ d_tag,
+                   float *__restrict__ d_half, uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
 {
     __shared__ float s_sum[3][KB_STREAMS * KB_LD];
     __shared__ float s_max[3][KB_STREAMS * KB_LD];
@@ -502,11 +503,10 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                     const float s = sr[k];                                              // :48
                     // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps; no fixture reaches it): what
                     // was collected is dropped -- the burst index is abandoned with its flag clear -- and collection goes on
-                    // in a fresh buffer [0.0].  KNOWN DEVIATION in one corner: when the guard fires with trigger == 1, the
-                    // reference sends the reset buffer [0.0] at the next block (a burst of one 0 bit); here that burst has no
-                    // tagged block and contributes no bit, so transition positions after it are one lower than the
-                    // reference's.  DESIGN.md section 7.
-                    if (buf_len > 1000u * OOK_TRIGGER_DURATION * OOK_BLOCK) {
+                    // in a fresh buffer [0.0].  When the guard fires with trigger == 1 nothing is pushed after the reset and the
+                    // next block sends the buffer [0.0] as it is: a sent burst (flags 3, max/2 = 0) without a tagged block, which
+                    // the slicer turns into its one 0 bit (lone_zero_bursts in ook_rle_kernel).
+                    if (buf_len > guard_samples) {
                         if (burst < max_bursts) flags[burst] = 0;
                         burst += 1; dropped = true;
                         buf_len = 1; lead0 = true; cur_max = 0.0f;
@@ -668,7 +668,7 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
                size_t max_bursts, size_t max_runs, const uint16_t *__restrict__ g_rank,
                const int32_t *__restrict__ d_tag,
                const float *__restrict__ d_half, const float *__restrict__ uniq, uint32_t n_uniq,
-               const uint8_t *__restrict__ d_bflags,
+               const uint8_t *__restrict__ d_bflags, const uint32_t *__restrict__ d_nbursts,
                uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans, uint32_t *__restrict__ d_nbits)
 {
     extern __shared__ __align__(16) uint16_t kc_rank[];
@@ -690,8 +690,21 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
     int32_t cur_burst = -1;
     uint32_t h = 0;              // rank threshold of the current burst
     // one collected block: 16 samples per lane -> bit mask -> transitions appended in order
+    // a burst that was SENT without a single collected block: the OOM guard (:52-54) reset the buffer to [0.0] on the block where
+    // the trigger counter stood at 1, nothing was pushed, and the next block sent that lone 0.0 (:78-81) -- one 0 bit
+    // (0.0 > 0.0 / 2 is false).  No tag points at such a burst, so the walk picks them up from the flags of the burst indices
+    // it steps over (flags == 3: sent, leading 0.0; an abandoned burst has bit 0 clear and contributes nothing).
+    auto lone_zero_bursts = [&](int32_t from, int32_t to) {
+        for (int32_t j = from; j < to; ++j) {
+            if ((flags[j] & 3u) == 3u) {
+                if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }
+                prev = 0u; pos += 1;
+            }
+        }
+    };
     auto process = [&](int32_t tg, const uint4 &q0, const uint4 &q1) {
         if (tg != cur_burst) {
+            lone_zero_bursts(cur_burst + 1, tg);
             cur_burst = tg;
             h = warp_upper_bound(uniq, n_uniq, half[tg], lane);
             if (flags[tg] & 2u) {
@@ -777,53 +790,60 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
             for (int i = 0; i < PF; ++i) { kA[i] = kB[i]; dA[i][0] = dB[i][0]; dA[i][1] = dB[i][1]; }
         }
     }
+    {
+        const uint32_t nbu = d_nbursts[st];
+        lone_zero_bursts(cur_burst + 1, (int32_t)(nbu < max_bursts ? nbu : max_bursts));
+    }
     if (lane == 0) { d_ntrans[st] = ntr; d_nbits[st] = pos; }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K-D: dle + matchers + shaper_optional, one thread per stream
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool in_rng(float d, float lo, float hi) { return d >= lo && d <= hi; }
 
-struct Shaper {
+// The pulse-pair matchers of ratpak.rs:88-97 (looper bodies) and shaper_optional (kpn.rs:266-275), one run at a time.
+// Lane 0 runs protocol A and lane 1 protocol B in the same warp, so the two state machines are written as ONE instruction
+// stream of selects over per-protocol constants (as branches the lanes would take turns, and every run costs a reconvergence):
+//   idle      : run value 1 with a duration in [a1lo, a1hi] or [a2lo, a2hi] starts a pair (the FOLLOWING run is consumed,
+//               `a.next().unwrap()`), anything else is None for the shaper
+//   pair open : the run must be a 0 with a duration in [s1lo, s1hi] or [s2lo, s2hi]: Some(bit), bit = "second range" for
+//               protocol A (:91-92), d > e for protocol B (:96); anything else None
+//   shaper    : Some(y) => push; None => the collected bits are sent iff there are exactly `want` of them, then cleared.
+// A pulse still pending when the runs end: the reference block dies in unwrap() with nothing sent.
+struct Matcher {
+    float a1lo, a1hi, a2lo, a2hi, s1lo, s1hi, s2lo, s2hi;
+    bool  proto_b;
+    bool  pending; float d;
     unsigned long long acc; uint32_t n, want, count;
     unsigned long long *out; size_t cap;
-    __device__ void feed(int opt)
+    __device__ __forceinline__ void init(int proto, unsigned long long *o, size_t c)
     {
-        if (opt >= 0) {                          // Some(y) => x.push(y)
-            if (n < 64) acc = (acc << 1) | (unsigned long long)opt;
-            n++;
-        } else {                                 // None if x.len() == l => send; None => clear
-            if (n == want) { if (count < cap) out[count] = acc; count++; }
-            n = 0; acc = 0;
-        }
+        proto_b = proto != 0;
+        a1lo = proto_b ? 125e-6f : 2e-4f;  a1hi = proto_b ? 250e-6f : 6e-4f;                 // ratpak.rs:91 / :96, first run
+        a2lo = proto_b ? 500e-6f : 1.0f;   a2hi = proto_b ? 650e-6f : 0.0f;                  // (A has no second range: empty)
+        s1lo = proto_b ? 500e-6f : 1.5e-3f; s1hi = proto_b ? 650e-6f : 2.5e-3f;              // second run
+        s2lo = proto_b ? 125e-6f : 3.5e-3f; s2hi = proto_b ? 250e-6f : 4.5e-3f;
+        pending = false; d = 0.0f; acc = 0ull; n = 0u; want = proto_b ? 24u : 36u; count = 0u; out = o; cap = c;
     }
-};
-
-// one run at a time through the pulse-pair matchers of ratpak.rs:88-97 (looper bodies) and shaper_optional
-struct Matcher {
-    int proto; bool pending; float d; Shaper sh;
-    __device__ void feed(uint32_t v, float dur)
+    __device__ __forceinline__ void feed(uint32_t v, float dur)
     {
-        if (!pending) {
-            bool first;
-            if (proto == 0) first = (v == 1u) && in_rng(dur, 2e-4f, 6e-4f);                                         // ratpak.rs:91
-            else first = (v == 1u) && (in_rng(dur, 125e-6f, 250e-6f) || in_rng(dur, 500e-6f, 650e-6f));            // :96
-            if (!first) sh.feed(-1);
-            else { pending = true; d = dur; }
-            return;
+        const bool first_ok = v == 1u && ((dur >= a1lo && dur <= a1hi) || (dur >= a2lo && dur <= a2hi));
+        const bool r1 = dur >= s1lo && dur <= s1hi, r2 = dur >= s2lo && dur <= s2hi;
+        const bool second_ok = v == 0u && (r1 || r2);
+        const uint32_t bit = proto_b ? (d > dur ? 1u : 0u) : (r1 ? 0u : 1u);
+        const bool push = pending && second_ok;
+        const bool none = pending ? !second_ok : !first_ok;
+        d = pending ? d : dur;                                    // only read while a pair is open
+        pending = !pending && first_ok;
+        // Some(y) => x.push(y)
+        const unsigned long long pushed = (acc << 1) | (unsigned long long)bit;
+        acc = push && n < 64u ? pushed : acc;
+        n += push ? 1u : 0u;
+        // None if x.len() == l => send; None => clear
+        if (none) {
+            if (n == want) { if (count < cap) out[count] = acc; count++; }
+            n = 0u; acc = 0ull;
         }
-        pending = false;                                    // a.next().unwrap(): the following run is consumed
-        const float e = dur;
-        if (proto == 0) {
-            if (v == 0u && in_rng(e, 1.5e-3f, 2.5e-3f)) sh.feed(0);
-            else if (v == 0u && in_rng(e, 3.5e-3f, 4.5e-3f)) sh.feed(1);
-            else sh.feed(-1);
-        } else {
-            if (v == 0u && (in_rng(e, 500e-6f, 650e-6f) || in_rng(e, 125e-6f, 250e-6f))) sh.feed(d > e ? 1 : 0);
-            else sh.feed(-1);
-        }
-        // a pulse still pending when the runs end: the reference block dies in unwrap() with nothing sent
     }
 };
 
@@ -846,8 +866,8 @@ ook_match_kernel(const uint32_t *__restrict__ d_trans, const uint32_t *__restric
     if (nr > max_runs) nr = (uint32_t)max_runs;           // overflow is reported by fetch
     // run k: value = k & 1 (the stream starts with the 0 bit of vec!(0.0)), length = tr[k] - tr[k-1]
     uint32_t *dbg = d_runs_dbg + st * max_runs;
-    Matcher mt{lane, false, 0.0f,
-               Shaper{0ull, 0u, lane == 0 ? 36u : 24u, 0u, d_packets + (st * 2 + (lane & 1)) * max_packets, max_packets}};
+    Matcher mt;
+    mt.init(lane & 1, d_packets + (st * 2 + (lane & 1)) * max_packets, max_packets);
     float *dur = s_dur[warp];
     for (uint32_t k0 = 0; k0 < nr; k0 += KD_CHUNK) {
         const uint32_t nk = nr - k0 < (uint32_t)KD_CHUNK ? nr - k0 : (uint32_t)KD_CHUNK;
@@ -862,7 +882,7 @@ ook_match_kernel(const uint32_t *__restrict__ d_trans, const uint32_t *__restric
             for (uint32_t i = 0; i < nk; ++i) mt.feed((k0 + i) & 1u, dur[i]);
         __syncwarp();
     }
-    if (lane < 2) d_npackets[st * 2 + lane] = mt.sh.count;
+    if (lane < 2) d_npackets[st * 2 + lane] = mt.count;
 }
 
 __global__ void ook_envelope_table_kernel(float *__restrict__ table)
@@ -886,7 +906,15 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     o->ctx = ctx; o->n_streams = n_streams; o->n_blocks = n_blocks; o->sample_rate = sample_rate;
     o->max_runs = max_runs ? max_runs : 4096;
     o->max_packets = max_packets ? max_packets : 64;
-    o->max_bursts = n_blocks / 49 + 2;                    // a burst is at least 49 collected blocks
+    // bitfount.rs:52 `1000*trigger_duration*block_size`.  LRC_OOK_TEST_GUARD_BLOCKS shrinks it (in blocks) so that a test can reach
+    // the guard with a capture of a few hundred blocks instead of 50 000; the oracle has the same hook (orc_test_set_trigger_guard)
+    size_t guard_blocks = 1000u * (size_t)OOK_TRIGGER_DURATION;
+    if (const char *g = getenv("LRC_OOK_TEST_GUARD_BLOCKS")) { const long v = atol(g); if (v >= 1) guard_blocks = (size_t)v; }
+    o->guard_samples = (uint32_t)(guard_blocks * OOK_BLOCK);
+    // a sent burst is at least 49 collected blocks, except the pieces the guard cuts one into (an abandoned burst of more than
+    // guard_blocks blocks followed by its remainder, possibly empty): at least guard_blocks / 2 blocks per index on average
+    const size_t min_burst = std::min<size_t>(49, std::max<size_t>(1, guard_blocks / 2));
+    o->max_bursts = n_blocks / min_burst + 2;
     const size_t sb = n_streams * n_blocks;
     cudaError_t e = cudaSuccess;
 #define OOK_ALLOC(ptr, count) if (e == cudaSuccess) e = cudaMalloc(&o->ptr, (count) * sizeof(*o->ptr))
@@ -1024,13 +1052,13 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     }
     LRC_CUDA(cudaGetLastError());
     ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_STREAMS), KB_THREADS, 0, s>>>(
-        o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
+        o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->guard_samples, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
     LRC_CUDA(cudaGetLastError());
     size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
     if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
     ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
         d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
-        o->d_uniq, o->n_uniq, o->d_bflags, o->d_trans, o->d_ntrans, o->d_nbits);
+        o->d_uniq, o->n_uniq, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
     LRC_CUDA(cudaGetLastError());
     ook_match_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KD_WARPS), KD_WARPS * 32, 0, s>>>(
         o->d_trans, o->d_ntrans, o->n_streams, o->max_runs, o->max_packets, (float)o->sample_rate, o->d_packets,

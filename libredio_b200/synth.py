@@ -143,3 +143,32 @@ def ook_capture_u8(n_blocks: int, seed: int = 4, n_packets: int = 2, noise_lsb: 
     iq[0::2] = i
     iq[1::2] = q
     return np.clip(np.rint(iq), 0, 255).astype(np.uint8), sent
+
+
+def ook_guard_capture_u8(loud_blocks: int, seed: int = 0, before: bool = True, after: bool = True, tail_quiet: int = 80):
+    """A capture that drives bitfount::trigger's OOM guard (bitfount.rs:52-54) once its constant is shrunk by the test hooks
+    (oracle.set_trigger_guard_blocks / LRC_OOK_TEST_GUARD_BLOCKS): a quiet floor, optionally a short loud burst (3 blocks,
+    sent 48 blocks later), then `loud_blocks` blocks that every one re-fire the trigger (the threshold is frozen while
+    triggered, :62-65), optionally another short burst, and a quiet tail.  The long stretch collects loud_blocks + 48 blocks:
+    with a guard of G blocks it is cut into abandoned pieces of G + 1 blocks, and when loud_blocks + 48 == G exactly the guard
+    fires on the block where the counter stands at 1 -- nothing is pushed and the NEXT block sends the reset buffer [0.0]."""
+    rng = np.random.default_rng(seed)
+
+    def quiet(n):
+        return np.clip(np.rint(127 + 1.5 * rng.standard_normal(n * 2 * OOK_BLOCK)), 0, 255).astype(np.uint8)
+
+    def loud(n):
+        # pulsed inside every block, so the slicer has transitions to place after the guard moved the bit positions
+        x = 127 + 60 * rng.standard_normal(n * 2 * OOK_BLOCK)
+        gate = (np.arange(n * 2 * OOK_BLOCK) // 128) % 2 == 0
+        return np.clip(np.rint(np.where(gate, x, 127 + 1.5 * rng.standard_normal(n * 2 * OOK_BLOCK))), 0, 255).astype(np.uint8)
+
+    parts = [quiet(100)]
+    if before:
+        parts += [loud(3), quiet(70)]
+    parts += [loud(loud_blocks), quiet(70)]
+    if after:
+        parts += [loud(3), quiet(70)]
+    parts += [quiet(tail_quiet)]
+    return np.concatenate(parts)
+

@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         L.orc_ook_decode.restype = C.c_int
         L.orc_ook_decode.argtypes = [vp, sz, C.c_uint, C.POINTER(_OokResult)]
         L.orc_ook_free.argtypes = [C.POINTER(_OokResult)]
+        L.orc_test_set_trigger_guard.argtypes = [sz]
+        L.orc_test_set_trigger_guard.restype = None
         L.orc_b2d.restype = sz
         L.orc_b2d.argtypes = [vp, sz]
         L.orc_eat.argtypes = [vp, vp, sz, vp]
@@ -217,6 +219,14 @@ def eat(bits, widths) -> list:
     out = np.empty(w.size, dtype=np.uint64)
     lib().orc_eat(_ptr(bits), _ptr(w), w.size, _ptr(out))
     return [int(v) for v in out]
+
+
+def set_trigger_guard_blocks(blocks: int) -> None:
+    """Test hook: shrink the trigger's OOM guard (bitfount.rs:52, 50 000 blocks) to `blocks` blocks in the C restatement and the
+    pure-Python one; 0 restores the reference's constant.  The CUDA side has LRC_OOK_TEST_GUARD_BLOCKS."""
+    from . import restated_py
+    lib().orc_test_set_trigger_guard(int(blocks) * 512)
+    restated_py.TEST_GUARD_SAMPLES = int(blocks) * 512
 
 
 def ook_decode(iq: np.ndarray, s_rate: int = 256000) -> dict:

@@ -368,6 +368,12 @@ void orc_trigger_init(orc_trigger *t)
 }
 void orc_trigger_free(orc_trigger *t) { free(t->buf); t->buf = NULL; t->len = t->cap = 0; }
 
+/* Test hook: the OOM guard of bitfount.rs:52 is `1000*trigger_duration*block_size` = 25.6 M samples (100 s of capture).  A parity
+ * test of the guard path shrinks it ON BOTH SIDES (here and LRC_OOK_TEST_GUARD_BLOCKS in the CUDA library); 0 restores the
+ * reference's constant. */
+static size_t g_trigger_guard_samples = 0;
+void orc_test_set_trigger_guard(size_t samples) { g_trigger_guard_samples = samples; }
+
 int orc_trigger_block(orc_trigger *t, const float *samples, size_t n, float **burst,
                       size_t *burst_len, float *block_sum_out)
 {
@@ -377,7 +383,8 @@ int orc_trigger_block(orc_trigger *t, const float *samples, size_t n, float **bu
     float s = 0.0f;                               /* :48 sum(), sequential from 0.0 */
     for (size_t i = 0; i < n; ++i) s = s + samples[i];
     if (block_sum_out) *block_sum_out = s;
-    if (t->len > 1000u * (size_t)trigger_duration * block_size) {   /* :52-54 */
+    const size_t guard = g_trigger_guard_samples ? g_trigger_guard_samples : 1000u * (size_t)trigger_duration * block_size;
+    if (t->len > guard) {                         /* :52-54 */
         t->buf[0] = 0.0f; t->len = 1;
     }
     if (t->threshold == 0.0f) t->threshold = s;   /* :57-59 */

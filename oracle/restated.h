@@ -76,6 +76,7 @@ typedef struct {
 } orc_trigger;
 void   orc_trigger_init(orc_trigger *t);
 void   orc_trigger_free(orc_trigger *t);
+void   orc_test_set_trigger_guard(size_t samples);   /* test hook, 0 = the reference's 1000*50*512 */
 /* returns 1 and hands out the burst (*burst malloc'd, caller frees) when a burst is sent */
 int    orc_trigger_block(orc_trigger *t, const float *samples, size_t n, float **burst,
                          size_t *burst_len, float *block_sum_out);

@@ -80,9 +80,13 @@ def cross_applicator_vecs(src, f):
         yield [f(*x) for x in v]
 
 
+TEST_GUARD_SAMPLES = 0      # test hook: non-zero replaces the OOM guard's 1000*trigger_duration*BLOCK (bitfount.rs:52) on this side
+
+
 def trigger(src):
     """bitfount.rs:36-85, statement by statement"""
     trigger_duration = 50
+    guard = TEST_GUARD_SAMPLES if TEST_GUARD_SAMPLES else 1000 * trigger_duration * BLOCK
     trig = 0
     sample_buffer = [F(0.0)]
     threshold = F(0.0)
@@ -91,7 +95,7 @@ def trigger(src):
         s = F(0.0)
         for x in samples:                                   # iter().sum(): left fold from 0.0
             s = F(s + x)
-        if len(sample_buffer) > 1000 * trigger_duration * BLOCK:
+        if len(sample_buffer) > guard:
             sample_buffer = [F(0.0)]
         if threshold == F(0.0):
             threshold = s

@@ -273,6 +273,27 @@ def test_ook_chain_two_independent_restatements_agree_bit_for_bit(seed, n_blocks
         assert len(sent) - 1 <= a["a_packets"].shape[0] + a["b_packets"].shape[0] <= len(sent)
 
 
+@pytest.mark.parametrize("loud,before", [(72, False), (73, True), (200, True)])
+def test_ook_chain_restatements_agree_on_the_oom_guard_path(loud, before):
+    """bitfount.rs:52-54 with the guard shrunk to 120 blocks in both restatements (the reference's 50 000 blocks would need 100 s
+    of capture): abandoned pieces, the remainder sent with a leading 0.0, and -- loud + 48 collected blocks == the guard -- the
+    reset buffer [0.0] sent on its own as a single 0 bit."""
+    from oracle import restated_py as P
+    from libredio_b200 import synth
+    iq = synth.ook_guard_capture_u8(loud, seed=loud, before=before, after=True)
+    oracle.set_trigger_guard_blocks(120)
+    try:
+        a, b = oracle.ook_decode(iq), P.ook_decode(iq)
+    finally:
+        oracle.set_trigger_guard_blocks(0)
+    _same(a, b)
+    if loud != 200:
+        assert a["bits"].size == (2 if before else 1) * (51 * 512 + 1), "the lone 0 bit is there (the other +1: vec!(0.0) of the first burst)"
+    full = oracle.ook_decode(iq)                             # the reference's constant: a capture this short never reaches it,
+    if loud != 200:                                          # the stretch is sent whole instead of its reset buffer
+        assert full["bits"].size == a["bits"].size - 1 + (loud + 48) * 512 + (0 if before else 1)      # + its own vec!(0.0)
+
+
 def test_ook_chain_restatements_agree_on_unstructured_input():
     """not packets: amplitude steps and noise bursts that drive the threshold arithmetic (bitfount.rs:57-70) through
     re-triggers, a burst still open at the end of the capture and runs spanning burst boundaries"""

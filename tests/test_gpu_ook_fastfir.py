@@ -131,6 +131,36 @@ def test_ook_edge_cases_match_oracle(ctx, case):
     check_against_oracle(caps, pk, dbg)
 
 
+def test_ook_oom_guard_path_matches_oracle_with_the_guard_shrunk_on_both_sides(ctx, monkeypatch):
+    """bitfount.rs:52-54: a buffer longer than 1000*50*512 samples is thrown away and collection restarts from [0.0].  The real
+    constant needs 100 s of capture per stream, so the test shrinks it to 120 blocks in the oracle AND in the plan (test hooks on
+    both sides) and drives every way through the guard: a long loud stretch cut into abandoned pieces whose remainder is sent with
+    a leading 0.0; the guard firing exactly on the block where the counter stands at 1, after which the reference sends the
+    lone [0.0] -- one 0 bit, first, between and after ordinary bursts; several firings in one stretch."""
+    guard = 120
+    cases = [(L, bf, af) for L in (60, 71, 72, 73, 74, 200, 400) for bf in (True, False) for af in (True, False)]
+    caps = [synth.ook_guard_capture_u8(L, seed=1000 + i, before=bf, after=af) for i, (L, bf, af) in enumerate(cases)]
+    n = max(c.size for c in caps)
+    rng = np.random.default_rng(5)
+    caps = [np.concatenate([c, np.clip(np.rint(127 + 1.5 * rng.standard_normal(n - c.size)), 0, 255).astype(np.uint8)]) for c in caps]
+    monkeypatch.setenv("LRC_OOK_TEST_GUARD_BLOCKS", str(guard))
+    oracle.set_trigger_guard_blocks(guard)
+    try:
+        # the construction reaches the corner: the whole output of these two captures is the lone 0 bit / two 51-block bursts + 2
+        lone = oracle.ook_decode(caps[cases.index((72, False, False))])
+        assert lone["n_bursts"] == 1 and lone["bits"].size == 1
+        mid = oracle.ook_decode(caps[cases.index((73, True, True))])
+        assert mid["n_bursts"] == 3 and mid["bits"].size == 2 * 51 * 512 + 2
+        pk, dbg = run_ook(ctx, caps, max_runs=1 << 15)
+        check_against_oracle(caps, pk, dbg)
+    finally:
+        oracle.set_trigger_guard_blocks(0)
+    # and with the reference's constant the same captures never reach the guard: both sides agree there too
+    monkeypatch.delenv("LRC_OOK_TEST_GUARD_BLOCKS")
+    pk, dbg = run_ook(ctx, caps[:6], max_runs=1 << 18)
+    check_against_oracle(caps[:6], pk, dbg)
+
+
 @pytest.mark.parametrize("n_blocks", [1, 5, 31, 32, 33, 65])
 def test_ook_captures_shorter_than_a_warp_group(ctx, n_blocks):
     """the block-sum kernel's TMA box is 32 blocks tall: captures with fewer blocks (and a ragged second group) rely on the
