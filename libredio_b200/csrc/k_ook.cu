@@ -142,6 +142,11 @@ struct lrc_ook {
     float    *d_lut;                  // triangular envelope table, OOK_LUT_N floats (LRC_OOK_KA=0 variant)
     float    *d_flut;                 // folded envelope table, OOK_FLUT_N floats (default block-sum kernel)
     void     *encode_tiled;           // cuTensorMapEncodeTiled (driver entry point, fetched once)
+    uint16_t *d_mask;                 // [n_streams][n_blocks][32] slicer output of collected blocks, 512 bits each (split K-C)
+    uint32_t *d_hrank;                // [n_streams][max_bursts] rank threshold of a sent burst (split K-C)
+    uint32_t *d_next;                 // [1] next (stream, group) the slice kernel hands out
+    uint32_t *d_bsum;                 // [n_streams][n_blocks] {inner transitions, first bit, last bit} of a collected block
+    uint4    *d_binfo;                // [n_streams][n_blocks] place of a collected block in the bit stream and the transition list
     uint16_t *d_rank;                 // [65536] rank of the pair's envelope among the distinct envelope values
     float    *d_uniq;                 // [n_uniq] the distinct envelope values, ascending
     uint32_t  n_uniq;
@@ -400,11 +405,12 @@ ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams,
 // one __syncthreads per tile.  A burst that is dropped (the OOM guard :52-54, or still open when the capture ends) keeps bit 0
 // of its flag clear and has its blocks un-tagged once all tags are in global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp
+constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp (and of the keeper warp)
 constexpr int KB_HELPERS = 96;                // helper threads (three warps)
-constexpr int KB_THREADS = KB_STREAMS + KB_HELPERS;
+constexpr int KB_THREADS = 2 * KB_STREAMS + KB_HELPERS;
 constexpr int KB_TILE = 32;                   // blocks per staged tile
 constexpr int KB_LD = KB_TILE + 1;            // conflict-free both ways: helpers move rows, the walker reads columns
+constexpr int KB_CLD = KB_TILE + 4;           // bytes per stream in a tile of codes: 9 words, lanes 9 banks apart
 
 __global__ void __launch_bounds__(KB_THREADS)
 ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_max, size_t n_streams,
@@ -412,22 +418,30 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                    float *__restrict__ d_half, uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
 {
     __shared__ float s_sum[3][KB_STREAMS * KB_LD];
-    __shared__ float s_max[3][KB_STREAMS * KB_LD];
+    __shared__ float s_max[4][KB_STREAMS * KB_LD];
     __shared__ float s_q[2][KB_STREAMS * KB_LD];
     __shared__ int32_t s_tag[2][KB_STREAMS * KB_LD];
+    __shared__ __align__(4) uint8_t s_code[2][KB_STREAMS * KB_CLD];
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t st0 = (size_t)blockIdx.x * KB_STREAMS;
     const int n_tiles = (int)((n_blocks + KB_TILE - 1) / KB_TILE);
+    // Round-2 split of the walk: the reference's statements fall into a CHAIN -- threshold and trigger counter (:46, :57-70), each
+    // block's values needing the previous block's -- and BOOK-KEEPING that only reads the counter (:52-54 guard, :73-81 collect and
+    // send: buffer length, burst index, running maximum, tags).  The walker warp (threads 0-31) runs the chain alone and leaves one
+    // byte per block {counter > 1, counter == 0}; the keeper warp (threads 32-63, same lane = same stream) does the book-keeping
+    // one tile behind from those bytes.  Neither warp carries the other's instructions on its dependent-issue path.
     const bool walker = tid < KB_STREAMS;
-    const int ht = tid - KB_STREAMS, hwarp = ht >> 5;                  // helpers: 3 warps, warp w moves rows w, w + 3, ...
-    // cp.async (LDGSTS) of tile `tile` into its buffer: a helper warp moves 32 consecutive floats of one stream per step
+    const bool keeper = tid >= KB_STREAMS && tid < 2 * KB_STREAMS;
+    const bool helper = tid >= 2 * KB_STREAMS;
+    const int ht = tid - 2 * KB_STREAMS, hwarp = ht >> 5;              // helpers: 3 warps, warp w moves rows w, w + 3, ...
+    // cp.async (LDGSTS) of tile `tile` into its buffers: a helper warp moves 32 consecutive floats of one stream per step.  Sums
+    // are read by the walker in the tile's own iteration (3 buffers), maxima by the keeper one iteration later (4 buffers).
     auto stage = [&](int tile) {
         if (tile < n_tiles) {
-            const int buf = tile % 3;
             const size_t b = (size_t)tile * KB_TILE + lane;
             for (int r = hwarp; r < KB_STREAMS; r += KB_HELPERS / 32) {
                 const size_t s = st0 + r;
-                float *ds = &s_sum[buf][r * KB_LD + lane], *dm = &s_max[buf][r * KB_LD + lane];
+                float *ds = &s_sum[tile % 3][r * KB_LD + lane], *dm = &s_max[tile & 3][r * KB_LD + lane];
                 if (s < n_streams && b < n_blocks) {
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(ds)), "l"(d_sum + s * n_blocks + b) : "memory");
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dm)), "l"(d_max + s * n_blocks + b) : "memory");
@@ -457,19 +471,21 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
             if (s < n_streams && b < n_blocks) d_tag[s * n_blocks + b] = src[r * KB_LD + lane];
         }
     };
-    // walker state (one stream per lane)
-    const size_t st = st0 + tid;
-    const bool live = walker && st < n_streams;
+    // one stream per lane, in the walker and in the keeper
+    const size_t st = st0 + lane;
+    const bool live = (walker || keeper) && st < n_streams;
     float *half = d_half + st * max_bursts;
     uint8_t *flags = d_bflags + st * max_bursts;
+    // walker state
     int trigger = 0;                          // :41 (isize there; |trigger| <= n_blocks here)
     float threshold = 0.0f;                   // :44
-    uint32_t buf_len = 1;                     // :43 sample_buffer = vec!(0.0); capped at 25.6 M + 512 by the guard below
+    // keeper state
+    uint32_t buf_len = 1;                     // :43 sample_buffer = vec!(0.0); capped at the guard + 512 below
     bool lead0 = true;                        // the buffer currently starts with that 0.0
     float cur_max = 0.0f;
     uint32_t burst = 0;                       // index of the burst being collected
     bool dropped = false;                     // the OOM guard abandoned a burst of this stream
-    if (!walker) {
+    if (helper) {
         stage(0);
         stage(1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");            // tile 0 has landed (this thread's part)
@@ -477,83 +493,122 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
         quotients(0);
     }
     __syncthreads();
-    for (int tile = 0; tile < n_tiles; ++tile) {
-        if (!walker) {
+    // iteration i: helpers tile i + 1 / i + 2 in, tile i - 2 out; walker tile i; keeper tile i - 1
+    for (int tile = 0; tile <= n_tiles; ++tile) {
+        if (helper) {
             asm volatile("cp.async.wait_all;" ::: "memory");            // tile + 1 (issued an iteration ago)
             named_bar_sync(1, KB_HELPERS);                              // ... every helper's part of it
             quotients(tile + 1);
-            tags_out(tile - 1);
-            stage(tile + 2);                                            // its buffer was last read in iteration tile - 1
-        } else if (live) {
-            const float *t_sum = s_sum[tile % 3] + tid * KB_LD, *t_max = s_max[tile % 3] + tid * KB_LD;
-            const float *t_q = s_q[tile & 1] + tid * KB_LD;
-            int32_t *t_tag = s_tag[tile & 1] + tid * KB_LD;
-            const size_t b0 = (size_t)tile * KB_TILE;
-            const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
-            for (int u0 = 0; u0 < nb; u0 += 8) {
-                // the block's inputs do not depend on the chain: eight blocks ahead into registers
-                float sr[8], qr[8], mr[8];
+            tags_out(tile - 2);
+            stage(tile + 2);                                            // sums: last read in iteration tile - 1; maxima: tile - 1's
+        } else if (walker) {                                            // buffer is (tile + 3) & 3, not this one
+            if (live && tile < n_tiles) {
+                const float *t_sum = s_sum[tile % 3] + lane * KB_LD;
+                const float *t_q = s_q[tile & 1] + lane * KB_LD;
+                uint32_t *t_code = reinterpret_cast<uint32_t *>(s_code[tile & 1] + lane * KB_CLD);
+                const size_t b0 = (size_t)tile * KB_TILE;
+                const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
+                for (int u0 = 0; u0 < nb; u0 += 8) {
+                    // the block's inputs do not depend on the chain: eight blocks ahead into registers
+                    float sr[8], qr[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { sr[k] = t_sum[u0 + k]; qr[k] = t_q[u0 + k]; mr[k] = t_max[u0 + k]; }
+                    for (int k = 0; k < 8; ++k) { sr[k] = t_sum[u0 + k]; qr[k] = t_q[u0 + k]; }
+                    uint32_t code[2] = {0u, 0u};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        // (blocks past the end of a ragged last tile are walked too: their zero sums change nothing the keeper reads,
+                        // and the walker's state is not used after the last tile)
+                        trigger -= 1;                                                       // :46
+                        const float s = sr[k];                                              // :48
+                        // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
+                        // candidate sums exist before the select -- and the fire test s > threshold * 4 (:68-70) is made as
+                        // s / 4 > threshold with s / 4 taken off the chain: both scalings by a power of two are exact (s is 0 or
+                        // >= 0.0078, the smallest non-zero envelope), so the comparison is the same one
+                        const bool unset = threshold == 0.0f;                               // :57-59
+                        const float thr0 = unset ? s : threshold;
+                        const float thr1 = unset ? __fadd_rn(s, qr[k]) : __fadd_rn(threshold, qr[k]);   // :62-65
+                        const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
+                        threshold = trigger < 0 ? thr2 : thr0;
+                        trigger = __fmul_rn(s, 0.25f) > threshold ? OOK_TRIGGER_DURATION : trigger;  // :68-70
+                        // what the keeper needs of the counter: collect (:73) and send (:78)
+                        const uint32_t c = (trigger > 1 ? 1u : 0u) | (trigger == 0 ? 2u : 0u);
+                        code[k >> 2] |= c << (8 * (k & 3));
+                    }
+                    t_code[(u0 >> 2)] = code[0];
+                    t_code[(u0 >> 2) + 1] = code[1];
+                }
+            }
+        } else if (tile >= 1) {                                         // keeper, one tile behind
+            // All 32 lanes walk (a lane without a stream reads whatever its row of codes holds and stores nothing outside shared
+            // memory), so the two rare events -- the guard and the end of a burst -- can sit behind warp-uniform votes and the
+            // common block is a dozen selects.  First version of the split: both events as per-lane branches, 87 instructions per
+            // block with the reconvergence points, and the keeper -- not the chain -- set the kernel's duration (ncu source page:
+            // 500 of a warp's 600 samples in the keeper, 110 in the walker).
+            const int kt = tile - 1;
+            const float *t_max = s_max[kt & 3] + lane * KB_LD;
+            const uint32_t *t_code = reinterpret_cast<const uint32_t *>(s_code[kt & 1] + lane * KB_CLD);
+            int32_t *t_tag = s_tag[kt & 1] + lane * KB_LD;
+            const size_t b0 = (size_t)kt * KB_TILE;
+            const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
+            const uint32_t mb = (uint32_t)(max_bursts < 0x7fffffffull ? max_bursts : 0x7fffffffull);
+            for (int u0 = 0; u0 < nb; u0 += 8) {
+                float mr[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mr[k] = t_max[u0 + k];
+                const uint32_t code[2] = {t_code[u0 >> 2], t_code[(u0 >> 2) + 1]};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int u = u0 + k;
                     if (u >= nb) break;
-                    trigger -= 1;                                                       // :46
-                    const float s = sr[k];                                              // :48
-                    // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps; no fixture reaches it): what
-                    // was collected is dropped -- the burst index is abandoned with its flag clear -- and collection goes on
-                    // in a fresh buffer [0.0].  When the guard fires with trigger == 1 nothing is pushed after the reset and the
-                    // next block sends the buffer [0.0] as it is: a sent burst (flags 3, max/2 = 0) without a tagged block, which
-                    // the slicer turns into its one 0 bit (lone_zero_bursts in ook_rle_kernel).
-                    if (buf_len > guard_samples) {
-                        if (burst < max_bursts) flags[burst] = 0;
-                        burst += 1; dropped = true;
-                        buf_len = 1; lead0 = true; cur_max = 0.0f;
+                    const uint32_t c = (code[k >> 2] >> (8 * (k & 3))) & 3u;
+                    // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps): what was collected is dropped -- the
+                    // burst index is abandoned with its flag clear -- and collection goes on in a fresh buffer [0.0].  When the
+                    // guard fires with the counter at 1 nothing is pushed after the reset and the next block sends the buffer [0.0]
+                    // as it is: a sent burst (flags 3, max/2 = 0) without a tagged block, which the slicer turns into its one 0 bit.
+                    const bool over = buf_len > guard_samples;
+                    if (__any_sync(0xffffffffu, over)) {
+                        if (over) {
+                            if (live && burst < mb) flags[burst] = 0;
+                            burst += 1; dropped = true;
+                            buf_len = 1; lead0 = true; cur_max = 0.0f;
+                        }
                     }
-                    // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
-                    // candidate sums exist before the select -- and the fire test s > threshold * 4 (:68-70) is made as
-                    // s / 4 > threshold with s / 4 taken off the chain: both scalings by a power of two are exact (s is 0 or
-                    // >= 0.0078, the smallest non-zero envelope), so the comparison is the same one
-                    const bool unset = threshold == 0.0f;                               // :57-59
-                    const float thr0 = unset ? s : threshold;
-                    const float thr1 = unset ? __fadd_rn(s, qr[k]) : __fadd_rn(threshold, qr[k]);   // :62-65
-                    const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
-                    threshold = trigger < 0 ? thr2 : thr0;
-                    trigger = __fmul_rn(s, 0.25f) > threshold ? OOK_TRIGGER_DURATION : trigger;  // :68-70
-                    const bool collect = trigger > 1;                                   // :73-75 push_all
+                    const bool collect = (c & 1u) != 0u;                                // :73-75 push_all
                     buf_len += collect ? (uint32_t)OOK_BLOCK : 0u;
                     cur_max = collect ? fmaxf(cur_max, mr[k]) : cur_max;
-                    t_tag[u] = (collect && burst < max_bursts) ? (int32_t)burst : -1;
-                    if (trigger == 0) {                                                 // :78-81 send, buffer = vec!()
-                        if (burst < max_bursts) {
-                            half[burst] = __fdiv_rn(cur_max, 2.0f);                     // discretize :90-91 max/2f32
-                            flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                    t_tag[u] = (collect && burst < mb) ? (int32_t)burst : -1;
+                    const bool send = (c & 2u) != 0u;                                   // :78-81 send, buffer = vec!()
+                    if (__any_sync(0xffffffffu, send)) {
+                        if (send && live && burst < mb) {
+                            half[burst] = __fmul_rn(cur_max, 0.5f);                     // discretize :90-91 max/2f32 (x / 2 == x * 0.5:
+                            flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));           // the same real number, rounded once)
                         }
-                        burst += 1;
-                        buf_len = 0; lead0 = false; cur_max = 0.0f;
+                        burst += send ? 1u : 0u;
+                        buf_len = send ? 0u : buf_len;
+                        lead0 = send ? false : lead0;
+                        cur_max = send ? 0.0f : cur_max;
                     }
                 }
             }
         }
         __syncthreads();
     }
-    if (!walker) tags_out(n_tiles - 1);
+    if (helper) tags_out(n_tiles - 1);
     // a burst still open when the capture ends is never sent: its blocks (at most the tail of the capture) are un-tagged, and so
     // are -- in one pass over the stream's tags, which only a capture that tripped the OOM guard pays for -- the blocks of the
     // bursts the guard abandoned (flag bit 0 clear).  The slicer only ever sees blocks of bursts that were sent.  The whole CTA
     // does it, a stream at a time with coalesced accesses, and it simply looks for the index of the burst that was never sent (the
     // walk itself carries no "first block of this burst" bookkeeping: every instruction in it is latency on the chain).
     uint32_t *s_open = reinterpret_cast<uint32_t *>(s_q[0]);         // [32] 1 = live stream, [32] index of its unsent burst,
-    if (live) {                                                       // [32] guard fired -- s_q is free after the last tile
+    if (keeper && live) {                                             // [32] guard fired -- s_q is free after the last tile
         if (burst < max_bursts) flags[burst] = 0;
         d_nbursts[st] = burst;                // may exceed max_bursts -> reported by fetch
     }
     __syncthreads();                          // all tags are in global memory, s_q is no longer read
-    if (walker) {
-        s_open[tid] = live ? 1u : 0u;
-        s_open[32 + tid] = burst;
-        s_open[64 + tid] = live && dropped ? 1u : 0u;
+    if (keeper) {
+        s_open[lane] = live ? 1u : 0u;
+        s_open[32 + lane] = burst;
+        s_open[64 + lane] = live && dropped ? 1u : 0u;
     }
     __syncthreads();
     // The unsent burst's blocks end within the last two blocks of the capture (it is still being collected, or the counter just
@@ -567,7 +622,7 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
             const int r = w * 8 + j;
             const size_t s = st0 + r;
             const long long k0 = (long long)n_blocks - 1 - lane, k1 = k0 - 32;
-            const bool on = s < n_streams && s_open[r];
+            const bool on = r < KB_STREAMS && s < n_streams && s_open[r];
             t0[j] = on && k0 >= 0 ? d_tag[s * n_blocks + k0] : -1;
             t1[j] = on && k1 >= 0 ? d_tag[s * n_blocks + k1] : -1;
         }
@@ -575,7 +630,7 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
         for (int j = 0; j < 8; ++j) {
             const int r = w * 8 + j;
             const size_t s = st0 + r;
-            if (s >= n_streams || !s_open[r]) continue;               // warp-uniform
+            if (r >= KB_STREAMS || s >= n_streams || !s_open[r]) continue;     // warp-uniform
             int32_t *tag = d_tag + s * n_blocks;
             const int32_t bidx = (int32_t)s_open[32 + r];
             const long long k0 = (long long)n_blocks - 1 - lane, k1 = k0 - 32;
@@ -798,6 +853,297 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
 }
 
 // ---------------------------------------------------------------------------------------------
+// K-C, split form (default): the same slicer + rle as ook_rle_kernel in three kernels, so that nothing heavy is tied to the walk
+// along a stream.  ook_rle_kernel gives a stream to ONE warp, which reads and slices its collected blocks one after the other:
+// 4096 streams keep 28 warps per SM busy, but the kernel is bound by the latency of that walk (long-scoreboard 2.7 per issue),
+// and a shard of 512 streams (4096 streams over 8 GPUs) leaves three warps per SM walking for just as long.  Here
+//   C1 ook_slice_kernel   : every (stream, group of 32 blocks) is an independent unit of work (grid-stride, one CTA per SM beside
+//                           the rank table): collected blocks -> 512-bit masks (64 B per block) and a summary word per block
+//                           {transitions between its own bits, first bit, last bit};
+//   C2 ook_scan_kernel    : one warp per stream, 32 blocks per step with warp scans: bits inserted before a block (the 0.0 of
+//                           vec!(0.0) that leads a burst, lone [0.0] bursts), position of every block in the flattened bit stream,
+//                           index of its first entry in the transition list, transition at its first bit -- 20 bytes per block in,
+//                           16 out, no sample is touched;
+//   C3 ook_scatter_kernel : every (stream, group) independent again: blocks that hold a transition write them at their place.
+// Same transition list, bit for bit, as ook_rle_kernel (LRC_OOK_KC=0 keeps that kernel for A/B runs).
+// ---------------------------------------------------------------------------------------------
+constexpr int KC1_WARPS = 28;
+constexpr uint32_t KC_SUM_FIRST = 1u << 30, KC_SUM_LAST = 1u << 31, KC_SUM_CNT = 0x3ffu;
+
+// bit i of the result: sample i of the lane's 16 (32 contiguous bytes) has rank >= h, i.e. x > max/2f32 (bitfount.rs:91)
+__device__ __forceinline__ uint32_t kc_slice16(uint32_t rank_s, uint32_t hm1, const uint4 &q0, const uint4 &q1)
+{
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t raw0 = w[i] & 0xffffu, raw1 = __umulhi(w[i], 65536u);        // w >> 16 on the FMA pipe
+        const uint32_t a0 = rank_s + 2u * (raw0 + (raw0 >> 5)), a1 = rank_s + 2u * (raw1 + (raw1 >> 5));
+        unsigned short r0, r1;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r0) : "r"(a0));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r1) : "r"(a1));
+        m = __funnelshift_l(hm1 - (uint32_t)r0, m, 1);                   // rank >= h  <=>  (h - 1) - rank < 0: the sign bit
+        m = __funnelshift_l(hm1 - (uint32_t)r1, m, 1);
+    }
+    return __brev(m) >> 16;                                              // bits arrive reversed: sample i -> bit i
+}
+
+// transitions BETWEEN the 512 bits of one block (lane l holds bits 16 l .. 16 l + 15): bit i of the result is set when sample
+// 16 l + i differs from the one before it; the block's very first bit is left out (it depends on what precedes the block)
+__device__ __forceinline__ uint32_t kc_inner_transitions(uint32_t m, int lane)
+{
+    const uint32_t pb = __shfl_up_sync(0xffffffffu, m >> 15, 1) & 1u;
+    uint32_t tm = (m ^ ((m << 1) | pb)) & 0xffffu;
+    if (lane == 0) tm &= ~1u;
+    return tm;
+}
+
+// C0: a burst's max/2 as a rank threshold  #{distinct envelope values <= max/2}  (see ook_rle_kernel), one warp per (stream, burst)
+constexpr int KC0_WARPS = 8;
+__global__ void __launch_bounds__(KC0_WARPS * 32)
+ook_rankthr_kernel(size_t n_streams, size_t max_bursts, const float *__restrict__ d_half, const uint8_t *__restrict__ d_bflags,
+                   const uint32_t *__restrict__ d_nbursts, const float *__restrict__ uniq, uint32_t n_uniq,
+                   uint32_t *__restrict__ d_hrank, uint32_t *__restrict__ d_next, uint32_t next_init)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_next = next_init;         // the slice kernel's group counter (it runs after this one)
+    if (w >= n_streams * max_bursts) return;
+    const size_t st = w / max_bursts, j = w % max_bursts;
+    const uint32_t nbu = d_nbursts[st], fl = d_bflags[w];                // three independent loads: one latency (slots past the
+    const float hv = d_half[w];                                          // stream's last burst hold stale values, never used)
+    if (j >= nbu || !(fl & 1u)) return;                                  // never sent: no block carries its index
+    const uint32_t h = warp_upper_bound(uniq, n_uniq, hv, lane);
+    if (lane == 0) d_hrank[w] = h;
+}
+
+__global__ void __launch_bounds__(KC1_WARPS * 32, 1)
+ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks, size_t max_bursts,
+                 const uint16_t *__restrict__ g_rank, const int32_t *__restrict__ d_tag, const uint32_t *__restrict__ d_hrank,
+                 uint32_t *__restrict__ d_next, uint16_t *__restrict__ d_mask, uint32_t *__restrict__ d_bsum)
+{
+    extern __shared__ __align__(16) uint16_t kc_rank[];
+    for (int i = threadIdx.x; i < OOK_RANK_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(kc_rank)[i] = __ldg(reinterpret_cast<const uint4 *>(g_rank) + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t rank_s = smem_u32(kc_rank);
+    const size_t groups_per_stream = (n_blocks + 31) / 32;
+    const size_t n_groups = groups_per_stream * n_streams;
+    const size_t warps_total = (size_t)gridDim.x * KC1_WARPS;
+    constexpr int PF = 2;
+    // lane l of a group looks after block l's tag and rank threshold; both are fetched ahead of the group that uses them (tags two
+    // groups ahead, the thresholds -- addressed by the tags -- one), so a group starts with everything but its samples in registers.
+    // Groups are handed out through a counter: the work in a group is the number of its collected blocks, 0 to 32, and bursts sit
+    // at similar places in similar streams -- with a fixed stride (4144 warps = 259 x 16 groups per stream) a warp met the SAME
+    // place of every stream it visited: 13 of 28 warps per SM busy on average, 340 us.  The first three groups of a warp are fixed
+    // (no start-up latency), the counter -- set to 3 x warps by ook_rankthr_kernel -- gives out the rest three groups ahead.
+    const uint32_t gps = (uint32_t)groups_per_stream, ng = (uint32_t)n_groups;
+    auto tag_of = [&](uint32_t g) -> int32_t {
+        if (g >= ng) return -1;
+        const size_t b = (size_t)(g % gps) * 32 + lane;
+        return b < n_blocks ? d_tag[(size_t)(g / gps) * n_blocks + b] : -1;
+    };
+    auto thr_of = [&](uint32_t g, int32_t tg) -> uint32_t {
+        return tg >= 0 ? d_hrank[(size_t)(g / gps) * max_bursts + tg] - 1u : 0u;           // rank >= h  <=>  (h - 1) - rank < 0
+    };
+    const uint32_t wt = (uint32_t)warps_total;
+    uint32_t g0 = blockIdx.x * KC1_WARPS + warp, g1 = g0 + wt, g2 = g1 + wt;
+    int32_t tg_l = tag_of(g0), tg_n1 = tag_of(g1);
+    uint32_t hm1_l = thr_of(g0, tg_l);
+    while (g0 < ng) {
+        uint32_t g3 = 0;
+        if (lane == 0) g3 = atomicAdd(d_next, 1u);                         // consumed at the end of the iteration
+        const uint32_t hm1_n1 = thr_of(g1, tg_n1);
+        const int32_t tg_n2 = tag_of(g2);
+        const size_t st = g0 / gps, b0 = (size_t)(g0 % gps) * 32;
+        unsigned rem = __ballot_sync(0xffffffffu, tg_l >= 0);
+        if (rem != 0u) {
+            const uint8_t *base = iq + st * stream_stride + b0 * (size_t)(OOK_BLOCK * 2);
+            int kA[PF], kB[PF];
+            uint4 dA[PF][2], dB[PF][2];
+            auto take = [&](int (&ks)[PF], uint4 (&d)[PF][2]) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    ks[i] = rem ? __ffs(rem) - 1 : -1;
+                    if (rem) rem &= rem - 1;
+                    if (ks[i] >= 0) {
+                        const uint4 *p = reinterpret_cast<const uint4 *>(base + ks[i] * (size_t)(OOK_BLOCK * 2) + lane * 32);
+                        d[i][0] = ldg_stream_u4(p); d[i][1] = ldg_stream_u4(p + 1);
+                    }
+                }
+            };
+            take(kA, dA);
+            while (kA[0] >= 0) {
+                take(kB, dB);
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    if (kA[i] < 0) continue;                              // warp-uniform
+                    const uint32_t hm1 = __shfl_sync(0xffffffffu, hm1_l, kA[i]);
+                    const uint32_t m = kc_slice16(rank_s, hm1, dA[i][0], dA[i][1]);
+                    const size_t blk = st * n_blocks + b0 + kA[i];
+                    d_mask[blk * 32 + lane] = (uint16_t)m;                // 64 contiguous bytes per block
+                    const uint32_t tm = kc_inner_transitions(m, lane);
+                    uint32_t cnt = 0;
+                    if (__ballot_sync(0xffffffffu, tm != 0u) != 0u) cnt = __reduce_add_sync(0xffffffffu, __popc(tm));
+                    const uint32_t first = __shfl_sync(0xffffffffu, m, 0) & 1u, last = (__shfl_sync(0xffffffffu, m, 31) >> 15) & 1u;
+                    if (lane == 0) d_bsum[blk] = cnt | (first ? KC_SUM_FIRST : 0u) | (last ? KC_SUM_LAST : 0u);
+                }
+#pragma unroll
+                for (int i = 0; i < PF; ++i) { kA[i] = kB[i]; dA[i][0] = dB[i][0]; dA[i][1] = dB[i][1]; }
+            }
+        }
+        tg_l = tg_n1; hm1_l = hm1_n1; tg_n1 = tg_n2;
+        g0 = g1; g1 = g2; g2 = __shfl_sync(0xffffffffu, g3, 0);
+    }
+}
+
+// per collected block, written by C2: .x position of its first bit in the flattened bit stream, .y index of its first entry in the
+// transition list, .z position of the transition made by the zeros inserted before it (valid with KC_INFO_PRE), .w flags
+constexpr uint32_t KC_INFO_PRE = 1u, KC_INFO_FIRST = 2u;
+constexpr int KC2_WARPS = 4;
+
+__global__ void __launch_bounds__(KC2_WARPS * 32)
+ook_scan_kernel(size_t n_streams, size_t n_blocks, size_t max_bursts, size_t max_runs, const int32_t *__restrict__ d_tag,
+                const uint32_t *__restrict__ d_bsum, const uint8_t *__restrict__ d_bflags, const uint32_t *__restrict__ d_nbursts,
+                uint4 *__restrict__ d_binfo, uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans,
+                uint32_t *__restrict__ d_nbits)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (st >= n_streams) return;
+    const int32_t *tag = d_tag + st * n_blocks;
+    const uint32_t *bsum = d_bsum + st * n_blocks;
+    const uint8_t *flags = d_bflags + st * max_bursts;
+    uint4 *binfo = d_binfo + st * n_blocks;
+    // bursts that were sent without a collected block (the OOM guard reset the buffer to [0.0] with the counter at 1, :52-54 and
+    // :78-81): one 0 bit each, found among the burst indices the walk steps over (flags == 3: sent, leading 0.0)
+    auto lone_zero_bursts = [&](int32_t from, int32_t to) {
+        uint32_t n = 0;
+        for (int32_t j = from; j < to; ++j) n += (flags[j] & 3u) == 3u ? 1u : 0u;
+        return n;
+    };
+    uint32_t pos = 0, ntr = 0, prev = 0;          // the walk's carry: bits so far, transitions so far, value of the last bit
+    int32_t cur_burst = -1;
+    constexpr int CH = 4;                         // groups whose tags and summaries are fetched together (one latency per 128 blocks)
+    for (size_t c0 = 0; c0 < n_blocks; c0 += 32 * CH) {
+        int32_t tgs[CH]; uint32_t sms[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const size_t b = c0 + 32 * c + lane;
+            tgs[c] = b < n_blocks ? tag[b] : -1;
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const size_t b = c0 + 32 * c + lane;
+            sms[c] = b < n_blocks ? bsum[b] : 0u;          // not behind the tag's latency; only read where the block is collected
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int32_t tg = tgs[c];
+            const bool col = tg >= 0;
+            const unsigned cmask = __ballot_sync(0xffffffffu, col);
+            if (cmask == 0u) continue;                                     // warp-uniform
+            const uint32_t sm = sms[c];
+            const uint32_t first = (sm & KC_SUM_FIRST) ? 1u : 0u, last = (sm & KC_SUM_LAST) ? 1u : 0u, cnt = sm & KC_SUM_CNT;
+            // the collected block before this one: in the group, or the carry
+            const unsigned lower = cmask & ((1u << lane) - 1u);
+            const int pidx = lower ? 31 - __clz(lower) : 0;
+            const int32_t ptag_g = __shfl_sync(0xffffffffu, tg, pidx);
+            const uint32_t plast_g = __shfl_sync(0xffffffffu, last, pidx);
+            const int32_t ptag = lower ? ptag_g : cur_burst;
+            const uint32_t plast = lower ? plast_g : prev;
+            // bits inserted before the block: lone [0.0] bursts stepped over, then the burst's own leading 0.0
+            uint32_t n_ins = 0;
+            if (col && tg != ptag) n_ins = lone_zero_bursts(ptag + 1, tg) + ((flags[tg] & 2u) ? 1u : 0u);
+            const uint32_t bits = col ? (uint32_t)OOK_BLOCK + n_ins : 0u;
+            uint32_t incl = bits;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t pos_ins = pos + incl - bits;                    // where the inserted zeros start
+            const uint32_t pos_base = pos_ins + n_ins;                     // the block's first bit
+            const uint32_t before = n_ins ? 0u : plast;                    // value of the bit before it
+            const bool pre = col && n_ins && pos_ins > 0u && plast != 0u;  // 1 -> 0 at the first inserted zero
+            const bool firstT = col && pos_base > 0u && first != before;
+            const uint32_t mine = col ? cnt + (pre ? 1u : 0u) + (firstT ? 1u : 0u) : 0u;
+            uint32_t tincl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, tincl, d);
+                if (lane >= d) tincl += v;
+            }
+            if (col)
+                binfo[c0 + 32 * c + lane] = make_uint4(pos_base, ntr + tincl - mine, pos_ins,
+                                                       (pre ? KC_INFO_PRE : 0u) | (firstT ? KC_INFO_FIRST : 0u));
+            const int lastc = 31 - __clz(cmask);
+            pos += __shfl_sync(0xffffffffu, incl, 31);
+            ntr += __shfl_sync(0xffffffffu, tincl, 31);
+            cur_burst = __shfl_sync(0xffffffffu, tg, lastc);
+            prev = __shfl_sync(0xffffffffu, last, lastc);
+        }
+    }
+    {   // lone [0.0] bursts after the last collected block
+        const uint32_t nbu = d_nbursts[st];
+        const uint32_t n = lone_zero_bursts(cur_burst + 1, (int32_t)(nbu < max_bursts ? nbu : max_bursts));
+        if (n) {
+            if (pos > 0u && prev != 0u) { if (lane == 0 && ntr < max_runs) d_trans[st * max_runs + ntr] = pos; ntr++; }
+            pos += n;
+        }
+    }
+    if (lane == 0) { d_ntrans[st] = ntr; d_nbits[st] = pos; }
+}
+
+constexpr int KC3_WARPS = 8;
+
+// C3: lane l of a warp owns block l of a (stream, group): its transitions go to consecutive entries of the list starting at the
+// index C2 gave it, so no lane needs another's count -- the blocks of a group are written side by side, each lane fetching the 64
+// bytes of its own mask in one go
+__global__ void __launch_bounds__(KC3_WARPS * 32)
+ook_scatter_kernel(size_t n_streams, size_t n_blocks, size_t max_runs, const int32_t *__restrict__ d_tag,
+                   const uint32_t *__restrict__ d_bsum, const uint4 *__restrict__ d_binfo, const uint16_t *__restrict__ d_mask,
+                   uint32_t *__restrict__ d_trans)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t groups_per_stream = (n_blocks + 31) / 32;
+    const size_t n_groups = groups_per_stream * n_streams;
+    const size_t grp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (grp >= n_groups) return;
+    const size_t st = grp / groups_per_stream, b0 = (grp % groups_per_stream) * 32;
+    if (b0 + lane >= n_blocks) return;
+    const size_t blk = st * n_blocks + b0 + lane;
+    if (d_tag[blk] < 0) return;
+    const uint32_t sm = d_bsum[blk];
+    const uint4 info = d_binfo[blk];
+    uint32_t *trans = d_trans + st * max_runs;
+    uint32_t o = info.y;
+    if (info.w & KC_INFO_PRE) { if (o < max_runs) trans[o] = info.z; ++o; }        // 1 -> 0 at the zeros inserted before the block
+    if (info.w & KC_INFO_FIRST) { if (o < max_runs) trans[o] = info.x; ++o; }      // at the block's first bit
+    if ((sm & KC_SUM_CNT) == 0u) return;
+    const uint4 *mp = reinterpret_cast<const uint4 *>(d_mask + blk * 32);
+    uint4 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = __ldg(mp + i);
+    uint32_t prevbit = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint4 &v = q[i >> 2];
+        const uint32_t w = (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+        uint32_t tm = w ^ ((w << 1) | prevbit);
+        if (i == 0) tm &= ~1u;                                                     // the first bit was dealt with above
+        prevbit = w >> 31;
+        while (tm) {
+            const int b = __ffs(tm) - 1;
+            tm &= tm - 1;
+            if (o < max_runs) trans[o] = info.x + 32u * i + b;
+            ++o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K-D: dle + matchers + shaper_optional, one thread per stream
 // ---------------------------------------------------------------------------------------------
 
@@ -900,6 +1246,7 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     LRC_BIND(ctx);
     LRC_REQUIRE(out && n_streams >= 1 && n_blocks >= 1 && sample_rate >= 1, LRC_ERR_INVALID, "lrc_ook_create: bad arguments");
     LRC_REQUIRE(n_blocks * (size_t)OOK_BLOCK < 0xffffffffull, LRC_ERR_UNSUPPORTED, "lrc_ook_create: capture too long (2^32 samples)");
+    LRC_REQUIRE(n_streams * ((n_blocks + 31) / 32) < 0x7fffffffull, LRC_ERR_UNSUPPORTED, "lrc_ook_create: too many 32-block groups (2^31)");
     lrc_ook *o = new (std::nothrow) lrc_ook();
     LRC_REQUIRE(o != nullptr, LRC_ERR_NOMEM, "out of host memory");
     memset(o, 0, sizeof(*o));
@@ -924,6 +1271,7 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
     OOK_ALLOC(d_trans, n_streams * o->max_runs); OOK_ALLOC(d_ntrans, n_streams); OOK_ALLOC(d_nbits, n_streams);
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
     OOK_ALLOC(d_runs_dbg, n_streams * o->max_runs);
+    OOK_ALLOC(d_mask, sb * 32); OOK_ALLOC(d_bsum, sb); OOK_ALLOC(d_binfo, sb); OOK_ALLOC(d_hrank, n_streams * o->max_bursts); OOK_ALLOC(d_next, 1);
     OOK_ALLOC(d_lut, (size_t)OOK_LUT_N);
     OOK_ALLOC(d_flut, (size_t)OOK_FLUT_N);
     OOK_ALLOC(d_rank, (size_t)OOK_RANK_N); OOK_ALLOC(d_uniq, (size_t)65536);
@@ -952,6 +1300,7 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
             }
         }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_RANK_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ook_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OOK_RANK_BYTES);
     }
     if (e == cudaSuccess) {
         // rank table for the slicer: the envelope of every byte pair, computed ON THE DEVICE by the routine the
@@ -990,7 +1339,7 @@ extern "C" int lrc_ook_destroy(lrc_ook *o)
     cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags);
     cudaFree(o->d_nbursts); cudaFree(o->d_trans); cudaFree(o->d_ntrans); cudaFree(o->d_nbits);
     cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut); cudaFree(o->d_flut);
-    cudaFree(o->d_rank); cudaFree(o->d_uniq);
+    cudaFree(o->d_rank); cudaFree(o->d_uniq); cudaFree(o->d_mask); cudaFree(o->d_bsum); cudaFree(o->d_binfo); cudaFree(o->d_hrank); cudaFree(o->d_next);
     delete o;
     return LRC_OK;
 }
@@ -1054,12 +1403,38 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_STREAMS), KB_THREADS, 0, s>>>(
         o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->guard_samples, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
     LRC_CUDA(cudaGetLastError());
-    size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
-    if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
-    ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
-        d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
-        o->d_uniq, o->n_uniq, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
-    LRC_CUDA(cudaGetLastError());
+    // Which K-C: the one-warp-per-stream kernel needs many streams per SM to cover the latency of its walk (4096 streams: 240 us
+    // against 296 us for rank thresholds + slice + scan + scatter); below about 14 streams per SM the split form wins (2048: a
+    // tie, 1024: 0.296 against 0.337 ms for the whole chain, 512 -- one GPU's share of 4096 streams over eight -- 0.210 against
+    // 0.292).  LRC_OOK_KC = 0 / 1 forces one or the other for A/B runs; identical transition lists.
+    static const int kc_env = getenv("LRC_OOK_KC") ? atoi(getenv("LRC_OOK_KC")) : -1;
+    const int kc = kc_env >= 0 ? kc_env : (o->n_streams <= (size_t)12 * o->ctx->n_sm ? 1 : 0);
+    if (kc == 0) {
+        size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
+        if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
+        ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
+            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
+            o->d_uniq, o->n_uniq, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
+        LRC_CUDA(cudaGetLastError());
+    } else {
+        size_t blocks = ceil_div(groups, (size_t)KC1_WARPS);
+        if (blocks > cap) blocks = cap;
+        ook_rankthr_kernel<<<(unsigned)ceil_div(o->n_streams * o->max_bursts, (size_t)KC0_WARPS), KC0_WARPS * 32, 0, s>>>(
+            o->n_streams, o->max_bursts, o->d_half, o->d_bflags, o->d_nbursts, o->d_uniq, o->n_uniq, o->d_hrank, o->d_next,
+            (uint32_t)(3 * blocks * KC1_WARPS));
+        LRC_CUDA(cudaGetLastError());
+        ook_slice_kernel<<<(unsigned)blocks, KC1_WARPS * 32, OOK_RANK_BYTES, s>>>(
+            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->d_rank, o->d_tag, o->d_hrank, o->d_next,
+            o->d_mask, o->d_bsum);
+        LRC_CUDA(cudaGetLastError());
+        ook_scan_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KC2_WARPS), KC2_WARPS * 32, 0, s>>>(
+            o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_tag, o->d_bsum, o->d_bflags, o->d_nbursts, o->d_binfo,
+            o->d_trans, o->d_ntrans, o->d_nbits);
+        LRC_CUDA(cudaGetLastError());
+        ook_scatter_kernel<<<(unsigned)ceil_div(groups, (size_t)KC3_WARPS), KC3_WARPS * 32, 0, s>>>(
+            o->n_streams, o->n_blocks, o->max_runs, o->d_tag, o->d_bsum, o->d_binfo, o->d_mask, o->d_trans);
+        LRC_CUDA(cudaGetLastError());
+    }
     ook_match_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KD_WARPS), KD_WARPS * 32, 0, s>>>(
         o->d_trans, o->d_ntrans, o->n_streams, o->max_runs, o->max_packets, (float)o->sample_rate, o->d_packets,
         o->d_npackets, o->d_runs_dbg);

@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--cpu", action="store_true", help="time the reference's CPU path (oracle/) beside each config")
+    ap.add_argument("--ook-streams", type=int, default=0, help="streams of the OOK config (default 4096; 512 = one GPU's shard of eight)")
     a = ap.parse_args()
     if a.cpu:
         import oracle
@@ -253,7 +254,7 @@ def main():
             del x
 
     if want("ook"):
-        n_streams, n_blocks = 4096 // q, 500
+        n_streams, n_blocks = (a.ook_streams or 4096 // q), 500
         caps = [synth.ook_capture_u8(n_blocks, seed=4 + s, n_packets=2)[0] for s in range(32)]
         iq = torch.from_numpy(np.stack(caps)).to(dev).repeat(n_streams // 32, 1).contiguous()
         ook = blocks.Ook(ctx, n_streams, n_blocks, 256000, 4096, 64)
@@ -263,7 +264,7 @@ def main():
         if a.cpu:
             extra.update(cpu_rate(lambda: oracle.ook_decode(caps[0]), n_blocks * 512))
             extra["cpu_what"] = "restated ratpak.rs:60-111 chain (envelope..shaper_optional), strict f32 C, one stream per core"
-        report("OOK chain 4 kernels (config 4, K7)", ns, ns * 2, ms, extra)
+        report(f"OOK chain, {n_streams} streams (config 4, K7)", ns, ns * 2, ms, extra)
         ook.close()
     ctx.close()
 

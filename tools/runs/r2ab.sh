@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, visit AB: K-C split into slice / scan / scatter: parity with both forms, A/B timing at 4096 and 512 streams, launch list
+set -u
+O=gpurun_out; mkdir -p $O; export PYTHONUNBUFFERED=1
+timeout 900 python -m pytest tests/test_gpu_ook_fastfir.py tests/test_gpu_full_size.py tests/test_gpu_kpn.py -m gpu -x -q -k "ook or envelope or eat or apps" > $O/r2ab_pytest_split.log 2>&1; echo "pytest (split) exit $?"; tail -n 4 $O/r2ab_pytest_split.log
+LRC_OOK_KC=0 timeout 900 python -m pytest tests/test_gpu_ook_fastfir.py -m gpu -x -q -k "ook" > $O/r2ab_pytest_onewarp.log 2>&1; echo "pytest (one warp per stream) exit $?"; tail -n 2 $O/r2ab_pytest_onewarp.log
+for n in 4096 512; do for kc in 1 0 1 0; do echo "streams $n KC=$kc"; LRC_OOK_KC=$kc timeout 200 python tools/bench_kernels.py --only ook --ook-streams $n 2>/dev/null | tail -1 | cut -c1-160; done; done
+for n in 4096 512; do
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/r2ab_launches_ook_$n.csv python tools/bench_kernels.py --only ook --ook-streams $n > $O/r2ab_ncu_launch_$n.log 2>&1; echo "ncu launches exit $?"
+python - $n <<'PY'
+import csv,collections,statistics,sys
+d=collections.defaultdict(list)
+rows=[r for r in csv.reader(open('gpurun_out/r2ab_launches_ook_%s.csv' % sys.argv[1])) if len(r)>5]
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
+for r in rows[1:]:
+    if 'ook_' in r[ki]: d[r[ki].split('(')[0]].append(float(r[vi].replace(',','')))
+for k,v in d.items(): print(sys.argv[1], k, len(v), 'median us', statistics.median(v)/1000)
+PY
+done
+LRC_OOK_KC=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r2ab_launches_ook_512_onewarp.csv python tools/bench_kernels.py --only ook --ook-streams 512 > /dev/null 2>&1
+grep -c ook_rle $O/r2ab_launches_ook_512_onewarp.csv; grep ook_rle $O/r2ab_launches_ook_512_onewarp.csv | tail -2 | cut -c1-60,200-400
