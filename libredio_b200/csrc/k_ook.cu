@@ -132,6 +132,7 @@ struct lrc_ook {
     int32_t  *d_tag;                  // [n_streams][n_blocks] burst index the block is collected into, -1 = none
     float    *d_half;                 // [n_streams][max_bursts]  max/2 of the burst
     uint8_t  *d_bflags;               // [n_streams][max_bursts]  bit0 = emitted, bit1 = leading 0.0 sample
+    uint32_t *d_bend;                 // [n_streams][max_bursts]  last block that can belong to the burst (the one that sent / dropped it)
     uint32_t *d_nbursts;              // [n_streams]
     uint32_t *d_trans;                // [n_streams][max_runs] positions where the bit stream changes value
     uint32_t *d_ntrans;               // [n_streams]  (may exceed max_runs: overflow is detected on fetch)
@@ -406,48 +407,53 @@ ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams,
 // of its flag clear and has its blocks un-tagged once all tags are in global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp (and of the keeper warp)
-constexpr int KB_HELPERS = 96;                // helper threads (three warps)
+constexpr int KB_HELPERS = 192;               // helper threads (six warps: with three they, not the chain, set the pace)
 constexpr int KB_THREADS = 2 * KB_STREAMS + KB_HELPERS;
 constexpr int KB_TILE = 32;                   // blocks per staged tile
 constexpr int KB_LD = KB_TILE + 1;            // conflict-free both ways: helpers move rows, the walker reads columns
-constexpr int KB_CLD = KB_TILE + 4;           // bytes per stream in a tile of codes: 9 words, lanes 9 banks apart
 
 __global__ void __launch_bounds__(KB_THREADS)
-ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_max, size_t n_streams,
-                   size_t n_blocks, size_t max_bursts, uint32_t guard_samples, int32_t *__restrict__ d_tag,
-                   float *__restrict__ d_half, uint8_t *__restrict__ d_bflags, uint32_t *__restrict__ d_nbursts)
+ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_blocks, size_t max_bursts, uint32_t guard_samples,
+                   int32_t *__restrict__ d_tag, uint32_t *__restrict__ d_bend, uint8_t *__restrict__ d_bflags,
+                   uint32_t *__restrict__ d_nbursts)
 {
-    __shared__ float s_sum[3][KB_STREAMS * KB_LD];
-    __shared__ float s_max[4][KB_STREAMS * KB_LD];
+    __shared__ float s_sum[4][KB_STREAMS * KB_LD];        // tile t in buffer t & 3: copies run two tiles ahead of the divisions
     __shared__ float s_q[2][KB_STREAMS * KB_LD];
-    __shared__ int32_t s_tag[2][KB_STREAMS * KB_LD];
-    __shared__ __align__(4) uint8_t s_code[2][KB_STREAMS * KB_CLD];
+    __shared__ int32_t s_tag[2][KB_STREAMS * KB_LD];      // explicit tags of a tile the keeper walked block by block
+    __shared__ uint32_t s_cm[4][KB_STREAMS], s_sm[4][KB_STREAMS];   // per tile and stream: blocks collected / blocks that send
+    __shared__ uint32_t s_b0[2][KB_STREAMS];              // burst index of the stream when the tile starts
+    __shared__ uint32_t s_mode[2];                        // 1 = the tile's tags are in s_tag
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t st0 = (size_t)blockIdx.x * KB_STREAMS;
     const int n_tiles = (int)((n_blocks + KB_TILE - 1) / KB_TILE);
-    // Round-2 split of the walk: the reference's statements fall into a CHAIN -- threshold and trigger counter (:46, :57-70), each
+    // Round-2 split of the walk.  The reference's statements fall into a CHAIN -- threshold and trigger counter (:46, :57-70), each
     // block's values needing the previous block's -- and BOOK-KEEPING that only reads the counter (:52-54 guard, :73-81 collect and
-    // send: buffer length, burst index, running maximum, tags).  The walker warp (threads 0-31) runs the chain alone and leaves one
-    // byte per block {counter > 1, counter == 0}; the keeper warp (threads 32-63, same lane = same stream) does the book-keeping
-    // one tile behind from those bytes.  Neither warp carries the other's instructions on its dependent-issue path.
+    // send).  The walker warp (threads 0-31) runs the chain alone and leaves two bit masks per tile of 32 blocks: counter > 1
+    // (collect) and counter == 0 (send).  The keeper warp (threads 32-63, same lane = same stream), one tile behind, does not walk
+    // blocks at all: it steps from SEND to SEND (a handful per stream and capture), counting the collected blocks in between with
+    // popc for the buffer length; the tags are expanded from the masks by the helper warps (tag = burst index at the start of the
+    // tile + sends before the block), and a burst's maximum is taken afterwards, in parallel, by ook_burst_kernel from the per-block
+    // maxima and the tags.  Only a tile in which the OOM guard could fire (buffer within 32 blocks of the limit: 100 s of
+    // uninterrupted burst) is walked block by block, with the tags written out explicitly.
+    // Measured on the way here (4096 streams x 500 blocks): one warp doing everything 133 us; walker + helpers 60 us; walker +
+    // per-block keeper 53 us with the KEEPER the bound (40 instructions per block against the chain's 21, ncu source page:
+    // profiles/r2_ae_ookB_ncu_keys.txt).
     const bool walker = tid < KB_STREAMS;
     const bool keeper = tid >= KB_STREAMS && tid < 2 * KB_STREAMS;
     const bool helper = tid >= 2 * KB_STREAMS;
-    const int ht = tid - 2 * KB_STREAMS, hwarp = ht >> 5;              // helpers: 3 warps, warp w moves rows w, w + 3, ...
-    // cp.async (LDGSTS) of tile `tile` into its buffers: a helper warp moves 32 consecutive floats of one stream per step.  Sums
-    // are read by the walker in the tile's own iteration (3 buffers), maxima by the keeper one iteration later (4 buffers).
+    const int ht = tid - 2 * KB_STREAMS, hwarp = ht >> 5;              // helpers: warp w moves rows w, w + 6, ...
+    const uint32_t mb = (uint32_t)(max_bursts < 0x7fffffffull ? max_bursts : 0x7fffffffull);
+    // cp.async (LDGSTS) of tile `tile` into its buffer: a helper warp moves 32 consecutive floats of one stream per step
     auto stage = [&](int tile) {
         if (tile < n_tiles) {
             const size_t b = (size_t)tile * KB_TILE + lane;
             for (int r = hwarp; r < KB_STREAMS; r += KB_HELPERS / 32) {
                 const size_t s = st0 + r;
-                float *ds = &s_sum[tile % 3][r * KB_LD + lane], *dm = &s_max[tile & 3][r * KB_LD + lane];
-                if (s < n_streams && b < n_blocks) {
+                float *ds = &s_sum[tile & 3][r * KB_LD + lane];
+                if (s < n_streams && b < n_blocks)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(ds)), "l"(d_sum + s * n_blocks + b) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dm)), "l"(d_max + s * n_blocks + b) : "memory");
-                } else {
-                    *ds = 0.0f; *dm = 0.0f;
-                }
+                else
+                    *ds = 0.0f;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -455,26 +461,38 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     // s / 1000 (:63) of tile `tile`, whose copies have landed: 1024 independent IEEE divisions over 96 threads
     auto quotients = [&](int tile) {
         if (tile >= n_tiles) return;
-        const float *src = s_sum[tile % 3];
+        const float *src = s_sum[tile & 3];
         float *dst = s_q[tile & 1];
         for (int i = ht; i < KB_STREAMS * KB_TILE; i += KB_HELPERS) {
             const int r = i >> 5, c = i & 31;
             dst[r * KB_LD + c] = __fdiv_rn(src[r * KB_LD + c], 1000.0f);
         }
     };
+    // tags of tile `tile` to global memory: lane = block, a helper warp takes a stream per step
     auto tags_out = [&](int tile) {
-        if (tile < 0) return;
+        if (tile < 0 || tile >= n_tiles) return;
+        const bool expl = s_mode[tile & 1] != 0u;
         const int32_t *src = s_tag[tile & 1];
         const size_t b = (size_t)tile * KB_TILE + lane;
         for (int r = hwarp; r < KB_STREAMS; r += KB_HELPERS / 32) {
             const size_t s = st0 + r;
-            if (s < n_streams && b < n_blocks) d_tag[s * n_blocks + b] = src[r * KB_LD + lane];
+            if (s < n_streams && b < n_blocks) {
+                int32_t tg;
+                if (expl) {
+                    tg = src[r * KB_LD + lane];
+                } else {
+                    const uint32_t cm = s_cm[tile & 3][r], sm = s_sm[tile & 3][r];
+                    const uint32_t bi = s_b0[tile & 1][r] + (uint32_t)__popc(sm & ((1u << lane) - 1u));
+                    tg = ((cm >> lane) & 1u) && bi < mb ? (int32_t)bi : -1;
+                }
+                d_tag[s * n_blocks + b] = tg;
+            }
         }
     };
     // one stream per lane, in the walker and in the keeper
     const size_t st = st0 + lane;
     const bool live = (walker || keeper) && st < n_streams;
-    float *half = d_half + st * max_bursts;
+    uint32_t *bend = d_bend + st * max_bursts;
     uint8_t *flags = d_bflags + st * max_bursts;
     // walker state
     int trigger = 0;                          // :41 (isize there; |trigger| <= n_blocks here)
@@ -482,42 +500,43 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
     // keeper state
     uint32_t buf_len = 1;                     // :43 sample_buffer = vec!(0.0); capped at the guard + 512 below
     bool lead0 = true;                        // the buffer currently starts with that 0.0
-    float cur_max = 0.0f;
     uint32_t burst = 0;                       // index of the burst being collected
     bool dropped = false;                     // the OOM guard abandoned a burst of this stream
     if (helper) {
         stage(0);
         stage(1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");            // tile 0 has landed (this thread's part)
+        stage(2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");            // tile 0 has landed (this thread's part)
         named_bar_sync(1, KB_HELPERS);
         quotients(0);
     }
     __syncthreads();
-    // iteration i: helpers tile i + 1 / i + 2 in, tile i - 2 out; walker tile i; keeper tile i - 1
-    for (int tile = 0; tile <= n_tiles; ++tile) {
+    // iteration i: helpers tile i + 1 / i + 2 in, tags of tile i - 2 out; walker tile i; keeper tile i - 1
+    for (int tile = 0; tile <= n_tiles + 1; ++tile) {
         if (helper) {
-            asm volatile("cp.async.wait_all;" ::: "memory");            // tile + 1 (issued an iteration ago)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");        // tile + 1 (issued two iterations ago; tile + 2 may be in flight)
             named_bar_sync(1, KB_HELPERS);                              // ... every helper's part of it
             quotients(tile + 1);
             tags_out(tile - 2);
-            stage(tile + 2);                                            // sums: last read in iteration tile - 1; maxima: tile - 1's
-        } else if (walker) {                                            // buffer is (tile + 3) & 3, not this one
-            if (live && tile < n_tiles) {
-                const float *t_sum = s_sum[tile % 3] + lane * KB_LD;
+            stage(tile + 3);                                            // its buffer was last read in iteration tile - 1
+        } else if (walker) {
+            if (tile < n_tiles) {
+                const float *t_sum = s_sum[tile & 3] + lane * KB_LD;
                 const float *t_q = s_q[tile & 1] + lane * KB_LD;
-                uint32_t *t_code = reinterpret_cast<uint32_t *>(s_code[tile & 1] + lane * KB_CLD);
                 const size_t b0 = (size_t)tile * KB_TILE;
                 const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
-                for (int u0 = 0; u0 < nb; u0 += 8) {
+                uint32_t cm = 0u, sm = 0u;
+#pragma unroll 1
+                for (int u0 = 0; u0 < KB_TILE; u0 += 8) {
                     // the block's inputs do not depend on the chain: eight blocks ahead into registers
                     float sr[8], qr[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { sr[k] = t_sum[u0 + k]; qr[k] = t_q[u0 + k]; }
-                    uint32_t code[2] = {0u, 0u};
+                    uint32_t c8 = 0u, s8 = 0u;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        // (blocks past the end of a ragged last tile are walked too: their zero sums change nothing the keeper reads,
-                        // and the walker's state is not used after the last tile)
+                        // (blocks past the end of a ragged last tile are walked too, on zero sums: their bits are masked off
+                        // below and the walker's state is not used after the last tile)
                         trigger -= 1;                                                       // :46
                         const float s = sr[k];                                              // :48
                         // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
@@ -530,70 +549,73 @@ ook_trigger_kernel(const float *__restrict__ d_sum, const float *__restrict__ d_
                         const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
                         threshold = trigger < 0 ? thr2 : thr0;
                         trigger = __fmul_rn(s, 0.25f) > threshold ? OOK_TRIGGER_DURATION : trigger;  // :68-70
-                        // what the keeper needs of the counter: collect (:73) and send (:78)
-                        const uint32_t c = (trigger > 1 ? 1u : 0u) | (trigger == 0 ? 2u : 0u);
-                        code[k >> 2] |= c << (8 * (k & 3));
+                        // what the book-keeping needs of the counter: collect (:73) and send (:78)
+                        c8 |= (trigger > 1 ? 1u : 0u) << k;
+                        s8 |= (trigger == 0 ? 1u : 0u) << k;
                     }
-                    t_code[(u0 >> 2)] = code[0];
-                    t_code[(u0 >> 2) + 1] = code[1];
+                    cm |= c8 << u0;
+                    sm |= s8 << u0;
                 }
+                const uint32_t valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                s_cm[tile & 3][lane] = cm & valid;
+                s_sm[tile & 3][lane] = sm & valid;
             }
-        } else if (tile >= 1) {                                         // keeper, one tile behind
-            // All 32 lanes walk (a lane without a stream reads whatever its row of codes holds and stores nothing outside shared
-            // memory), so the two rare events -- the guard and the end of a burst -- can sit behind warp-uniform votes and the
-            // common block is a dozen selects.  First version of the split: both events as per-lane branches, 87 instructions per
-            // block with the reconvergence points, and the keeper -- not the chain -- set the kernel's duration (ncu source page:
-            // 500 of a warp's 600 samples in the keeper, 110 in the walker).
+        } else if (tile >= 1 && tile <= n_tiles) {                      // keeper, one tile behind
             const int kt = tile - 1;
-            const float *t_max = s_max[kt & 3] + lane * KB_LD;
-            const uint32_t *t_code = reinterpret_cast<const uint32_t *>(s_code[kt & 1] + lane * KB_CLD);
-            int32_t *t_tag = s_tag[kt & 1] + lane * KB_LD;
+            const uint32_t cm = s_cm[kt & 3][lane], sm = s_sm[kt & 3][lane];
             const size_t b0 = (size_t)kt * KB_TILE;
-            const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
-            const uint32_t mb = (uint32_t)(max_bursts < 0x7fffffffull ? max_bursts : 0x7fffffffull);
-            for (int u0 = 0; u0 < nb; u0 += 8) {
-                float mr[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) mr[k] = t_max[u0 + k];
-                const uint32_t code[2] = {t_code[u0 >> 2], t_code[(u0 >> 2) + 1]};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int u = u0 + k;
-                    if (u >= nb) break;
-                    const uint32_t c = (code[k >> 2] >> (8 * (k & 3))) & 3u;
+            s_b0[kt & 1][lane] = burst;
+            // could the guard fire in this tile?  It looks at the buffer before a block is pushed (:52), and the buffer grows by
+            // at most 32 blocks here
+            const bool near_guard = live && buf_len + (uint32_t)(KB_TILE * OOK_BLOCK) > guard_samples;
+            if (!__any_sync(0xffffffffu, near_guard)) {
+                if (lane == 0) s_mode[kt & 1] = 0u;
+                // from send to send: the blocks collected since the last one lengthen the buffer (:73-75), the send empties it
+                uint32_t rem = live ? sm : 0u, done = 0u;                // `done`: bits of the blocks already accounted for
+                while (rem) {
+                    const int u = __ffs(rem) - 1;
+                    rem &= rem - 1u;
+                    const uint32_t upto = (1u << u) - 1u;                // blocks before u (u itself sends, it is not collected)
+                    buf_len += (uint32_t)OOK_BLOCK * (uint32_t)__popc(cm & upto & ~done);
+                    done = upto | (1u << u);
+                    if (burst < mb) {                                                   // :78-81 send, buffer = vec!()
+                        bend[burst] = (uint32_t)(b0 + u);
+                        flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
+                    }
+                    burst += 1;
+                    buf_len = 0; lead0 = false;
+                }
+                buf_len += (uint32_t)OOK_BLOCK * (uint32_t)__popc(cm & ~done);
+            } else {
+                if (lane == 0) s_mode[kt & 1] = 1u;
+                int32_t *t_tag = s_tag[kt & 1] + lane * KB_LD;
+                const int nb = (int)((n_blocks - b0) < (size_t)KB_TILE ? (n_blocks - b0) : (size_t)KB_TILE);
+                for (int u = 0; u < nb; ++u) {
                     // :52-54 OOM guard (a burst longer than 50 000 blocks = 100 s at 256 ksps): what was collected is dropped -- the
                     // burst index is abandoned with its flag clear -- and collection goes on in a fresh buffer [0.0].  When the
                     // guard fires with the counter at 1 nothing is pushed after the reset and the next block sends the buffer [0.0]
                     // as it is: a sent burst (flags 3, max/2 = 0) without a tagged block, which the slicer turns into its one 0 bit.
-                    const bool over = buf_len > guard_samples;
-                    if (__any_sync(0xffffffffu, over)) {
-                        if (over) {
-                            if (live && burst < mb) flags[burst] = 0;
-                            burst += 1; dropped = true;
-                            buf_len = 1; lead0 = true; cur_max = 0.0f;
-                        }
+                    if (buf_len > guard_samples) {
+                        if (live && burst < mb) { flags[burst] = 0; bend[burst] = (uint32_t)(b0 + u) - 1u; }
+                        burst += 1; dropped = true;
+                        buf_len = 1; lead0 = true;
                     }
-                    const bool collect = (c & 1u) != 0u;                                // :73-75 push_all
+                    const bool collect = ((cm >> u) & 1u) != 0u;                        // :73-75 push_all
                     buf_len += collect ? (uint32_t)OOK_BLOCK : 0u;
-                    cur_max = collect ? fmaxf(cur_max, mr[k]) : cur_max;
                     t_tag[u] = (collect && burst < mb) ? (int32_t)burst : -1;
-                    const bool send = (c & 2u) != 0u;                                   // :78-81 send, buffer = vec!()
-                    if (__any_sync(0xffffffffu, send)) {
-                        if (send && live && burst < mb) {
-                            half[burst] = __fmul_rn(cur_max, 0.5f);                     // discretize :90-91 max/2f32 (x / 2 == x * 0.5:
-                            flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));           // the same real number, rounded once)
+                    if ((sm >> u) & 1u) {                                               // :78-81 send, buffer = vec!()
+                        if (live && burst < mb) {
+                            bend[burst] = (uint32_t)(b0 + u);
+                            flags[burst] = (uint8_t)(1u | (lead0 ? 2u : 0u));
                         }
-                        burst += send ? 1u : 0u;
-                        buf_len = send ? 0u : buf_len;
-                        lead0 = send ? false : lead0;
-                        cur_max = send ? 0.0f : cur_max;
+                        burst += 1;
+                        buf_len = 0; lead0 = false;
                     }
                 }
             }
         }
         __syncthreads();
     }
-    if (helper) tags_out(n_tiles - 1);
     // a burst still open when the capture ends is never sent: its blocks (at most the tail of the capture) are un-tagged, and so
     // are -- in one pass over the stream's tags, which only a capture that tripped the OOM guard pays for -- the blocks of the
     // bursts the guard abandoned (flag bit 0 clear).  The slicer only ever sees blocks of bursts that were sent.  The whole CTA
@@ -898,23 +920,43 @@ __device__ __forceinline__ uint32_t kc_inner_transitions(uint32_t m, int lane)
     return tm;
 }
 
-// C0: a burst's max/2 as a rank threshold  #{distinct envelope values <= max/2}  (see ook_rle_kernel), one warp per (stream, burst)
+// K-B2: what the trigger kernel leaves open about a sent burst, one warp per (stream, burst): its maximum (bitfount.rs:90 fold(0.0,
+// max) -- order-free, so the per-block maxima of the blocks that carry its tag can be reduced in any order), max/2 (:91), and that
+// threshold in the rank domain  #{distinct envelope values <= max/2}  (see ook_rle_kernel).  The burst's blocks lie between the
+// block that ended the previous burst and the one that ended this one (d_bend).
 constexpr int KC0_WARPS = 8;
 __global__ void __launch_bounds__(KC0_WARPS * 32)
-ook_rankthr_kernel(size_t n_streams, size_t max_bursts, const float *__restrict__ d_half, const uint8_t *__restrict__ d_bflags,
-                   const uint32_t *__restrict__ d_nbursts, const float *__restrict__ uniq, uint32_t n_uniq,
-                   uint32_t *__restrict__ d_hrank, uint32_t *__restrict__ d_next, uint32_t next_init)
+ook_burst_kernel(size_t n_streams, size_t n_blocks, size_t max_bursts, const float *__restrict__ d_max,
+                 const int32_t *__restrict__ d_tag, const uint32_t *__restrict__ d_bend, const uint8_t *__restrict__ d_bflags,
+                 const uint32_t *__restrict__ d_nbursts, const float *__restrict__ uniq, uint32_t n_uniq,
+                 float *__restrict__ d_half, uint32_t *__restrict__ d_hrank, uint32_t *__restrict__ d_next, uint32_t next_init)
 {
     const int lane = threadIdx.x & 31;
     const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_next = next_init;         // the slice kernel's group counter (it runs after this one)
     if (w >= n_streams * max_bursts) return;
     const size_t st = w / max_bursts, j = w % max_bursts;
-    const uint32_t nbu = d_nbursts[st], fl = d_bflags[w];                // three independent loads: one latency (slots past the
-    const float hv = d_half[w];                                          // stream's last burst hold stale values, never used)
+    const uint32_t nbu = d_nbursts[st], fl = d_bflags[w];                // independent loads: one latency (slots past the stream's
+    const uint32_t hi = d_bend[w], lo = j ? d_bend[w - 1] + 1u : 0u;     // last burst hold stale values, never used)
     if (j >= nbu || !(fl & 1u)) return;                                  // never sent: no block carries its index
+    float mx = 0.0f;
+    const size_t end = (size_t)hi + 1 < n_blocks ? (size_t)hi + 1 : n_blocks;
+    for (size_t b0 = lo; b0 < end; b0 += 128) {                          // 128 blocks per step, all loads independent: one latency
+        int32_t tg[4]; float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t b = b0 + 32 * i + lane;
+            tg[i] = b < end ? d_tag[st * n_blocks + b] : -1;
+            v[i] = b < end ? d_max[st * n_blocks + b] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = tg[i] == (int32_t)j ? fmaxf(mx, v[i]) : mx;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    const float hv = __fdiv_rn(mx, 2.0f);                                // discretize :90-91 max/2f32
     const uint32_t h = warp_upper_bound(uniq, n_uniq, hv, lane);
-    if (lane == 0) d_hrank[w] = h;
+    if (lane == 0) { d_half[w] = hv; d_hrank[w] = h; }
 }
 
 __global__ void __launch_bounds__(KC1_WARPS * 32, 1)
@@ -1267,6 +1309,7 @@ extern "C" int lrc_ook_create(lrc_ctx *ctx, size_t n_streams, size_t n_blocks, u
 #define OOK_ALLOC(ptr, count) if (e == cudaSuccess) e = cudaMalloc(&o->ptr, (count) * sizeof(*o->ptr))
     OOK_ALLOC(d_sum, sb); OOK_ALLOC(d_max, sb); OOK_ALLOC(d_tag, sb);
     OOK_ALLOC(d_half, n_streams * o->max_bursts); OOK_ALLOC(d_bflags, n_streams * o->max_bursts);
+    OOK_ALLOC(d_bend, n_streams * o->max_bursts);
     OOK_ALLOC(d_nbursts, n_streams);
     OOK_ALLOC(d_trans, n_streams * o->max_runs); OOK_ALLOC(d_ntrans, n_streams); OOK_ALLOC(d_nbits, n_streams);
     OOK_ALLOC(d_packets, n_streams * 2 * o->max_packets); OOK_ALLOC(d_npackets, n_streams * 2);
@@ -1336,7 +1379,7 @@ extern "C" int lrc_ook_destroy(lrc_ook *o)
 {
     if (!o) return LRC_OK;
     cudaSetDevice(o->ctx->device);
-    cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags);
+    cudaFree(o->d_sum); cudaFree(o->d_max); cudaFree(o->d_tag); cudaFree(o->d_half); cudaFree(o->d_bflags); cudaFree(o->d_bend);
     cudaFree(o->d_nbursts); cudaFree(o->d_trans); cudaFree(o->d_ntrans); cudaFree(o->d_nbits);
     cudaFree(o->d_packets); cudaFree(o->d_npackets); cudaFree(o->d_runs_dbg); cudaFree(o->d_lut); cudaFree(o->d_flut);
     cudaFree(o->d_rank); cudaFree(o->d_uniq); cudaFree(o->d_mask); cudaFree(o->d_bsum); cudaFree(o->d_binfo); cudaFree(o->d_hrank); cudaFree(o->d_next);
@@ -1401,7 +1444,12 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     }
     LRC_CUDA(cudaGetLastError());
     ook_trigger_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KB_STREAMS), KB_THREADS, 0, s>>>(
-        o->d_sum, o->d_max, o->n_streams, o->n_blocks, o->max_bursts, o->guard_samples, o->d_tag, o->d_half, o->d_bflags, o->d_nbursts);
+        o->d_sum, o->n_streams, o->n_blocks, o->max_bursts, o->guard_samples, o->d_tag, o->d_bend, o->d_bflags, o->d_nbursts);
+    LRC_CUDA(cudaGetLastError());
+    const size_t kc1_blocks = std::min(ceil_div(groups, (size_t)KC1_WARPS), cap);
+    ook_burst_kernel<<<(unsigned)ceil_div(o->n_streams * o->max_bursts, (size_t)KC0_WARPS), KC0_WARPS * 32, 0, s>>>(
+        o->n_streams, o->n_blocks, o->max_bursts, o->d_max, o->d_tag, o->d_bend, o->d_bflags, o->d_nbursts, o->d_uniq, o->n_uniq,
+        o->d_half, o->d_hrank, o->d_next, (uint32_t)(3 * kc1_blocks * KC1_WARPS));
     LRC_CUDA(cudaGetLastError());
     // Which K-C: the one-warp-per-stream kernel needs many streams per SM to cover the latency of its walk (4096 streams: 240 us
     // against 296 us for rank thresholds + slice + scan + scatter); below about 14 streams per SM the split form wins (2048: a
@@ -1417,13 +1465,7 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
             o->d_uniq, o->n_uniq, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
         LRC_CUDA(cudaGetLastError());
     } else {
-        size_t blocks = ceil_div(groups, (size_t)KC1_WARPS);
-        if (blocks > cap) blocks = cap;
-        ook_rankthr_kernel<<<(unsigned)ceil_div(o->n_streams * o->max_bursts, (size_t)KC0_WARPS), KC0_WARPS * 32, 0, s>>>(
-            o->n_streams, o->max_bursts, o->d_half, o->d_bflags, o->d_nbursts, o->d_uniq, o->n_uniq, o->d_hrank, o->d_next,
-            (uint32_t)(3 * blocks * KC1_WARPS));
-        LRC_CUDA(cudaGetLastError());
-        ook_slice_kernel<<<(unsigned)blocks, KC1_WARPS * 32, OOK_RANK_BYTES, s>>>(
+        ook_slice_kernel<<<(unsigned)kc1_blocks, KC1_WARPS * 32, OOK_RANK_BYTES, s>>>(
             d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->d_rank, o->d_tag, o->d_hrank, o->d_next,
             o->d_mask, o->d_bsum);
         LRC_CUDA(cudaGetLastError());

@@ -481,6 +481,42 @@ def test_round2_index_models_exhaustive():
                     assert covered.all()
 
 
+def test_trigger_bookkeeping_from_masks_equals_the_blockwise_statements():
+    """ook_trigger_kernel, round 2: the walker leaves collect / send bit masks per tile of 32 blocks; the keeper steps from send to
+    send (buffer length by popc) and the helpers expand the tags (burst index at the start of the tile + sends before the block).
+    tools/models/index_models.py restates both that and bitfount.rs:52-54,73-81 taken block by block: same tags, same burst
+    events, same state -- with the reference's guard, a shrunk one (the block-by-block tiles near it) and a tiny burst capacity."""
+    import sys
+    import random
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models"))
+    import index_models as im
+    random.seed(1)
+
+    def masks(n_tiles, p_fire, long_run):
+        tiles, trig = [], 0
+        for t in range(n_tiles):
+            cm = sm = 0
+            nb = 32 if t < n_tiles - 1 else random.randint(1, 32)
+            for u in range(nb):
+                trig -= 1
+                if random.random() < (0.9 if long_run else p_fire):
+                    trig = 50 if long_run else random.choice([50, 50, 3, 2])
+                cm |= (trig > 1) << u
+                sm |= (trig == 0) << u
+            tiles.append((cm, sm, nb))
+        return tiles
+
+    n_events = 0
+    for it in range(300):
+        tiles = masks(random.randint(1, 20), random.choice([0.01, 0.05, 0.3]), it % 7 == 0)
+        for guard in (1000 * 50 * 512, 120 * 512, 40 * 512):
+            for cap in (1000, 3):
+                a, b = im.keeper_blockwise(tiles, guard, cap), im.keeper_send_to_send(tiles, guard, cap)
+                assert a == b
+                n_events += len(a[1])
+    assert n_events > 1000
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3

@@ -62,3 +62,64 @@ def chunk_plan(tile_in: int, step: int):
         hand = tile_in - 1 if (tile_in & 1) and s0 + step >= tile_in and s0 < tile_in else None
         out.append((c, s0, max(ns, 0), hand))
     return out
+
+
+# ---- OOK trigger kernel, round 2: book-keeping from the walker's masks ------------------------------------------------------
+# The walker leaves, per stream and tile of 32 blocks, cm (bit u: block u is collected, bitfount.rs:73) and sm (bit u: block u
+# sends, :78).  keeper_blockwise is the reference's statements taken block by block (the kernel's slow path, used where the OOM
+# guard :52-54 could fire); keeper_send_to_send / tags_from_masks are the fast path: the keeper steps from send to send counting
+# collected blocks with popc, the helpers expand tags as "burst index at the start of the tile + sends before the block".
+OOK_BLOCK_SAMPLES = 512
+
+
+def _keeper_tile_blockwise(cm, sm, nb, t, state, guard_samples, max_bursts, tags, events):
+    buf_len, lead0, burst, dropped = state
+    for u in range(nb):
+        if buf_len > guard_samples:                              # :52-54
+            if burst < max_bursts:
+                events.append((burst, 0, t * 32 + u - 1))
+            burst += 1; dropped = True; buf_len = 1; lead0 = True
+        collect = (cm >> u) & 1                                  # :73-75
+        buf_len += OOK_BLOCK_SAMPLES if collect else 0
+        tags.append(burst if (collect and burst < max_bursts) else -1)
+        if (sm >> u) & 1:                                        # :78-81
+            if burst < max_bursts:
+                events.append((burst, 1 | (2 if lead0 else 0), t * 32 + u))
+            burst += 1; buf_len = 0; lead0 = False
+    return buf_len, lead0, burst, dropped
+
+
+def keeper_blockwise(tiles, guard_samples, max_bursts):
+    """tiles: list of (cm, sm, nb).  Returns (tags per block, [(burst, flags, end block)], (buf_len, lead0, burst, dropped))."""
+    state, tags, events = (1, True, 0, False), [], []
+    for t, (cm, sm, nb) in enumerate(tiles):
+        state = _keeper_tile_blockwise(cm, sm, nb, t, state, guard_samples, max_bursts, tags, events)
+    return tags, events, state
+
+
+def keeper_send_to_send(tiles, guard_samples, max_bursts):
+    """The kernel's keeper: per tile the fast path unless the guard could fire in it (then block by block)."""
+    state, tags, events = (1, True, 0, False), [], []
+    popc = lambda x: bin(x & 0xFFFFFFFF).count("1")
+    for t, (cm, sm, nb) in enumerate(tiles):
+        buf_len, lead0, burst, dropped = state
+        if buf_len + 32 * OOK_BLOCK_SAMPLES > guard_samples:
+            state = _keeper_tile_blockwise(cm, sm, nb, t, state, guard_samples, max_bursts, tags, events)
+            continue
+        b0 = burst
+        rem, done = sm, 0
+        while rem:
+            u = (rem & -rem).bit_length() - 1
+            rem &= rem - 1
+            upto = (1 << u) - 1
+            buf_len += OOK_BLOCK_SAMPLES * popc(cm & upto & ~done)
+            done = upto | (1 << u)
+            if burst < max_bursts:
+                events.append((burst, 1 | (2 if lead0 else 0), t * 32 + u))
+            burst += 1; buf_len = 0; lead0 = False
+        buf_len += OOK_BLOCK_SAMPLES * popc(cm & ~done)
+        for u in range(nb):                                     # tags_out of the helpers
+            bi = b0 + popc(sm & ((1 << u) - 1))
+            tags.append(bi if ((cm >> u) & 1 and bi < max_bursts) else -1)
+        state = (buf_len, lead0, burst, dropped)
+    return tags, events, state
