@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1)
 ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
                size_t max_bursts, size_t max_runs, const uint16_t *__restrict__ g_rank,
                const int32_t *__restrict__ d_tag,
-               const float *__restrict__ d_half, const float *__restrict__ uniq, uint32_t n_uniq,
+               const uint32_t *__restrict__ d_hrank,
                const uint8_t *__restrict__ d_bflags, const uint32_t *__restrict__ d_nbursts,
                uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans, uint32_t *__restrict__ d_nbits)
 {
@@ -757,7 +757,7 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
     const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (st >= n_streams) return;
     const int32_t *tag = d_tag + st * n_blocks;
-    const float *half = d_half + st * max_bursts;
+    const uint32_t *hrank = d_hrank + st * max_bursts;
     const uint8_t *flags = d_bflags + st * max_bursts;
     uint32_t *trans = d_trans + st * max_runs;
     const uint8_t *base = iq + st * stream_stride;
@@ -783,7 +783,7 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
         if (tg != cur_burst) {
             lone_zero_bursts(cur_burst + 1, tg);
             cur_burst = tg;
-            h = warp_upper_bound(uniq, n_uniq, half[tg], lane);
+            h = hrank[tg];                                                    // ook_burst_kernel: #{values <= max/2}
             if (flags[tg] & 2u) {
                 // the burst starts with the literal 0.0 of vec!(0.0): 0.0 > max/2 is false -> bit 0
                 if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }
@@ -955,6 +955,8 @@ ook_burst_kernel(size_t n_streams, size_t n_blocks, size_t max_bursts, const flo
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     const float hv = __fdiv_rn(mx, 2.0f);                                // discretize :90-91 max/2f32
+    // (a two-level search -- every 32nd value staged in shared memory, one global load for the run that holds the boundary -- was
+    // measured slower: 15.3 us against 13.2 for 4096 streams; every CTA pays the staging and the barrier, most warps leave at once)
     const uint32_t h = warp_upper_bound(uniq, n_uniq, hv, lane);
     if (lane == 0) { d_half[w] = hv; d_hrank[w] = h; }
 }
@@ -1015,24 +1017,33 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
                     }
                 }
             };
-            take(kA, dA);
-            while (kA[0] >= 0) {
-                take(kB, dB);
+            // the group's rows of the two outputs: a block adds its index
+            uint16_t *mask_g = d_mask + (st * n_blocks + b0) * 32 + lane;
+            uint32_t *bsum_g = d_bsum + st * n_blocks + b0;
+            auto slice = [&](const int (&ks)[PF], const uint4 (&d)[PF][2]) {
 #pragma unroll
                 for (int i = 0; i < PF; ++i) {
-                    if (kA[i] < 0) continue;                              // warp-uniform
-                    const uint32_t hm1 = __shfl_sync(0xffffffffu, hm1_l, kA[i]);
-                    const uint32_t m = kc_slice16(rank_s, hm1, dA[i][0], dA[i][1]);
-                    const size_t blk = st * n_blocks + b0 + kA[i];
-                    d_mask[blk * 32 + lane] = (uint16_t)m;                // 64 contiguous bytes per block
+                    if (ks[i] < 0) continue;                              // warp-uniform
+                    const uint32_t hm1 = __shfl_sync(0xffffffffu, hm1_l, ks[i]);
+                    const uint32_t m = kc_slice16(rank_s, hm1, d[i][0], d[i][1]);
+                    mask_g[ks[i] * 32] = (uint16_t)m;                     // 64 contiguous bytes per block
                     const uint32_t tm = kc_inner_transitions(m, lane);
                     uint32_t cnt = 0;
                     if (__ballot_sync(0xffffffffu, tm != 0u) != 0u) cnt = __reduce_add_sync(0xffffffffu, __popc(tm));
-                    const uint32_t first = __shfl_sync(0xffffffffu, m, 0) & 1u, last = (__shfl_sync(0xffffffffu, m, 31) >> 15) & 1u;
-                    if (lane == 0) d_bsum[blk] = cnt | (first ? KC_SUM_FIRST : 0u) | (last ? KC_SUM_LAST : 0u);
+                    const uint32_t first = __ballot_sync(0xffffffffu, m & 1u) & 1u;              // lane 0, bit 0
+                    const uint32_t last = __ballot_sync(0xffffffffu, m & 0x8000u) >> 31;         // lane 31, bit 15
+                    if (lane == 0) bsum_g[ks[i]] = cnt | (first ? KC_SUM_FIRST : 0u) | (last ? KC_SUM_LAST : 0u);
                 }
-#pragma unroll
-                for (int i = 0; i < PF; ++i) { kA[i] = kB[i]; dA[i][0] = dB[i][0]; dA[i][1] = dB[i][1]; }
+            };
+            // two batches in turn: one is sliced while the other's loads are in flight (no register copies between them)
+            take(kA, dA);
+            while (true) {
+                take(kB, dB);
+                slice(kA, dA);
+                if (kB[0] < 0) break;
+                take(kA, dA);
+                slice(kB, dB);
+                if (kA[0] < 0) break;
             }
         }
         tg_l = tg_n1; hm1_l = hm1_n1; tg_n1 = tg_n2;
@@ -1451,18 +1462,18 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
         o->n_streams, o->n_blocks, o->max_bursts, o->d_max, o->d_tag, o->d_bend, o->d_bflags, o->d_nbursts, o->d_uniq, o->n_uniq,
         o->d_half, o->d_hrank, o->d_next, (uint32_t)(3 * kc1_blocks * KC1_WARPS));
     LRC_CUDA(cudaGetLastError());
-    // Which K-C: the one-warp-per-stream kernel needs many streams per SM to cover the latency of its walk (4096 streams: 240 us
-    // against 296 us for rank thresholds + slice + scan + scatter); below about 14 streams per SM the split form wins (2048: a
-    // tie, 1024: 0.296 against 0.337 ms for the whole chain, 512 -- one GPU's share of 4096 streams over eight -- 0.210 against
-    // 0.292).  LRC_OOK_KC = 0 / 1 forces one or the other for A/B runs; identical transition lists.
+    // Which K-C: the one-warp-per-stream kernel needs many streams per SM to cover the latency of its walk; below about 20 streams
+    // per SM the split form wins.  Whole chain, ms, one-warp-per-stream / split: 4096 streams 0.669 / 0.701, 2048 streams
+    // 0.433 / 0.407, 512 streams -- one GPU's share of 4096 over eight -- 0.272 / 0.184 (profiles/r2_aj_ook_forms.txt).
+    // LRC_OOK_KC = 0 / 1 forces one or the other for A/B runs; identical transition lists.
     static const int kc_env = getenv("LRC_OOK_KC") ? atoi(getenv("LRC_OOK_KC")) : -1;
-    const int kc = kc_env >= 0 ? kc_env : (o->n_streams <= (size_t)12 * o->ctx->n_sm ? 1 : 0);
+    const int kc = kc_env >= 0 ? kc_env : (o->n_streams <= (size_t)18 * o->ctx->n_sm ? 1 : 0);
     if (kc == 0) {
         size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
         if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
         ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
-            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_half,
-            o->d_uniq, o->n_uniq, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
+            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_hrank,
+            o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
         LRC_CUDA(cudaGetLastError());
     } else {
         ook_slice_kernel<<<(unsigned)kc1_blocks, KC1_WARPS * 32, OOK_RANK_BYTES, s>>>(
