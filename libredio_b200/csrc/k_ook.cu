@@ -5,21 +5,27 @@
 //   -> kpn::rle (kpn.rs:17-29) -> kpn::dle (:32-38) -> pulse-pair matchers (ratpak.rs:88-97)
 //   -> kpn::shaper_optional 36 / 24 (kpn.rs:266-275)
 //
-// The reference runs this as eight threads exchanging one message per SAMPLE.  Here it is four kernels
+// The reference runs this as eight threads exchanging one message per SAMPLE.  Here it is a handful of kernels
 // over all streams at once; every float operation that feeds a comparison is the same IEEE operation in
 // the same order as the reference (explicit __f*_rn / __d*_rn intrinsics, never contracted):
 //
-//   K-A ook_block_kernel : per 512-sample block, envelope of every sample, the strictly sequential f32
-//                          block sum `s` (bitfount.rs:48) and the block max (order-free, exact)
-//   K-B ook_trigger_kernel: one thread per stream walks its blocks through the trigger state machine
-//                          (:46-81), tags every block with the burst it is collected into, and keeps
-//                          max/2 per burst (discretize :90-91)
-//   K-C ook_rle_kernel   : one warp per stream re-derives the envelope of collected blocks, slices it
-//                          against the burst's max/2 into bit masks and emits the positions where the
-//                          continuous bit stream changes value (rle: runs span burst boundaries, the last
-//                          run is never flushed)
-//   K-D ook_match_kernel : one thread per stream: run lengths -> seconds (dle, IEEE f32 division) ->
-//                          matcher A and B -> shaper_optional -> packed packets
+//   K-A  ook_block_tma_kernel: per 512-sample block, envelope of every sample, the strictly sequential f32
+//                              block sum `s` (bitfount.rs:48) and the block max (order-free, exact)
+//   K-B  ook_trigger_kernel  : the trigger state machine (:46-81) per stream: a walker warp runs the dependent chain
+//                              (threshold, counter) and leaves collect / send bit masks, a keeper warp steps from send
+//                              to send (burst index, buffer length, OOM guard), helper warps stage the sums and expand
+//                              the masks into per-block tags (the burst a block is collected into, -1 = none)
+//   K-B2 ook_burst_kernel    : per sent burst its maximum (fold of the tagged blocks' maxima), max/2 (discretize
+//                              :90-91) and that threshold as a rank among the distinct envelope values
+//   K-C  the slicer + rle, in one of two forms with identical output (chosen per plan by streams per SM):
+//        ook_rle_kernel      : one warp per stream re-reads the collected blocks, slices them against the burst's
+//                              rank threshold into bit masks and emits the positions where the continuous bit stream
+//                              changes value (rle: runs span burst boundaries, the last run is never flushed)
+//        ook_slice_kernel + ook_scan_kernel + ook_scatter_kernel: every (stream, 32 blocks) sliced independently into
+//                              stored bit masks, a per-stream scan over per-block summaries places every block in the
+//                              bit stream and the transition list, every block writes its transitions in place
+//   K-D  ook_match_kernel    : per stream: run lengths -> seconds (dle, IEEE f32 division) -> matcher A and B ->
+//                              shaper_optional -> packed packets
 #include "common.cuh"
 #include "unpack.cuh"
 #include <cuda.h>
@@ -391,20 +397,22 @@ ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K-B: trigger state machine, one thread per stream (bitfount.rs:41-81, statement by statement)
+// K-B: trigger state machine (bitfount.rs:41-81, statement by statement), 32 streams per CTA
 //
-// The walk along a stream is one dependent chain (threshold -> compare -> trigger -> threshold ...): its length in
+// The walk along a stream is one dependent chain (threshold -> compare -> counter -> threshold ...): its length in
 // cycles IS the kernel's duration, whatever the number of streams.  Round 1 had every thread stage its tile, divide its
 // sums by 1000, walk, and write its tags back: ~2500 dependent-issue slots per 32-block tile on a warp that has an SM
-// sub-partition to itself (133 us for 500 blocks, 490 cycles per block).  Now a CTA is ONE walker warp (32 streams)
-// plus three helper warps that do everything that is not the chain, a tile ahead or behind the walker:
-//   helpers, iteration i : wait for the cp.async copies of tile i+1 (sums, maxima), q = s / 1000 (:63) for tile i+1,
-//                          tags of tile i-1 out to global memory (coalesced), cp.async of tile i+2
-//   walker,  iteration i : tile i from shared memory, eight blocks ahead into registers, the reference's statements
-//                          as selects (32 streams are in 32 different states: as branches every `if` would run both
-//                          sides one after the other), a branch only where a burst ends
-// one __syncthreads per tile.  A burst that is dropped (the OOM guard :52-54, or still open when the capture ends) keeps bit 0
-// of its flag clear and has its blocks un-tagged once all tags are in global memory.
+// sub-partition to itself (133 us for 500 blocks, 490 cycles per block).  Now a CTA is eight warps in three roles, a
+// tile of 32 blocks apart from each other and one __syncthreads per tile:
+//   helpers (6 warps), iteration i : wait for the cp.async copies of the sums of tile i+1 (issued two iterations ago),
+//                          q = s / 1000 (:63) for tile i+1, tags of tile i-2 out to global memory (expanded from the
+//                          masks, coalesced), cp.async of tile i+3
+//   walker,  iteration i : tile i from shared memory, eight blocks ahead into registers, the chain's statements as
+//                          selects (32 streams are in 32 different states: as branches every `if` would run both
+//                          sides one after the other); leaves the masks {counter > 1}, {counter == 0} of the tile
+//   keeper,  iteration i : tile i-1: burst index, buffer length and flags from the masks, send by send
+// A burst that is dropped (the OOM guard :52-54, or still open when the capture ends) keeps bit 0 of its flag clear and
+// has its blocks un-tagged once all tags are in global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp (and of the keeper warp)
 constexpr int KB_HELPERS = 192;               // helper threads (six warps: with three they, not the chain, set the pace)
@@ -1466,7 +1474,8 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
     // per SM the split form wins.  Whole chain, ms, one-warp-per-stream / split: 4096 streams 0.669 / 0.701, 2048 streams
     // 0.433 / 0.407, 512 streams -- one GPU's share of 4096 over eight -- 0.272 / 0.184 (profiles/r2_aj_ook_forms.txt).
     // LRC_OOK_KC = 0 / 1 forces one or the other for A/B runs; identical transition lists.
-    static const int kc_env = getenv("LRC_OOK_KC") ? atoi(getenv("LRC_OOK_KC")) : -1;
+    const char *kc_s = getenv("LRC_OOK_KC");                              // read at every call: a test runs both forms in one process
+    const int kc_env = kc_s && *kc_s ? atoi(kc_s) : -1;
     const int kc = kc_env >= 0 ? kc_env : (o->n_streams <= (size_t)18 * o->ctx->n_sm ? 1 : 0);
     if (kc == 0) {
         size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);

@@ -72,7 +72,7 @@ def check_against_oracle(caps, pk, dbg):
             assert np.array_equal(x, y)
 
 
-def test_ook_decodes_known_packets_bit_exact(ctx):
+def test_ook_decodes_known_packets_bit_exact(ctx, slicer_form):
     caps, sent = [], []
     for s in range(16):
         iq, snt = synth.ook_capture_u8(800, seed=4 + s, n_packets=3)
@@ -90,9 +90,20 @@ def test_ook_decodes_known_packets_bit_exact(ctx):
     assert sum(len(x) for x in sent) == len(pk) > 16
 
 
+@pytest.fixture(params=["per_plan", "one_warp_per_stream", "split"])
+def slicer_form(request, monkeypatch):
+    """the slicer has two forms with identical transition lists (k_ook.cu: ook_rle_kernel / ook_slice + scan + scatter); a plan picks
+    one by its streams per SM, LRC_OOK_KC forces one: the edge cases run through both"""
+    if request.param == "per_plan":
+        monkeypatch.delenv("LRC_OOK_KC", raising=False)
+    else:
+        monkeypatch.setenv("LRC_OOK_KC", "0" if request.param == "one_warp_per_stream" else "1")
+    return request.param
+
+
 @pytest.mark.parametrize("case", ["noise_only", "loud_noise", "ragged_blocks", "all_zero", "saturated", "burst_at_end",
                                   "long_gapped_burst_at_end", "gapped_bursts_sent"])
-def test_ook_edge_cases_match_oracle(ctx, case):
+def test_ook_edge_cases_match_oracle(ctx, case, slicer_form):
     rng = np.random.default_rng(hash(case) % 1000)
     if case == "noise_only":
         caps = [np.clip(np.rint(127 + 1.5 * rng.standard_normal(300 * 1024)), 0, 255).astype(np.uint8) for _ in range(3)]
@@ -131,7 +142,7 @@ def test_ook_edge_cases_match_oracle(ctx, case):
     check_against_oracle(caps, pk, dbg)
 
 
-def test_ook_oom_guard_path_matches_oracle_with_the_guard_shrunk_on_both_sides(ctx, monkeypatch):
+def test_ook_oom_guard_path_matches_oracle_with_the_guard_shrunk_on_both_sides(ctx, monkeypatch, slicer_form):
     """bitfount.rs:52-54: a buffer longer than 1000*50*512 samples is thrown away and collection restarts from [0.0].  The real
     constant needs 100 s of capture per stream, so the test shrinks it to 120 blocks in the oracle AND in the plan (test hooks on
     both sides) and drives every way through the guard: a long loud stretch cut into abandoned pieces whose remainder is sent with
