@@ -1046,7 +1046,9 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
             // two batches in turn: one is sliced while the other's loads are in flight (no register copies between them).
             // (A half-warp per block -- 32 samples = 64 bytes per lane, two blocks per step, half the per-block overhead per lane --
             // was measured slower: slice 254 us against 225 for 4096 streams, 0.185 against 0.184 ms for a 512-stream chain.  The
-            // kernel is not bound by its instruction count.)
+            // kernel is not bound by its instruction count.  Nor by the data in flight: three batches in turn on 20 warps x 102
+            // registers measured 232 us; nor by the L2 being asked for every 32-byte sector twice -- the two 128-bit loads of a
+            // lane share a sector -- since loads that allocate in L1 changed nothing, here and in ook_rle_kernel: tools/runs/r2ao.sh.)
             take(kA, dA);
             while (true) {
                 take(kB, dB);
