@@ -402,9 +402,9 @@ ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams,
 // The walk along a stream is one dependent chain (threshold -> compare -> counter -> threshold ...): its length in
 // cycles IS the kernel's duration, whatever the number of streams.  Round 1 had every thread stage its tile, divide its
 // sums by 1000, walk, and write its tags back: ~2500 dependent-issue slots per 32-block tile on a warp that has an SM
-// sub-partition to itself (133 us for 500 blocks, 490 cycles per block).  Now a CTA is eight warps in three roles, a
+// sub-partition to itself (133 us for 500 blocks, 490 cycles per block).  Now a CTA is 14 warps in three roles, a
 // tile of 32 blocks apart from each other and one __syncthreads per tile:
-//   helpers (6 warps), iteration i : wait for the cp.async copies of the sums of tile i+1 (issued two iterations ago),
+//   helpers (12 warps), iteration i: wait for the cp.async copies of the sums of tile i+1 (issued two iterations ago),
 //                          q = s / 1000 (:63) for tile i+1, tags of tile i-2 out to global memory (expanded from the
 //                          masks, coalesced), cp.async of tile i+3
 //   walker,  iteration i : tile i from shared memory, eight blocks ahead into registers, the chain's statements as
@@ -415,7 +415,7 @@ ook_block_tma_kernel(const __grid_constant__ CUtensorMap tmap, size_t n_streams,
 // has its blocks un-tagged once all tags are in global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int KB_STREAMS = 32;                // streams per CTA = lanes of the walker warp (and of the keeper warp)
-constexpr int KB_HELPERS = 192;               // helper threads (six warps: with three they, not the chain, set the pace)
+constexpr int KB_HELPERS = 384;               // helper threads (twelve warps: with three, then six, they -- not the chain -- set the pace)
 constexpr int KB_THREADS = 2 * KB_STREAMS + KB_HELPERS;
 constexpr int KB_TILE = 32;                   // blocks per staged tile
 constexpr int KB_LD = KB_TILE + 1;            // conflict-free both ways: helpers move rows, the walker reads columns
@@ -449,7 +449,7 @@ ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_b
     const bool walker = tid < KB_STREAMS;
     const bool keeper = tid >= KB_STREAMS && tid < 2 * KB_STREAMS;
     const bool helper = tid >= 2 * KB_STREAMS;
-    const int ht = tid - 2 * KB_STREAMS, hwarp = ht >> 5;              // helpers: warp w moves rows w, w + 6, ...
+    const int ht = tid - 2 * KB_STREAMS, hwarp = ht >> 5;              // helpers: warp w moves rows w, w + 12, ...
     const uint32_t mb = (uint32_t)(max_bursts < 0x7fffffffull ? max_bursts : 0x7fffffffull);
     // cp.async (LDGSTS) of tile `tile` into its buffer: a helper warp moves 32 consecutive floats of one stream per step
     auto stage = [&](int tile) {
@@ -505,6 +505,7 @@ ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_b
     // walker state
     int trigger = 0;                          // :41 (isize there; |trigger| <= n_blocks here)
     float threshold = 0.0f;                   // :44
+    bool fired = false, low2 = true;          // the block before did not fire, the counter two blocks back was below 2: 0 - 1 < 0
     // keeper state
     uint32_t buf_len = 1;                     // :43 sample_buffer = vec!(0.0); capped at the guard + 512 below
     bool lead0 = true;                        // the buffer currently starts with that 0.0
@@ -545,18 +546,30 @@ ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_b
                     for (int k = 0; k < 8; ++k) {
                         // (blocks past the end of a ragged last tile are walked too, on zero sums: their bits are masked off
                         // below and the walker's state is not used after the last tile)
+                        // `trigger < 0` after the decrement (:46, :62) is taken from PREDICATES instead of the counter: the counter
+                        // of the block before was `fired ? 50 : c - 1` (c: the counter two blocks back), so it is below 1 iff that
+                        // block did not fire and c < 2 -- the latter known a block early.  The threshold's critical path is then
+                        // compare -> predicate -> predicated add, not compare -> select -> compare -> predicated add.
+                        const bool upd = !fired && low2;
+                        low2 = trigger < 2;
                         trigger -= 1;                                                       // :46
                         const float s = sr[k];                                              // :48
                         // the chain is kept short: the `threshold == 0` case (:57-59) is evaluated beside the add it feeds -- both
                         // candidate sums exist before the select -- and the fire test s > threshold * 4 (:68-70) is made as
                         // s / 4 > threshold with s / 4 taken off the chain: both scalings by a power of two are exact (s is 0 or
                         // >= 0.0078, the smallest non-zero envelope), so the comparison is the same one
+                        // both outcomes of `threshold == 0` (:57-59) are carried through the update (:62-65) and selected at the end: the
+                        // one that starts from s never touches the chain, the other is three dependent operations from the old threshold
                         const bool unset = threshold == 0.0f;                               // :57-59
+                        const float a1 = __fadd_rn(s, qr[k]);                               // :62-65 from threshold = s
+                        const float a2 = __fsub_rn(a1, __fmul_rn(a1, 0.002f));
+                        const float b1 = __fadd_rn(threshold, qr[k]);                       // :62-65 from the old threshold
+                        const float b2 = __fsub_rn(b1, __fmul_rn(b1, 0.002f));
                         const float thr0 = unset ? s : threshold;
-                        const float thr1 = unset ? __fadd_rn(s, qr[k]) : __fadd_rn(threshold, qr[k]);   // :62-65
-                        const float thr2 = __fsub_rn(thr1, __fmul_rn(thr1, 0.002f));
-                        threshold = trigger < 0 ? thr2 : thr0;
-                        trigger = __fmul_rn(s, 0.25f) > threshold ? OOK_TRIGGER_DURATION : trigger;  // :68-70
+                        const float thr2 = unset ? a2 : b2;
+                        threshold = upd ? thr2 : thr0;                                      // upd == (trigger < 0)
+                        fired = __fmul_rn(s, 0.25f) > threshold;                            // :68-70
+                        trigger = fired ? OOK_TRIGGER_DURATION : trigger;
                         // what the book-keeping needs of the counter: collect (:73) and send (:78)
                         c8 |= (trigger > 1 ? 1u : 0u) << k;
                         s8 |= (trigger == 0 ? 1u : 0u) << k;
@@ -642,14 +655,16 @@ ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_b
     }
     __syncthreads();
     // The unsent burst's blocks end within the last two blocks of the capture (it is still being collected, or the counter just
-    // reached 1) and lie at most one block apart.  Each warp takes eight streams: the last 64 tags of all eight are loaded first
-    // (independent loads, one latency), matched and cleared; a run longer than that (rare) is followed backwards chunk by chunk.
+    // reached 1) and lie at most one block apart.  The warps share the streams out (warp w: streams w, w + 14, w + 28): the last 64
+    // tags of a warp's streams are loaded first (independent loads, one latency), matched and cleared; a run longer than that
+    // (rare) is followed backwards chunk by chunk.
     {
+        constexpr int NW = KB_THREADS / 32, NJ = (KB_STREAMS + NW - 1) / NW;
         const int w = tid >> 5;
-        int32_t t0[8], t1[8];
+        int32_t t0[NJ], t1[NJ];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = w * 8 + j;
+        for (int j = 0; j < NJ; ++j) {
+            const int r = w + NW * j;
             const size_t s = st0 + r;
             const long long k0 = (long long)n_blocks - 1 - lane, k1 = k0 - 32;
             const bool on = r < KB_STREAMS && s < n_streams && s_open[r];
@@ -657,8 +672,8 @@ ook_trigger_kernel(const float *__restrict__ d_sum, size_t n_streams, size_t n_b
             t1[j] = on && k1 >= 0 ? d_tag[s * n_blocks + k1] : -1;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = w * 8 + j;
+        for (int j = 0; j < NJ; ++j) {
+            const int r = w + NW * j;
             const size_t s = st0 + r;
             if (r >= KB_STREAMS || s >= n_streams || !s_open[r]) continue;     // warp-uniform
             int32_t *tag = d_tag + s * n_blocks;
