@@ -517,6 +517,71 @@ def test_trigger_bookkeeping_from_masks_equals_the_blockwise_statements():
     assert n_events > 1000
 
 
+def test_split_slicer_model_equals_the_sequential_walk_and_the_flattened_bit_stream():
+    """ook_slice_kernel / ook_scan_kernel / ook_scatter_kernel place every collected block in the bit stream and in the transition
+    list from per-block summaries and prefix sums, 32 blocks per step; ook_rle_kernel walks the blocks in order.  Both are restated
+    in tools/models/index_models.py and compared with the plainest statement there is: flatten the sent bursts (leading 0.0 bit,
+    lone [0.0] bursts of the OOM guard, abandoned bursts contributing nothing) and record where the value changes (kpn.rs:17-29)."""
+    import sys
+    import random
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "models"))
+    import index_models as im
+    random.seed(3)
+
+    def stream(n_blocks, p_lone, noisy):
+        blocks, flags, burst, k, first = [], [], 0, 0, True
+        while k < n_blocks:
+            for _ in range(min(random.randint(0, 40), n_blocks - k)):
+                blocks.append((-1, None)); k += 1
+            if k >= n_blocks:
+                break
+            while random.random() < p_lone:                      # abandoned (0) or lone [0.0] (3) bursts in front of this one
+                flags.append(random.choice([0, 3])); burst += 1
+            flags.append(1 | (2 if (first or random.random() < 0.3) else 0)); first = False
+            for i in range(min(random.randint(1, 70), n_blocks - k)):
+                if i and random.random() < 0.1:                  # a hole: the block at counter 1 is not collected
+                    blocks.append((-1, None)); k += 1
+                    continue
+                m = random.random()
+                if m < 0.5:
+                    bits = [0] * 512
+                elif m < 0.6:
+                    bits = [1] * 512
+                elif noisy:
+                    bits = [random.getrandbits(1) for _ in range(512)]
+                else:
+                    bits, v = [], random.getrandbits(1)
+                    while len(bits) < 512:
+                        bits += [v] * random.randint(1, 200); v ^= 1
+                    bits = bits[:512]
+                blocks.append((burst, bits)); k += 1
+            burst += 1
+        while random.random() < p_lone:
+            flags.append(random.choice([0, 3])); burst += 1
+        return blocks, flags, burst
+
+    def flattened(blocks, flags, n_bursts):
+        flat = []
+        for j in range(n_bursts):
+            if not flags[j] & 1:
+                continue
+            if flags[j] & 2:
+                flat.append(0)
+            for t, b in blocks:
+                if t == j:
+                    flat += b
+        return [i for i in range(1, len(flat)) if flat[i] != flat[i - 1]], len(flat)
+
+    n_tr = 0
+    for it in range(120):
+        blocks, flags, nb = stream(random.randint(1, 300), random.choice([0, 0.2, 0.5]), it % 3 == 0)
+        want = flattened(blocks, flags, nb)
+        assert im.rle_walk(blocks, flags, nb) == want
+        assert im.rle_split(blocks, flags, nb) == want
+        n_tr += len(want[0])
+    assert n_tr > 100_000
+
+
 def test_defined_stages_sanity():
     w = D.hann_periodic(1024)
     assert w[0] == 0 and w[512] == 1 and abs(w.sum() - 512) < 1e-3

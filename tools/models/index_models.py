@@ -123,3 +123,99 @@ def keeper_send_to_send(tiles, guard_samples, max_bursts):
             tags.append(bi if ((cm >> u) & 1 and bi < max_bursts) else -1)
         state = (buf_len, lead0, burst, dropped)
     return tags, events, state
+
+
+# ---- OOK slicer, split form: summaries -> scan -> scatter against the sequential walk ---------------------------------------
+# A stream is a list of blocks (tag, bits): tag = index of the burst the block is collected into (-1: not collected), bits = its
+# 512 slicer outputs.  flags[j] of burst j: bit 0 sent, bit 1 the burst starts with the 0.0 of vec!(0.0) (one 0 bit); a burst with
+# flags 3 and no tagged block is the lone [0.0] the OOM guard leaves behind (bitfount.rs:52-54, :78-81).  rle_walk is what
+# ook_rle_kernel does (and kpn::rle on the flattened bit stream, kpn.rs:17-29: a position is recorded where the value changes);
+# rle_split restates ook_slice_kernel's summaries, ook_scan_kernel's 32-block steps with their carry and ook_scatter_kernel.
+def rle_walk(blocks, flags, n_bursts):
+    pos, prev, trans, cur = 0, 0, [], -1
+
+    def zero_bit():
+        nonlocal pos, prev
+        if pos > 0 and prev != 0:
+            trans.append(pos)
+        prev = 0
+        pos += 1
+
+    def lone(frm, to):
+        for j in range(frm, to):
+            if flags[j] & 3 == 3:
+                zero_bit()
+
+    for tag, bits in blocks:
+        if tag < 0:
+            continue
+        if tag != cur:
+            lone(cur + 1, tag)
+            cur = tag
+            if flags[tag] & 2:
+                zero_bit()
+        for b in bits:
+            if pos > 0 and b != prev:
+                trans.append(pos)
+            prev = b
+            pos += 1
+    lone(cur + 1, n_bursts)
+    return trans, pos
+
+
+def rle_split(blocks, flags, n_bursts):
+    # C1: per collected block {transitions between its own bits, first bit, last bit}
+    summ = [None if t < 0 else (sum(1 for i in range(1, len(b)) if b[i] != b[i - 1]), b[0], b[-1]) for t, b in blocks]
+    lone = lambda frm, to: sum(1 for j in range(frm, to) if flags[j] & 3 == 3)
+    # C2: 32 blocks per step, everything inside a step from prefix sums, (pos, ntr, prev, cur) carried between steps
+    pos, ntr, prev, cur = 0, 0, 0, -1
+    info = [None] * len(blocks)
+    tail = []
+    for g0 in range(0, len(blocks), 32):
+        grp = range(g0, min(g0 + 32, len(blocks)))
+        col = [k for k in grp if blocks[k][0] >= 0]
+        if not col:
+            continue
+        n_ins, ptag, plast = {}, {}, {}
+        for i, k in enumerate(col):                               # the collected block before this one: in the group, or the carry
+            ptag[k] = blocks[col[i - 1]][0] if i else cur
+            plast[k] = summ[col[i - 1]][2] if i else prev
+            tg = blocks[k][0]
+            n_ins[k] = (lone(ptag[k] + 1, tg) + (1 if flags[tg] & 2 else 0)) if tg != ptag[k] else 0
+        excl_bits, excl_tr = 0, 0
+        for k in col:
+            cnt, first, last = summ[k]
+            pos_ins = pos + excl_bits
+            pos_base = pos_ins + n_ins[k]
+            before = 0 if n_ins[k] else plast[k]
+            pre = n_ins[k] > 0 and pos_ins > 0 and plast[k] != 0
+            first_t = pos_base > 0 and first != before
+            info[k] = (pos_base, ntr + excl_tr, pos_ins, pre, first_t)
+            excl_bits += 512 + n_ins[k]
+            excl_tr += cnt + int(pre) + int(first_t)
+        pos += excl_bits
+        ntr += excl_tr
+        cur = blocks[col[-1]][0]
+        prev = summ[col[-1]][2]
+    n = lone(cur + 1, n_bursts)
+    if n:
+        if pos > 0 and prev != 0:
+            tail.append((ntr, pos))
+            ntr += 1
+        pos += n
+    # C3: every block writes its transitions at its place
+    trans = [None] * ntr
+    for k, (t, b) in enumerate(blocks):
+        if t < 0:
+            continue
+        pos_base, o, pos_ins, pre, first_t = info[k]
+        if pre:
+            trans[o] = pos_ins; o += 1
+        if first_t:
+            trans[o] = pos_base; o += 1
+        for i in range(1, len(b)):
+            if b[i] != b[i - 1]:
+                trans[o] = pos_base + i; o += 1
+    for o, p in tail:
+        trans[o] = p
+    return trans, pos
