@@ -1004,7 +1004,9 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
     // Groups are handed out through a counter: the work in a group is the number of its collected blocks, 0 to 32, and bursts sit
     // at similar places in similar streams -- with a fixed stride (4144 warps = 259 x 16 groups per stream) a warp met the SAME
     // place of every stream it visited: 13 of 28 warps per SM busy on average, 340 us.  The first three groups of a warp are fixed
-    // (no start-up latency), the counter -- set to 3 x warps by ook_rankthr_kernel -- gives out the rest three groups ahead.
+    // (no start-up latency), the counter -- set to 3 x warps by ook_burst_kernel -- gives out the rest three groups ahead.
+    // (Handing out everything but a warp's first group through the counter was measured too: 2 % faster at 2048 and 4096 streams,
+    // but a 512-stream shard -- two groups per warp, no steady state -- pays the start-up: slice 50 -> 59 us.  tools/runs/r2aw.sh)
     const uint32_t gps = (uint32_t)groups_per_stream, ng = (uint32_t)n_groups;
     auto tag_of = [&](uint32_t g) -> int32_t {
         if (g >= ng) return -1;
