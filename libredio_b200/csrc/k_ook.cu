@@ -993,7 +993,9 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
     for (int i = threadIdx.x; i < OOK_RANK_BYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(kc_rank)[i] = __ldg(reinterpret_cast<const uint4 *>(g_rank) + i);
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp index through a shuffle: the compiler then knows it -- and the group loop that starts from it -- is warp-uniform, and
+    // leaves out the divergence guards (BRA.DIV / WARPSYNC.COLLECTIVE) it put around every vote and shuffle of the loop
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const uint32_t rank_s = smem_u32(kc_rank);
     const size_t groups_per_stream = (n_blocks + 31) / 32;
     const size_t n_groups = groups_per_stream * n_streams;
