@@ -759,7 +759,7 @@ __device__ __forceinline__ uint32_t warp_upper_bound(const float *__restrict__ u
     return lo;
 }
 
-constexpr int KC_THREADS = 1024;             // at most 32 streams per CTA, one CTA per SM (the table fills its shared memory).  The launch
+constexpr int KC_THREADS = 896;              // at most 28 streams per CTA, one CTA per SM (the table fills its shared memory).  The launch
                                              // uses ceil(n_streams / n_sm) warps per CTA so that every SM gets the same number of streams
                                              // (4096 streams: 147 CTAs of 28 warps instead of 128 CTAs of 32 with 20 SMs idle)
 
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1)
 ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks,
                size_t max_bursts, size_t max_runs, const uint16_t *__restrict__ g_rank,
                const int32_t *__restrict__ d_tag,
-               const uint32_t *__restrict__ d_hrank,
+               const uint32_t *__restrict__ d_hrank, const float *__restrict__ d_half, const float *__restrict__ d_max,
                const uint8_t *__restrict__ d_bflags, const uint32_t *__restrict__ d_nbursts,
                uint32_t *__restrict__ d_trans, uint32_t *__restrict__ d_ntrans, uint32_t *__restrict__ d_nbits)
 {
@@ -781,9 +781,16 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
     if (st >= n_streams) return;
     const int32_t *tag = d_tag + st * n_blocks;
     const uint32_t *hrank = d_hrank + st * max_bursts;
+    const float *half = d_half + st * max_bursts;
+    const float *bmax = d_max + st * n_blocks;
     const uint8_t *flags = d_bflags + st * max_bursts;
     uint32_t *trans = d_trans + st * max_runs;
     const uint8_t *base = iq + st * stream_stride;
+    // QUIET BLOCKS.  The block-sum kernel left every block's maximum; a collected block whose maximum does not exceed the burst's
+    // max/2 slices to 512 zeros (x <= block max <= max/2 for each of its samples: `x > max/2` is false, bitfount.rs:91) -- without
+    // being read.  That is the noise the trigger keeps collecting for 49 blocks after a burst and most of the gaps between the
+    // pulses of a packet: the slicer's share of the capture drops from the collected half to the blocks that hold a pulse.
+    float half_cur = -1.0f;      // max/2 of the current burst (no block maximum is below 0: nothing is quiet before a burst is entered)
     uint32_t pos = 0;            // length of the bit stream so far
     uint32_t ntr = 0;            // transitions so far
     uint32_t prev = 0;           // value of the last bit (meaningful once pos > 0)
@@ -802,16 +809,22 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
             }
         }
     };
-    auto process = [&](int32_t tg, const uint4 &q0, const uint4 &q1) {
+    auto process = [&](int32_t tg, float mxk, const uint4 &q0, const uint4 &q1) {
         if (tg != cur_burst) {
             lone_zero_bursts(cur_burst + 1, tg);
             cur_burst = tg;
             h = hrank[tg];                                                    // ook_burst_kernel: #{values <= max/2}
+            half_cur = half[tg];
             if (flags[tg] & 2u) {
                 // the burst starts with the literal 0.0 of vec!(0.0): 0.0 > max/2 is false -> bit 0
                 if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }
                 prev = 0u; pos += 1;
             }
+        }
+        if (mxk <= half_cur) {                                                // quiet: 512 zeros (its samples were not even fetched
+            if (pos > 0 && prev != 0u) { if (lane == 0 && ntr < max_runs) trans[ntr] = pos; ntr++; }   // when the burst was known)
+            prev = 0u; pos += OOK_BLOCK;
+            return;
         }
         const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         uint32_t m = 0;
@@ -860,23 +873,33 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
     // 2 x PF KB in flight instead of one block (the walk along a stream is sequential)
     constexpr int PF = 2;
     int32_t tg_next = lane < (int)n_blocks ? tag[lane] : -1;
+    float mx_next = lane < (int)n_blocks ? bmax[lane] : 0.0f;
     for (size_t b0 = 0; b0 < n_blocks; b0 += 32) {
         const int32_t tg_l = tg_next;
+        const float mx_l = mx_next;
         {
-            const size_t bn = b0 + 32 + lane;                                 // the next group's tags are on their way
+            const size_t bn = b0 + 32 + lane;                                 // the next group's tags and maxima are on their way
             tg_next = bn < n_blocks ? tag[bn] : -1;
+            mx_next = bn < n_blocks ? bmax[bn] : 0.0f;
         }
         unsigned rem = __ballot_sync(0xffffffffu, tg_l >= 0);
         int kA[PF], kB[PF];
         uint4 dA[PF][2], dB[PF][2];
+        // a block is fetched unless it is known to be quiet already: same burst as the one being sliced (its max/2 is at hand) and a
+        // maximum that does not exceed it.  Tags do not decrease along a stream, so the burst cannot change between this decision
+        // and the block's turn; a block of a burst not entered yet is fetched and judged when its turn comes.
         auto take = [&](int (&ks)[PF], uint4 (&d)[PF][2]) {
 #pragma unroll
             for (int i = 0; i < PF; ++i) {
                 ks[i] = rem ? __ffs(rem) - 1 : -1;
                 if (rem) rem &= rem - 1;
                 if (ks[i] >= 0) {
-                    const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + ks[i]) * (size_t)(OOK_BLOCK * 2) + lane * 32);
-                    d[i][0] = ldg_stream_u4(p); d[i][1] = ldg_stream_u4(p + 1);
+                    const int32_t tgk = __shfl_sync(0xffffffffu, tg_l, ks[i]);
+                    const float mxk = __shfl_sync(0xffffffffu, mx_l, ks[i]);
+                    if (!(tgk == cur_burst && mxk <= half_cur)) {
+                        const uint4 *p = reinterpret_cast<const uint4 *>(base + (b0 + ks[i]) * (size_t)(OOK_BLOCK * 2) + lane * 32);
+                        d[i][0] = ldg_stream_u4(p); d[i][1] = ldg_stream_u4(p + 1);
+                    }
                 }
             }
         };
@@ -885,7 +908,8 @@ ook_rle_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_st
             take(kB, dB);
 #pragma unroll
             for (int i = 0; i < PF; ++i)
-                if (kA[i] >= 0) process(__shfl_sync(0xffffffffu, tg_l, kA[i]), dA[i][0], dA[i][1]);
+                if (kA[i] >= 0)
+                    process(__shfl_sync(0xffffffffu, tg_l, kA[i]), __shfl_sync(0xffffffffu, mx_l, kA[i]), dA[i][0], dA[i][1]);
 #pragma unroll
             for (int i = 0; i < PF; ++i) { kA[i] = kB[i]; dA[i][0] = dB[i][0]; dA[i][1] = dB[i][1]; }
         }
@@ -987,6 +1011,7 @@ ook_burst_kernel(size_t n_streams, size_t n_blocks, size_t max_bursts, const flo
 __global__ void __launch_bounds__(KC1_WARPS * 32, 1)
 ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_streams, size_t n_blocks, size_t max_bursts,
                  const uint16_t *__restrict__ g_rank, const int32_t *__restrict__ d_tag, const uint32_t *__restrict__ d_hrank,
+                 const float *__restrict__ d_half, const float *__restrict__ d_max,
                  uint32_t *__restrict__ d_next, uint16_t *__restrict__ d_mask, uint32_t *__restrict__ d_bsum)
 {
     extern __shared__ __align__(16) uint16_t kc_rank[];
@@ -1018,17 +1043,26 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
     auto thr_of = [&](uint32_t g, int32_t tg) -> uint32_t {
         return tg >= 0 ? d_hrank[(size_t)(g / gps) * max_bursts + tg] - 1u : 0u;           // rank >= h  <=>  (h - 1) - rank < 0
     };
+    // quiet block (see ook_rle_kernel): its maximum does not exceed the burst's max/2, it slices to 512 zeros without being read
+    auto quiet_of = [&](uint32_t g, int32_t tg) -> bool {
+        if (tg < 0) return false;
+        const size_t st = g / gps;
+        return d_max[st * n_blocks + (size_t)(g % gps) * 32 + lane] <= d_half[st * max_bursts + tg];
+    };
     const uint32_t wt = (uint32_t)warps_total;
     uint32_t g0 = blockIdx.x * KC1_WARPS + warp, g1 = g0 + wt, g2 = g1 + wt;
     int32_t tg_l = tag_of(g0), tg_n1 = tag_of(g1);
     uint32_t hm1_l = thr_of(g0, tg_l);
+    bool q_l = quiet_of(g0, tg_l);
     while (g0 < ng) {
         uint32_t g3 = 0;
         if (lane == 0) g3 = atomicAdd(d_next, 1u);                         // consumed at the end of the iteration
         const uint32_t hm1_n1 = thr_of(g1, tg_n1);
+        const bool q_n1 = quiet_of(g1, tg_n1);
         const int32_t tg_n2 = tag_of(g2);
         const size_t st = g0 / gps, b0 = (size_t)(g0 % gps) * 32;
-        unsigned rem = __ballot_sync(0xffffffffu, tg_l >= 0);
+        if (tg_l >= 0 && q_l) d_bsum[st * n_blocks + b0 + lane] = 0u;      // quiet: no transition inside, first and last bit 0
+        unsigned rem = __ballot_sync(0xffffffffu, tg_l >= 0 && !q_l);
         if (rem != 0u) {
             const uint8_t *base = iq + st * stream_stride + b0 * (size_t)(OOK_BLOCK * 2);
             int kA[PF], kB[PF];
@@ -1078,7 +1112,7 @@ ook_slice_kernel(const uint8_t *__restrict__ iq, size_t stream_stride, size_t n_
                 if (kA[0] < 0) break;
             }
         }
-        tg_l = tg_n1; hm1_l = hm1_n1; tg_n1 = tg_n2;
+        tg_l = tg_n1; hm1_l = hm1_n1; q_l = q_n1; tg_n1 = tg_n2;
         g0 = g1; g1 = g2; g2 = __shfl_sync(0xffffffffu, g3, 0);
     }
 }
@@ -1494,24 +1528,25 @@ extern "C" int lrc_ook_decode(lrc_ook *o, const uint8_t *d_iq, size_t stream_str
         o->n_streams, o->n_blocks, o->max_bursts, o->d_max, o->d_tag, o->d_bend, o->d_bflags, o->d_nbursts, o->d_uniq, o->n_uniq,
         o->d_half, o->d_hrank, o->d_next, (uint32_t)(3 * kc1_blocks * KC1_WARPS));
     LRC_CUDA(cudaGetLastError());
-    // Which K-C: the one-warp-per-stream kernel needs many streams per SM to cover the latency of its walk; below about 20 streams
-    // per SM the split form wins.  Whole chain, ms, one-warp-per-stream / split: 4096 streams 0.669 / 0.701, 2048 streams
-    // 0.433 / 0.407, 512 streams -- one GPU's share of 4096 over eight -- 0.272 / 0.184 (profiles/r2_aj_ook_forms.txt).
-    // LRC_OOK_KC = 0 / 1 forces one or the other for A/B runs; identical transition lists.
+    // Which K-C.  Until quiet blocks were skipped the one-warp-per-stream kernel won where an SM had 20 or more streams to itself (its
+    // walk's latency covered by 28 warps); with them skipped the split form wins at every size measured -- whole chain, ms,
+    // one-warp-per-stream / split: 4096 streams 0.596 / 0.571, 3072 0.493 / 0.452, 2048 0.391 / 0.335, 1024 0.292 / 0.220, 512 -- one
+    // GPU's share of 4096 over eight -- 0.253 / 0.163 (profiles/r2_bb_ook_forms.txt) -- and is the default.  LRC_OOK_KC = 0 / 1 forces
+    // one or the other for A/B runs and for the tests that put both through the same cases; identical transition lists.
     const char *kc_s = getenv("LRC_OOK_KC");                              // read at every call: a test runs both forms in one process
     const int kc_env = kc_s && *kc_s ? atoi(kc_s) : -1;
-    const int kc = kc_env >= 0 ? kc_env : (o->n_streams <= (size_t)18 * o->ctx->n_sm ? 1 : 0);
+    const int kc = kc_env >= 0 ? kc_env : 1;
     if (kc == 0) {
         size_t kc_warps = ceil_div(o->n_streams, (size_t)o->ctx->n_sm);
         if (kc_warps > KC_THREADS / 32) kc_warps = KC_THREADS / 32;
         ook_rle_kernel<<<(unsigned)ceil_div(o->n_streams, kc_warps), (unsigned)(kc_warps * 32), OOK_RANK_BYTES, s>>>(
             d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_rank, o->d_tag, o->d_hrank,
-            o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
+            o->d_half, o->d_max, o->d_bflags, o->d_nbursts, o->d_trans, o->d_ntrans, o->d_nbits);
         LRC_CUDA(cudaGetLastError());
     } else {
         ook_slice_kernel<<<(unsigned)kc1_blocks, KC1_WARPS * 32, OOK_RANK_BYTES, s>>>(
-            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->d_rank, o->d_tag, o->d_hrank, o->d_next,
-            o->d_mask, o->d_bsum);
+            d_iq, stream_stride_bytes, o->n_streams, o->n_blocks, o->max_bursts, o->d_rank, o->d_tag, o->d_hrank, o->d_half,
+            o->d_max, o->d_next, o->d_mask, o->d_bsum);
         LRC_CUDA(cudaGetLastError());
         ook_scan_kernel<<<(unsigned)ceil_div(o->n_streams, (size_t)KC2_WARPS), KC2_WARPS * 32, 0, s>>>(
             o->n_streams, o->n_blocks, o->max_bursts, o->max_runs, o->d_tag, o->d_bsum, o->d_bflags, o->d_nbursts, o->d_binfo,
