@@ -172,6 +172,42 @@ def test_ook_oom_guard_path_matches_oracle_with_the_guard_shrunk_on_both_sides(c
     check_against_oracle(caps[:6], pk, dbg)
 
 
+def test_ook_quiet_block_boundary_block_maximum_equal_to_half_the_burst_maximum(ctx, slicer_form):
+    """The slicer does not read a collected block whose maximum does not exceed the burst's max/2 (k_ook.cu, quiet blocks): such a
+    block is 512 zeros because `x > max/2` (bitfount.rs:91) is false for x <= max/2 -- INCLUDING equality.  Byte pairs whose envelope
+    is exactly half of another pair's exist (2229 of the distinct values): (78, 115) is 0.3972283, (29, 103) twice that.  A burst
+    whose maximum is the latter gets one block that peaks exactly at max/2 (all zeros, not read) and one that peaks at the next
+    envelope value above it (one 1 bit: must be read); everything against the oracle, through both slicer forms."""
+    env = lambda b0, b1: oracle.norm(oracle.i2f(b0), oracle.i2f(b1))
+    top, mid = (29, 103), (78, 115)
+    assert np.float32(env(*top)) / np.float32(2) == np.float32(env(*mid))
+    # the smallest envelope above max/2, by brute force over the byte pairs
+    above = min(((env(a, b), a, b) for a in range(0, 256, 1) for b in (103, 115, 127, 140) if env(a, b) > env(*mid)))
+    rng = np.random.default_rng(12)
+    n_blocks = 260
+
+    def floor_block():
+        return np.clip(np.rint(127 + 1.2 * rng.standard_normal(1024)), 0, 255).astype(np.uint8)
+
+    blocks = [floor_block() for _ in range(n_blocks)]
+    loud = floor_block()
+    loud[0:600:2], loud[1:600:2] = 200, 60                       # fires the trigger; envelope below the top pair's
+    loud[700], loud[701] = top                                   # the burst's maximum
+    assert max(env(200, 60), env(*mid)) < env(*top)
+    blocks[100] = loud
+    at_half = floor_block(); at_half[300], at_half[301] = mid; at_half[640], at_half[641] = mid[::-1]
+    blocks[103] = at_half                                        # block maximum == max/2: quiet by equality
+    just_above = floor_block(); just_above[500], just_above[501] = above[1], above[2]
+    blocks[105] = just_above                                     # block maximum just above max/2: one sample is a 1
+    cap = np.concatenate(blocks)
+    r = oracle.ook_decode(cap)
+    assert r["n_bursts"] == 1 and r["bits"].size == 1 + 49 * 512
+    ones = np.flatnonzero(r["bits"])
+    assert 1 + 5 * 512 + 250 in ones and not np.any((ones > 1 + 3 * 512) & (ones <= 1 + 4 * 512))   # block 105 has its 1, block 103 none
+    pk, dbg = run_ook(ctx, [cap, cap[::-1].copy(), cap], max_runs=1 << 12)
+    check_against_oracle([cap, cap[::-1].copy(), cap], pk, dbg)
+
+
 @pytest.mark.parametrize("n_blocks", [1, 5, 31, 32, 33, 65])
 def test_ook_captures_shorter_than_a_warp_group(ctx, n_blocks):
     """the block-sum kernel's TMA box is 32 blocks tall: captures with fewer blocks (and a ragged second group) rely on the
