@@ -378,7 +378,7 @@ def run_extras(ctx, world, rank, peak_hbm, quick=False):
         dist.all_reduce(n_pk)
     entry("config4_ook_4096_streams", ns, ms, best, "hbm", ns * 2.0,
           workload=f"{n_streams} streams x {n_blocks} blocks of 512 u8 IQ samples, {n_streams // world} streams per GPU, "
-                   "envelope -> trigger -> slicer -> rle -> matchers -> packets (bit-exact chain; slicer form chosen by streams per SM)",
+                   "envelope -> trigger -> slicer -> rle -> matchers -> packets (bit-exact chain; blocks that cannot hold a 1 bit are sliced unread)",
           scaling="strong", packets_decoded=int(n_pk.item()))
     ook.close()
     del iq

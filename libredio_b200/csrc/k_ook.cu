@@ -17,7 +17,8 @@
 //                              the masks into per-block tags (the burst a block is collected into, -1 = none)
 //   K-B2 ook_burst_kernel    : per sent burst its maximum (fold of the tagged blocks' maxima), max/2 (discretize
 //                              :90-91) and that threshold as a rank among the distinct envelope values
-//   K-C  the slicer + rle, in one of two forms with identical output (chosen per plan by streams per SM):
+//   K-C  the slicer + rle, in one of two forms with identical output (the split form is the default, LRC_OOK_KC=0 selects the
+//        walk); neither reads a collected block whose maximum does not exceed the burst's max/2 (512 zeros):
 //        ook_rle_kernel      : one warp per stream re-reads the collected blocks, slices them against the burst's
 //                              rank threshold into bit masks and emits the positions where the continuous bit stream
 //                              changes value (rle: runs span burst boundaries, the last run is never flushed)
