@@ -90,11 +90,11 @@ def test_ook_decodes_known_packets_bit_exact(ctx, slicer_form):
     assert sum(len(x) for x in sent) == len(pk) > 16
 
 
-@pytest.fixture(params=["per_plan", "one_warp_per_stream", "split"])
+@pytest.fixture(params=["default", "one_warp_per_stream", "split"])
 def slicer_form(request, monkeypatch):
-    """the slicer has two forms with identical transition lists (k_ook.cu: ook_rle_kernel / ook_slice + scan + scatter); a plan picks
-    one by its streams per SM, LRC_OOK_KC forces one: the edge cases run through both"""
-    if request.param == "per_plan":
+    """the slicer has two forms with identical transition lists (k_ook.cu: ook_rle_kernel / ook_slice + scan + scatter); the split
+    form is the default, LRC_OOK_KC forces one or the other: the edge cases run through both (and through whatever the default is)"""
+    if request.param == "default":
         monkeypatch.delenv("LRC_OOK_KC", raising=False)
     else:
         monkeypatch.setenv("LRC_OOK_KC", "0" if request.param == "one_warp_per_stream" else "1")
